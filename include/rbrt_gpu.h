@@ -1,0 +1,224 @@
+/*
+ * rbrt_gpu.h — C-ABI boundary of the B200 path tracer that replaces rbrt_lib's hot path.
+ *
+ * rbrt (the reference, Rust) has no FFI today: the hot path sits behind the library call
+ *     pub fn render_scene(cam: Camera, num_samples: u32, scene: Scene) -> ImageBuffer<Rgb<u8>>
+ *                                                           (rbrt_lib/src/lib.rs:75-79)
+ * whose only caller is src/main.rs:82.  `Scene` holds type-erased `Box<dyn Intersectable>` /
+ * `Box<dyn RayScattering>` objects (rbrt_lib/src/scene.rs:12-16), so a GPU scene cannot be
+ * recovered from a built `Scene`; the boundary therefore hooks at the blueprint level
+ * (rbrt_lib/src/blueprints.rs:132 create_scene_from_scene_blueprint): plain-old-data sphere,
+ * mesh and material descriptions in, opaque scene handle out.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, never unwinds, returns
+ * 0 on success and a non-zero RBRT_E_* code on failure (message via rbrt_last_error()).
+ * The CPU oracle (oracle/rbrt_oracle.cpp) exports the same shapes under the prefix rbrt_ref_.
+ *
+ * One process drives one GPU (rbrt_gpu_init(device)); multi-GPU renders run one process per
+ * GPU, each rendering a shard selected by rbrt_render_opts.shard_*, and sum their
+ * accumulation buffers with one NCCL reduce (see rbrt_gpu_render_accum_device).
+ */
+#ifndef RBRT_GPU_H
+#define RBRT_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plain data mirrored from the reference ------------------------------------------ */
+
+/* = rbrt_lib::vec3::Vec3 (rbrt_lib/src/vec3.rs:6-10), 12 bytes */
+typedef struct rbrt_vec3 { float x, y, z; } rbrt_vec3;
+
+/* = rbrt_lib::ray::Ray (rbrt_lib/src/ray.rs:4-7), 24 bytes */
+typedef struct rbrt_ray { rbrt_vec3 origin, direction; } rbrt_ray;
+
+/* = rbrt_lib::cam::Camera, the 14 pub fields in declaration order (rbrt_lib/src/cam.rs:4-19) */
+typedef struct rbrt_camera {
+    float     hor_fov_rad;
+    uint32_t  img_width_pix;
+    float     img_height_mm;
+    float     vert_fov_rad;
+    uint32_t  img_height_pix;
+    float     img_width_mm;
+    rbrt_vec3 position;
+    float     focal_len_mm;
+    rbrt_vec3 look_at;
+    rbrt_vec3 up;
+    rbrt_vec3 right;
+    rbrt_vec3 img_center_point;
+    float     mm_per_pix_hor;
+    float     mm_per_pix_vert;
+} rbrt_camera;
+
+/* material kinds = the three RayScattering impls (lambertian.rs:6, metal.rs:6, dielectric.rs:6) */
+enum { RBRT_MAT_LAMBERTIAN = 0, RBRT_MAT_METAL = 1, RBRT_MAT_DIELECTRIC = 2 };
+
+/* albedo: Lambertian/Metal; param: Metal roughness or Dielectric ref_idx
+ * (blueprints.rs:50-74 create_material_from_description) */
+typedef struct rbrt_material { uint32_t kind; rbrt_vec3 albedo; float param; } rbrt_material;
+
+/* = rbrt_lib::sphere::Sphere (sphere.rs:6-10) */
+typedef struct rbrt_sphere_desc { rbrt_vec3 center; float radius; rbrt_material material; } rbrt_sphere_desc;
+
+/* = what TriangleMesh::new (mesh.rs:41-74) holds after load_mesh_vertices_from_file
+ * (mesh.rs:78-121): world-space triangle soup, 9 floats per triangle (v0 v1 v2), already
+ * scale -> rotate_point -> translate'd in f32.  One material per mesh (mesh.rs:24). */
+typedef struct rbrt_mesh_desc {
+    const float*  tri_vertices;   /* num_triangles * 9 floats, caller keeps ownership */
+    uint64_t      num_triangles;
+    rbrt_material material;
+} rbrt_mesh_desc;
+
+/* Result of one closest-hit query = what Scene::hit (scene.rs:19-43) returns, plus ids. */
+enum { RBRT_HIT_NONE = -1, RBRT_HIT_SPHERE = 0, RBRT_HIT_MESH = 1 };
+typedef struct rbrt_hit {
+    int32_t   kind;       /* RBRT_HIT_* */
+    uint32_t  elem_idx;   /* sphere index, or mesh index, in creation order */
+    uint32_t  tri_idx;    /* original triangle index inside the mesh (0 for spheres) */
+    float     t;          /* ray parameter */
+    float     dist;       /* dist_from_ray_orig (lib.rs:35) */
+    rbrt_vec3 point;      /* hit_point */
+    rbrt_vec3 normal;     /* hit_normal: unit for meshes, un-normalised for spheres (sphere.rs:56) */
+} rbrt_hit;
+
+/* ---- options -------------------------------------------------------------------------- */
+
+/* How triangle meshes are padded / truncated for SIMD.  The reference picks this at run time
+ * (mesh.rs:27-39 determine_num_vector_lanes); AVX (8) is the baseline build. */
+enum { RBRT_LANES_AVX = 8, RBRT_LANES_SSE = 4 };
+
+enum { RBRT_SHARD_NONE = 0, RBRT_SHARD_TILES = 1, RBRT_SHARD_SAMPLES = 2 };
+enum { RBRT_TRACE_BVH = 0, RBRT_TRACE_BRUTE = 1 };
+
+typedef struct rbrt_scene_opts {
+    uint32_t simd_lanes;     /* RBRT_LANES_*; 0 = 8 */
+    uint32_t leaf_size;      /* max triangles per BVH leaf; 0 = default */
+    float    box_pad_rel;    /* conservative padding of BVH boxes relative to the mesh extent; 0 = default (2e-5), <0 = none */
+    uint32_t reserved;
+} rbrt_scene_opts;
+
+typedef struct rbrt_render_opts {
+    uint64_t seed;           /* Philox key */
+    uint32_t max_depth;      /* 0 = 50 (lib.rs:99) */
+    uint32_t trace_mode;     /* RBRT_TRACE_* */
+    uint32_t shard_mode;     /* RBRT_SHARD_* */
+    uint32_t shard_rank;
+    uint32_t shard_count;    /* 0 or 1 = unsharded */
+    uint32_t batch_paths;    /* paths in flight per wavefront batch; 0 = default */
+    uint32_t integrator;     /* 0 = wavefront (default), 1 = persistent megakernel */
+    uint32_t reserved;
+} rbrt_render_opts;
+
+typedef struct rbrt_stats {
+    uint64_t rays;           /* closest-hit queries (= calls to Scene::hit): primary + bounces */
+    uint64_t paths;          /* samples rendered = pixels_in_shard * spp_in_shard */
+    uint64_t nan_rays;       /* rays the reference would have panicked on (sphere.rs:33) */
+    uint64_t node_visits;    /* BVH node visits (only when counters are compiled in / enabled) */
+    uint64_t tri_tests;
+    double   ms_total;       /* whole call, host clock */
+    double   ms_device;      /* device time of the render proper (CUDA events) */
+    double   ms_trace;       /* device time inside trace kernels (events, wavefront only) */
+    double   ms_h2d;
+    double   ms_d2h;
+    uint32_t launches;       /* kernels launched by this call */
+    uint32_t iterations;     /* wavefront bounce iterations executed */
+} rbrt_stats;
+
+typedef struct rbrt_scene_info {
+    uint32_t num_spheres, num_meshes;
+    uint64_t num_triangles;        /* real triangles handed in */
+    uint64_t num_triangles_tested; /* N_eff after the reference's SIMD tail rule */
+    uint64_t num_bvh_nodes;
+    uint64_t device_bytes;
+    double   ms_upload, ms_build;
+} rbrt_scene_info;
+
+typedef struct rbrt_scene rbrt_scene;   /* opaque */
+
+/* ---- error codes ---------------------------------------------------------------------- */
+enum {
+    RBRT_OK = 0,
+    RBRT_E_INVALID = 1,      /* bad argument */
+    RBRT_E_CUDA = 2,         /* CUDA runtime error */
+    RBRT_E_NODEVICE = 3,     /* no usable GPU: there is NO CPU fallback */
+    RBRT_E_ALLOC = 4
+};
+
+/* ---- host-side helpers (pure f32 arithmetic, no GPU) ------------------------------------ */
+
+/* = Camera::new(position, look_at, up, img_height_pix, img_width_pix, focal_len_mm)
+ *   (cam.rs:22-62).  NOTE the reference's argument order: height before width. */
+int rbrt_camera_new(rbrt_vec3 position, rbrt_vec3 look_at, rbrt_vec3 up,
+                    uint32_t img_height_pix, uint32_t img_width_pix, float focal_len_mm,
+                    rbrt_camera* out);
+
+/* = the per-vertex transform of load_mesh_vertices_from_file (mesh.rs:102-112):
+ *   v*scale -> Vec3::rotate_point(rotation) (vec3.rs:139-155) -> + translation, in place on
+ *   n_vertices xyz triples. */
+int rbrt_transform_vertices(float* xyz, uint64_t n_vertices, float scale,
+                            rbrt_vec3 rotation_rad, rbrt_vec3 translation);
+
+/* ---- GPU entry points ------------------------------------------------------------------- */
+
+/* Select the CUDA device this process renders on (one process per GPU). */
+int rbrt_gpu_init(int device);
+
+/* = create_scene_from_scene_blueprint (blueprints.rs:132-158) after material parsing: copies
+ *   the inputs to 16-byte-aligned SoA device buffers, applies the reference's SIMD tail rule
+ *   (mesh.rs:136-144 + triangle.rs:167), computes edges / unit normals / exact mesh AABB
+ *   (mesh.rs:50-61, triangle.rs:30-34, aabbox.rs:62-88) and builds one LBVH per mesh on the GPU.
+ *   opts may be NULL. */
+int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t num_spheres,
+                          const rbrt_mesh_desc* meshes, uint32_t num_meshes,
+                          const rbrt_scene_opts* opts, rbrt_scene** out);
+int rbrt_gpu_scene_info(const rbrt_scene* scene, rbrt_scene_info* out);
+int rbrt_gpu_scene_destroy(rbrt_scene* scene);
+
+/* = render_scene (lib.rs:75-124).  rgb_out: caller-allocated W*H*3 bytes, row-major RGB8 =
+ *   the layout of image::ImageBuffer<Rgb<u8>>.  opts / stats may be NULL.  HOST pointers. */
+int rbrt_gpu_render(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t num_samples,
+                    const rbrt_render_opts* opts, uint8_t* rgb_out, rbrt_stats* stats);
+
+/* Same render, but returns the pre-gamma mean colour (`color * (1.0/spp)`, lib.rs:101) as
+ * W*H*3 f32, row-major.  HOST pointer. */
+int rbrt_gpu_render_hdr(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t num_samples,
+                        const rbrt_render_opts* opts, float* rgb_f32_out, rbrt_stats* stats);
+
+/* Multi-GPU building block: renders this rank's shard and leaves the per-pixel SUM over its
+ * samples (lib.rs:95-100, before the 1/spp scale) in a DEVICE buffer of W*H*4 f32 (rgb + pad),
+ * zero outside the shard, on the given CUDA stream (0 = default stream).  Ranks then sum these
+ * buffers (NCCL reduce) and rank 0 calls rbrt_gpu_finalize_device. */
+int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam,
+                                 uint32_t num_samples, const rbrt_render_opts* opts,
+                                 void* d_accum_rgba_f32, void* cuda_stream, rbrt_stats* stats);
+
+/* = lib.rs:101 + lib.rs:116-122: colour *= 1/spp; (sqrt(c)*256) as u8 (saturating).
+ *   d_rgb_u8 (W*H*3) and d_hdr_f32 (W*H*3) are DEVICE pointers; either may be NULL. */
+int rbrt_gpu_finalize_device(const void* d_accum_rgba_f32, uint32_t width, uint32_t height,
+                             uint32_t num_samples, void* d_rgb_u8, void* d_hdr_f32,
+                             void* cuda_stream);
+
+/* Parity hook = Scene::hit (scene.rs:19-43) for caller-supplied rays; the reference's nearest
+ * public analogue is do_intersection_soa (mesh.rs:183-190).  HOST pointers.
+ * trace_mode: RBRT_TRACE_BVH or RBRT_TRACE_BRUTE (every triangle, the reference's own loop). */
+int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t n,
+                        uint32_t trace_mode, rbrt_hit* hits_out, rbrt_stats* stats);
+
+/* Primary rays exactly as the renderer generates them (cam.rs:64-82 with the Philox stream of
+ * sample `sample_idx`), one per pixel, row-major.  HOST pointer, W*H rays. */
+int rbrt_gpu_primary_rays(const rbrt_camera* cam, uint64_t seed, uint32_t sample_idx,
+                          rbrt_ray* rays_out);
+
+/* Thread-local message of the last failing call on this thread. */
+const char* rbrt_last_error(void);
+
+/* Library identification: "rbrt_b200 <version> sm_100a". */
+const char* rbrt_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBRT_GPU_H */

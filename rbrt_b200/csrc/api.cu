@@ -1,0 +1,337 @@
+// api.cu — the C-ABI of include/rbrt_gpu.h: scene upload (+LBVH build) and the render entry points.
+// There is NO CPU fallback: without a usable CUDA device every GPU entry point fails with
+// RBRT_E_NODEVICE / RBRT_E_CUDA and a message.
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "bvh_build.cuh"
+#include "engine.cuh"
+
+namespace rbrt {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    cudaGetLastError();
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RBRT_E_NODEVICE : RBRT_E_CUDA;
+}
+static int g_device = -1;
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#define CKA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
+
+static int ensure_device() {
+    if (g_device >= 0) { CKA(cudaSetDevice(g_device)); return RBRT_OK; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); rbrt_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return RBRT_E_NODEVICE;
+    }
+    g_device = 0;
+    CKA(cudaSetDevice(0));
+    return RBRT_OK;
+}
+
+template <typename T>
+static int dev_alloc(Scene* sc, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    sc->allocs.push_back(q);
+    sc->info.device_bytes += count * sizeof(T);
+    *p = (T*)q;
+    return RBRT_OK;
+}
+
+static void destroy_scene(Scene* sc) {
+    if (!sc) return;
+    free_wave_buffers(sc->wb);
+    for (void* p : sc->allocs) cudaFree(p);
+    delete sc;
+}
+
+// N_eff of the reference's SIMD sweep: padding appends N % lanes copies (mesh.rs:136-144) and the
+// sweep runs chunks_exact(lanes) (triangle.rs:167,296), so the last N % lanes triangles are never
+// tested when 2*(N % lanes) < lanes.
+static uint64_t tested_triangles(uint64_t n, uint32_t lanes) {
+    uint64_t r = n % lanes, total = n + r, tested = (total / lanes) * lanes;
+    return tested < n ? tested : n;
+}
+
+}  // namespace rbrt
+
+using namespace rbrt;
+
+extern "C" {
+
+const char* rbrt_last_error(void) { return g_err; }
+const char* rbrt_gpu_version(void) { return "rbrt_b200 0.1.0 sm_100a"; }
+
+int rbrt_gpu_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); rbrt_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return RBRT_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return RBRT_E_INVALID; }
+    CKA(cudaSetDevice(device));
+    g_device = device;
+    return RBRT_OK;
+}
+
+int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rbrt_mesh_desc* meshes, uint32_t nm,
+                          const rbrt_scene_opts* opts, rbrt_scene** out) {
+    if (!out || (ns && !spheres) || (nm && !meshes)) { set_error("null argument"); return RBRT_E_INVALID; }
+    *out = nullptr;
+    uint32_t lanes = (opts && opts->simd_lanes) ? opts->simd_lanes : 8;
+    if (lanes != 8 && lanes != 4) { set_error("simd_lanes must be 8 (AVX) or 4 (SSE)"); return RBRT_E_INVALID; }
+    uint32_t leaf_size = (opts && opts->leaf_size) ? opts->leaf_size : 4;
+    if (leaf_size > 8) { set_error("leaf_size must be <= 8"); return RBRT_E_INVALID; }
+    float pad_rel = 2e-5f;
+    if (opts && opts->box_pad_rel > 0.0f) pad_rel = opts->box_pad_rel;
+    else if (opts && opts->box_pad_rel < 0.0f) pad_rel = 0.0f;
+    if ((uint64_t)ns + nm > 65535) { set_error("more than 65535 scene elements"); return RBRT_E_INVALID; }
+    for (uint32_t i = 0; i < ns; ++i) if (spheres[i].material.kind > 2) { set_error("sphere %u: unknown material kind", i); return RBRT_E_INVALID; }
+    uint64_t total_tris = 0, total_eff = 0;
+    for (uint32_t i = 0; i < nm; ++i) {
+        if (meshes[i].material.kind > 2) { set_error("mesh %u: unknown material kind", i); return RBRT_E_INVALID; }
+        if (meshes[i].num_triangles && !meshes[i].tri_vertices) { set_error("mesh %u: null tri_vertices", i); return RBRT_E_INVALID; }
+        if (meshes[i].num_triangles > (1ull << 28)) { set_error("mesh %u: more than 2^28 triangles", i); return RBRT_E_INVALID; }
+        total_tris += meshes[i].num_triangles;
+        total_eff += tested_triangles(meshes[i].num_triangles, lanes);
+    }
+    if (total_eff > (1ull << 28)) { set_error("more than 2^28 triangles in the scene"); return RBRT_E_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+
+    Scene* sc = new Scene();
+    sc->device = g_device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, g_device);
+    if (e != cudaSuccess) { destroy_scene(sc); return cuda_fail(e, "cudaGetDeviceProperties"); }
+    sc->sm_count = prop.multiProcessorCount;
+    sc->info.num_spheres = ns; sc->info.num_meshes = nm;
+    sc->info.num_triangles = total_tris; sc->info.num_triangles_tested = total_eff;
+    double t0 = now_ms();
+
+#define CKS(x) do { int rc_ = (x); if (rc_) { destroy_scene(sc); return rc_; } } while (0)
+#define CKSC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { int rc_ = cuda_fail(e_, #x); destroy_scene(sc); return rc_; } } while (0)
+
+    // ---- elements: spheres + per-element materials (flattened SoA, 16-byte records)
+    std::vector<float4> sph(ns), mat(ns + nm);
+    std::vector<uint32_t> kind(ns + nm);
+    for (uint32_t i = 0; i < ns; ++i) {
+        sph[i] = make_float4(spheres[i].center.x, spheres[i].center.y, spheres[i].center.z, spheres[i].radius);
+        mat[i] = make_float4(spheres[i].material.albedo.x, spheres[i].material.albedo.y, spheres[i].material.albedo.z, spheres[i].material.param);
+        kind[i] = spheres[i].material.kind;
+    }
+    for (uint32_t i = 0; i < nm; ++i) {
+        mat[ns + i] = make_float4(meshes[i].material.albedo.x, meshes[i].material.albedo.y, meshes[i].material.albedo.z, meshes[i].material.param);
+        kind[ns + i] = meshes[i].material.kind;
+    }
+    float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals; uint32_t* d_kind; MeshDev* d_meshes;
+    CKS(dev_alloc(sc, &d_sph, ns)); CKS(dev_alloc(sc, &d_mat, ns + nm)); CKS(dev_alloc(sc, &d_kind, ns + nm));
+    CKS(dev_alloc(sc, &d_tris, 3 * total_eff)); CKS(dev_alloc(sc, &d_nodes, 4 * total_eff)); CKS(dev_alloc(sc, &d_normals, total_eff));
+    CKS(dev_alloc(sc, &d_meshes, nm));
+    if (ns) CKSC(cudaMemcpy(d_sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
+    if (ns + nm) {
+        CKSC(cudaMemcpy(d_mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice));
+        CKSC(cudaMemcpy(d_kind, kind.data(), 4ull * (ns + nm), cudaMemcpyHostToDevice));
+    }
+
+    // ---- meshes: exact AABB on the host (aabbox.rs:62-88, over ALL real triangles), then upload + LBVH
+    double ms_upload = 0, ms_build = 0;
+    uint64_t tri_off = 0, live_total = 0;
+    sc->meshes_h.resize(nm);
+    for (uint32_t i = 0; i < nm; ++i) {
+        const rbrt_mesh_desc& m = meshes[i];
+        MeshDev md; memset(&md, 0, sizeof(md));
+        float lo[3] = {3.40282347e+38f, 3.40282347e+38f, 3.40282347e+38f}, hi[3] = {-3.40282347e+38f, -3.40282347e+38f, -3.40282347e+38f};
+        for (uint64_t v = 0; v < m.num_triangles * 3; ++v)
+            for (int k = 0; k < 3; ++k) {
+                float x = m.tri_vertices[3 * v + k];
+                if (x < lo[k]) lo[k] = x;
+                if (x > hi[k]) hi[k] = x;
+            }
+        uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
+        for (int k = 0; k < 3; ++k) { md.lo[k] = lo[k]; md.hi[k] = hi[k]; }
+        md.tri_base = (uint32_t)tri_off; md.n_tris = (uint32_t)n_eff; md.node_base = (uint32_t)tri_off;
+        md.nrm_base = (uint32_t)tri_off; md.elem = ns + i; md.root_ref = make_leaf_ref(0, 1);
+        if (n_eff) {
+            double t1 = now_ms();
+            float* d_raw = nullptr;
+            CKSC(cudaMalloc(&d_raw, 36ull * n_eff));
+            cudaError_t ce = cudaMemcpy(d_raw, m.tri_vertices, 36ull * n_eff, cudaMemcpyHostToDevice);
+            double t2 = now_ms();
+            float mx = 0.0f;
+            for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]); }
+            float pad = pad_rel * mx;
+            uint64_t live = 0; int height = 0;
+            if (ce == cudaSuccess)
+                ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, d_tris + 3 * tri_off, d_normals + tri_off,
+                                    d_nodes + 4 * tri_off, &md.root_ref, &live, &height, 0);
+            cudaFree(d_raw);
+            if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
+            if (height + 2 > 96) { set_error("mesh %u: BVH height %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
+            live_total += live;
+            ms_upload += t2 - t1; ms_build += now_ms() - t2;
+        }
+        sc->meshes_h[i] = md;
+        tri_off += n_eff;
+    }
+    if (nm) CKSC(cudaMemcpy(d_meshes, sc->meshes_h.data(), sizeof(MeshDev) * nm, cudaMemcpyHostToDevice));
+    CKSC(cudaDeviceSynchronize());
+    sc->dev.spheres = d_sph; sc->dev.tris = d_tris; sc->dev.nodes = d_nodes; sc->dev.normals = d_normals;
+    sc->dev.mat = d_mat; sc->dev.mat_kind = d_kind; sc->dev.meshes = d_meshes; sc->dev.n_spheres = ns; sc->dev.n_meshes = nm;
+    sc->info.num_bvh_nodes = live_total;
+    sc->info.ms_upload = ms_upload + (now_ms() - t0 - ms_upload - ms_build);
+    sc->info.ms_build = ms_build;
+    *out = reinterpret_cast<rbrt_scene*>(sc);
+    return RBRT_OK;
+#undef CKS
+#undef CKSC
+}
+
+int rbrt_gpu_scene_info(const rbrt_scene* scene, rbrt_scene_info* out) {
+    if (!scene || !out) { set_error("null argument"); return RBRT_E_INVALID; }
+    *out = reinterpret_cast<const Scene*>(scene)->info;
+    return RBRT_OK;
+}
+
+int rbrt_gpu_scene_destroy(rbrt_scene* scene) {
+    if (!scene) return RBRT_OK;
+    Scene* sc = reinterpret_cast<Scene*>(scene);
+    cudaSetDevice(sc->device);
+    destroy_scene(sc);
+    return RBRT_OK;
+}
+
+int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
+                                 void* d_accum, void* stream, rbrt_stats* stats) {
+    if (!scene || !cam || !d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    CKA(cudaSetDevice(sc.device));
+    double t0 = now_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    int rc = render_accum(sc, *cam, spp, opts, (float4*)d_accum, (cudaStream_t)stream, stats);
+    if (rc) return rc;
+    if (stats) stats->ms_total = now_ms() - t0;
+    return RBRT_OK;
+}
+
+int rbrt_gpu_finalize_device(const void* d_accum, uint32_t W, uint32_t H, uint32_t spp, void* d_rgb, void* d_hdr, void* stream) {
+    if (!d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    return finalize((const float4*)d_accum, W, H, spp, (uint8_t*)d_rgb, (float*)d_hdr, (cudaStream_t)stream);
+}
+
+static int render_host(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
+                       uint8_t* rgb_out, float* hdr_out, rbrt_stats* stats) {
+    if (!scene || !cam || (!rgb_out && !hdr_out)) { set_error("null argument"); return RBRT_E_INVALID; }
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    CKA(cudaSetDevice(sc.device));
+    double t0 = now_ms();
+    size_t n = (size_t)cam->img_width_pix * cam->img_height_pix;
+    if (!n || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
+    WaveBuffers& wb = sc.wb;
+    if (wb.accum_px < n) { cudaFree(wb.accum); wb.accum = nullptr; wb.accum_px = 0; CKA(cudaMalloc(&wb.accum, 16 * n)); wb.accum_px = n; }
+    if (wb.out_px < n) {
+        cudaFree(wb.rgb); cudaFree(wb.hdr); wb.rgb = nullptr; wb.hdr = nullptr; wb.out_px = 0;
+        CKA(cudaMalloc(&wb.rgb, 3 * n)); CKA(cudaMalloc(&wb.hdr, 12 * n)); wb.out_px = n;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    rbrt_stats local; memset(&local, 0, sizeof(local));
+    int rc = render_accum(sc, *cam, spp, opts, wb.accum, 0, &local);
+    if (rc) return rc;
+    rc = finalize(wb.accum, cam->img_width_pix, cam->img_height_pix, spp, rgb_out ? wb.rgb : nullptr, hdr_out ? wb.hdr : nullptr, 0);
+    if (rc) return rc;
+    double t1 = now_ms();
+    if (rgb_out) CKA(cudaMemcpy(rgb_out, wb.rgb, 3 * n, cudaMemcpyDeviceToHost));
+    if (hdr_out) CKA(cudaMemcpy(hdr_out, wb.hdr, 12 * n, cudaMemcpyDeviceToHost));
+    double t2 = now_ms();
+    if (stats) { *stats = local; stats->ms_d2h = t2 - t1; stats->ms_total = t2 - t0; stats->launches += 1; }
+    return RBRT_OK;
+}
+
+int rbrt_gpu_render(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
+                    uint8_t* rgb_out, rbrt_stats* stats) {
+    if (!rgb_out) { set_error("null rgb_out"); return RBRT_E_INVALID; }
+    return render_host(scene, cam, spp, opts, rgb_out, nullptr, stats);
+}
+
+int rbrt_gpu_render_hdr(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
+                        float* hdr_out, rbrt_stats* stats) {
+    if (!hdr_out) { set_error("null rgb_f32_out"); return RBRT_E_INVALID; }
+    return render_host(scene, cam, spp, opts, nullptr, hdr_out, stats);
+}
+
+int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t n, uint32_t mode, rbrt_hit* hits, rbrt_stats* stats) {
+    if (!scene || (n && (!rays || !hits))) { set_error("null argument"); return RBRT_E_INVALID; }
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    CKA(cudaSetDevice(sc.device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!n) return RBRT_OK;
+    double t0 = now_ms();
+    rbrt_ray* d_rays = nullptr; rbrt_hit* d_hits = nullptr; unsigned long long* d_stats = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = RBRT_OK;
+    cudaError_t ce;
+#define CKT(x) do { ce = (x); if (ce != cudaSuccess) { rc = cuda_fail(ce, #x); goto done; } } while (0)
+    CKT(cudaMalloc(&d_rays, sizeof(rbrt_ray) * n)); CKT(cudaMalloc(&d_hits, sizeof(rbrt_hit) * n));
+    CKT(cudaMalloc(&d_stats, 8 * ST_COUNT)); CKT(cudaMemset(d_stats, 0, 8 * ST_COUNT));
+    CKT(cudaEventCreate(&e0)); CKT(cudaEventCreate(&e1));
+    {
+        double t1 = now_ms();
+        CKT(cudaMemcpy(d_rays, rays, sizeof(rbrt_ray) * n, cudaMemcpyHostToDevice));
+        double t2 = now_ms();
+        CKT(cudaEventRecord(e0, 0));
+        rc = trace_rays_device(sc, d_rays, n, mode, d_hits, stats ? d_stats : nullptr, 0);
+        if (rc) goto done;
+        CKT(cudaEventRecord(e1, 0));
+        CKT(cudaEventSynchronize(e1));
+        double t3 = now_ms();
+        CKT(cudaMemcpy(hits, d_hits, sizeof(rbrt_hit) * n, cudaMemcpyDeviceToHost));
+        double t4 = now_ms();
+        if (stats) {
+            unsigned long long h[ST_COUNT];
+            CKT(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+            float ms = 0; CKT(cudaEventElapsedTime(&ms, e0, e1));
+            stats->rays = n; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS];
+            stats->ms_device = ms; stats->ms_trace = ms; stats->ms_h2d = t2 - t1; stats->ms_d2h = t4 - t3; stats->launches = 1;
+            stats->ms_total = now_ms() - t0;
+        }
+    }
+done:
+#undef CKT
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_stats);
+    return rc;
+}
+
+int rbrt_gpu_primary_rays(const rbrt_camera* cam, uint64_t seed, uint32_t sample, rbrt_ray* rays_out) {
+    if (!cam || !rays_out) { set_error("null argument"); return RBRT_E_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    size_t n = (size_t)cam->img_width_pix * cam->img_height_pix;
+    if (!n) return RBRT_OK;
+    rbrt_ray* d = nullptr;
+    CKA(cudaMalloc(&d, sizeof(rbrt_ray) * n));
+    rc = primary_rays_device(*cam, seed, sample, d, 0);
+    if (!rc) { cudaError_t e = cudaMemcpy(rays_out, d, sizeof(rbrt_ray) * n, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy"); }
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// bvh_build.cu — scene upload kernels + GPU LBVH build (north_star (1),(2)).
+//
+// Replaces the reference's per-mesh SoA conversion (mesh.rs:41-74,123-181): per triangle
+// e1 = v1-v0, e2 = v2-v0 (mesh.rs:57-60) and the unit geometric normal normalize(cross(e1,e2))
+// (triangle.rs:30-34) are computed with the same individually rounded f32 ops, then the
+// triangles are put in Morton order and a binary LBVH is built over them:
+//   63-bit Morton code of the triangle-box centre -> radix sort (CUB) -> Karras 2012 topology
+//   -> bottom-up AABB refit with atomic arrival flags -> emission of 64-byte traversal nodes with
+//   subtrees of <= leaf_size triangles collapsed into leaves.
+#include "bvh_build.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace rbrt {
+
+// ------------------------------------------------------------------ per-triangle preparation
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {   // spread the low 21 bits, 2 zero bits between
+    uint64_t x = v & 0x1FFFFFu;
+    x = (x | x << 32) & 0x1F00000000FFFFull;
+    x = (x | x << 16) & 0x1F0000FF0000FFull;
+    x = (x | x << 8) & 0x100F00F00F00F00Full;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_prepare(const float* __restrict__ raw, uint32_t n, float3 lo, float3 inv_ext,
+                          float4* __restrict__ normals, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = raw + 9 * (size_t)i;
+    f3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
+    f3 e1 = b - a, e2 = c - a;
+    f3 nn = norm3(cross3(e1, e2));                                        // triangle.rs:30-34
+    normals[i] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+    float cx = 0.5f * (fminf(a.x, fminf(b.x, c.x)) + fmaxf(a.x, fmaxf(b.x, c.x)));
+    float cy = 0.5f * (fminf(a.y, fminf(b.y, c.y)) + fmaxf(a.y, fmaxf(b.y, c.y)));
+    float cz = 0.5f * (fminf(a.z, fminf(b.z, c.z)) + fmaxf(a.z, fmaxf(b.z, c.z)));
+    float fx = fminf(fmaxf((cx - lo.x) * inv_ext.x, 0.0f), 1.0f);
+    float fy = fminf(fmaxf((cy - lo.y) * inv_ext.y, 0.0f), 1.0f);
+    float fz = fminf(fmaxf((cz - lo.z) * inv_ext.z, 0.0f), 1.0f);
+    uint32_t qx = min((uint32_t)(fx * 2097152.0f), 2097151u);
+    uint32_t qy = min((uint32_t)(fy * 2097152.0f), 2097151u);
+    uint32_t qz = min((uint32_t)(fz * 2097152.0f), 2097151u);
+    keys[i] = (expand21(qx) << 2) | (expand21(qy) << 1) | expand21(qz);
+    vals[i] = i;
+}
+
+// sorted position p -> triangle record {v0|orig, e1, e2} and padded leaf box
+__global__ void k_emit_tris(const float* __restrict__ raw, const uint32_t* __restrict__ order, uint32_t n, float pad,
+                            float4* __restrict__ tris, float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t orig = order[p];
+    const float* t = raw + 9 * (size_t)orig;
+    f3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
+    f3 e1 = b - a, e2 = c - a;                                            // mesh.rs:57-60
+    tris[3 * (size_t)p] = make_float4(a.x, a.y, a.z, __uint_as_float(orig));
+    tris[3 * (size_t)p + 1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+    tris[3 * (size_t)p + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+    leaf_lo[p] = make_float4(fminf(a.x, fminf(b.x, c.x)) - pad, fminf(a.y, fminf(b.y, c.y)) - pad, fminf(a.z, fminf(b.z, c.z)) - pad, 0.0f);
+    leaf_hi[p] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)) + pad, fmaxf(a.y, fmaxf(b.y, c.y)) + pad, fmaxf(a.z, fmaxf(b.z, c.z)) + pad, 0.0f);
+}
+
+// ------------------------------------------------------------------ Karras 2012
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);                                 // tie-break on position
+    return __clzll((long long)(a ^ b));
+}
+
+// child reference inside the build: >= 0 internal node, < 0 -> ~leaf position
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children, int2* __restrict__ range,
+                         int* __restrict__ parent_int, int* __restrict__ parent_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    int left = (first == gamma) ? ~gamma : gamma;
+    int right = (last == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    range[i] = make_int2(first, last);
+    if (left >= 0) parent_int[left] = i; else parent_leaf[~left] = i;
+    if (right >= 0) parent_int[right] = i; else parent_leaf[~right] = i;
+    if (i == 0) parent_int[0] = -1;
+}
+
+// bottom-up refit: the second thread to arrive at a node merges its children (Karras 2012 §4)
+__global__ void k_refit(int n, const int2* __restrict__ children, const int* __restrict__ parent_int,
+                        const int* __restrict__ parent_leaf, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                        float4* __restrict__ node_lo, float4* __restrict__ node_hi, int* __restrict__ flags, int* __restrict__ height) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int cur = parent_leaf[p];
+    while (cur >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1) == 0) return;
+        __threadfence();
+        int2 ch = children[cur];
+        volatile const float4* nl = node_lo; volatile const float4* nh = node_hi;
+        float lx, ly, lz, hx, hy, hz; int hl, hr;
+        if (ch.x >= 0) { lx = nl[ch.x].x; ly = nl[ch.x].y; lz = nl[ch.x].z; hx = nh[ch.x].x; hy = nh[ch.x].y; hz = nh[ch.x].z; hl = ((volatile int*)height)[ch.x]; }
+        else { float4 a = leaf_lo[~ch.x], b = leaf_hi[~ch.x]; lx = a.x; ly = a.y; lz = a.z; hx = b.x; hy = b.y; hz = b.z; hl = 0; }
+        float rlx, rly, rlz, rhx, rhy, rhz;
+        if (ch.y >= 0) { rlx = nl[ch.y].x; rly = nl[ch.y].y; rlz = nl[ch.y].z; rhx = nh[ch.y].x; rhy = nh[ch.y].y; rhz = nh[ch.y].z; hr = ((volatile int*)height)[ch.y]; }
+        else { float4 a = leaf_lo[~ch.y], b = leaf_hi[~ch.y]; rlx = a.x; rly = a.y; rlz = a.z; rhx = b.x; rhy = b.y; rhz = b.z; hr = 0; }
+        node_lo[cur] = make_float4(fminf(lx, rlx), fminf(ly, rly), fminf(lz, rlz), 0.0f);
+        node_hi[cur] = make_float4(fmaxf(hx, rhx), fmaxf(hy, rhy), fmaxf(hz, rhz), 0.0f);
+        height[cur] = max(hl, hr) + 1;
+        cur = parent_int[cur];
+    }
+}
+
+// traversal node emission with leaf collapse
+__global__ void k_emit_nodes(int n, uint32_t leaf_size, const int2* __restrict__ children, const int2* __restrict__ range,
+                             const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                             const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                             float4* __restrict__ out, unsigned long long* __restrict__ live) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int2 rg = range[i];
+    uint32_t cnt = (uint32_t)(rg.y - rg.x + 1);
+    if (i != 0 && cnt <= leaf_size) {                                     // swallowed by an ancestor's leaf
+        out[4 * (size_t)i] = out[4 * (size_t)i + 1] = out[4 * (size_t)i + 2] = out[4 * (size_t)i + 3] = make_float4(0, 0, 0, 0);
+        return;
+    }
+    atomicAdd(live, 1ull);
+    int2 ch = children[i];
+    float4 lo[2], hi[2]; int32_t ref[2];
+    int c[2] = {ch.x, ch.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (c[k] < 0) { lo[k] = leaf_lo[~c[k]]; hi[k] = leaf_hi[~c[k]]; ref[k] = make_leaf_ref((uint32_t)(~c[k]), 1); }
+        else {
+            lo[k] = node_lo[c[k]]; hi[k] = node_hi[c[k]];
+            int2 r = range[c[k]];
+            uint32_t cc = (uint32_t)(r.y - r.x + 1);
+            ref[k] = cc <= leaf_size ? make_leaf_ref((uint32_t)r.x, cc) : c[k];
+        }
+    }
+    out[4 * (size_t)i] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+    out[4 * (size_t)i + 1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+    out[4 * (size_t)i + 2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+    out[4 * (size_t)i + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.0f, 0.0f);
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size,
+                           float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
+                           int* tree_height, cudaStream_t st) {
+    *live_nodes = 0; *tree_height = 0;
+    if (n == 0) { *root_ref = make_leaf_ref(0, 1); return cudaSuccess; }
+    const int B = 256;
+    uint32_t g = (n + B - 1) / B;
+    uint64_t *keys = nullptr, *keys_s = nullptr; uint32_t *vals = nullptr, *vals_s = nullptr;
+    float4 *leaf_lo = nullptr, *leaf_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
+    int2 *children = nullptr, *range = nullptr; int *parent_int = nullptr, *parent_leaf = nullptr, *flags = nullptr, *height = nullptr;
+    unsigned long long* d_live = nullptr; void* tmp = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto cleanup = [&]() {
+        cudaFree(keys); cudaFree(keys_s); cudaFree(vals); cudaFree(vals_s); cudaFree(leaf_lo); cudaFree(leaf_hi);
+        cudaFree(node_lo); cudaFree(node_hi); cudaFree(children); cudaFree(range); cudaFree(parent_int);
+        cudaFree(parent_leaf); cudaFree(flags); cudaFree(height); cudaFree(d_live); cudaFree(tmp);
+    };
+#define CKC(x) do { err = (x); if (err != cudaSuccess) { cleanup(); return err; } } while (0)
+    CKC(cudaMalloc(&keys, 8ull * n)); CKC(cudaMalloc(&keys_s, 8ull * n));
+    CKC(cudaMalloc(&vals, 4ull * n)); CKC(cudaMalloc(&vals_s, 4ull * n));
+    CKC(cudaMalloc(&leaf_lo, 16ull * n)); CKC(cudaMalloc(&leaf_hi, 16ull * n));
+    float3 flo = make_float3(lo[0], lo[1], lo[2]);
+    float3 inv = make_float3(hi[0] > lo[0] ? 1.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1.0f / (hi[1] - lo[1]) : 0.0f,
+                             hi[2] > lo[2] ? 1.0f / (hi[2] - lo[2]) : 0.0f);
+    k_prepare<<<g, B, 0, st>>>(d_raw, n, flo, inv, d_normals, keys, vals);
+    CKC(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
+    CKC(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    CKC(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
+    k_emit_tris<<<g, B, 0, st>>>(d_raw, vals_s, n, pad, d_tris, leaf_lo, leaf_hi);
+    CKC(cudaGetLastError());
+    if (n <= leaf_size || n == 1) {
+        *root_ref = make_leaf_ref(0, n);
+        CKC(cudaStreamSynchronize(st));
+        cleanup();
+        return cudaSuccess;
+    }
+    uint32_t ni = n - 1;
+    CKC(cudaMalloc(&node_lo, 16ull * ni)); CKC(cudaMalloc(&node_hi, 16ull * ni));
+    CKC(cudaMalloc(&children, 8ull * ni)); CKC(cudaMalloc(&range, 8ull * ni));
+    CKC(cudaMalloc(&parent_int, 4ull * ni)); CKC(cudaMalloc(&parent_leaf, 4ull * n));
+    CKC(cudaMalloc(&flags, 4ull * ni)); CKC(cudaMalloc(&height, 4ull * ni)); CKC(cudaMalloc(&d_live, 8));
+    CKC(cudaMemsetAsync(flags, 0, 4ull * ni, st)); CKC(cudaMemsetAsync(d_live, 0, 8, st));
+    k_karras<<<(ni + B - 1) / B, B, 0, st>>>(keys_s, (int)n, children, range, parent_int, parent_leaf);
+    CKC(cudaGetLastError());
+    k_refit<<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+    CKC(cudaGetLastError());
+    k_emit_nodes<<<(ni + B - 1) / B, B, 0, st>>>((int)n, leaf_size, children, range, leaf_lo, leaf_hi, node_lo, node_hi, d_nodes, d_live);
+    CKC(cudaGetLastError());
+    unsigned long long live = 0; int h = 0;
+    CKC(cudaMemcpyAsync(&live, d_live, 8, cudaMemcpyDeviceToHost, st));
+    CKC(cudaMemcpyAsync(&h, height, 4, cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    *live_nodes = live; *tree_height = h; *root_ref = 0;
+    cleanup();
+    return cudaSuccess;
+#undef CKC
+}
+
+}  // namespace rbrt

@@ -1,0 +1,77 @@
+// engine.cuh — host-side objects behind the opaque rbrt_scene handle and the wavefront state.
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/rbrt_gpu.h"
+#include "common.cuh"
+
+namespace rbrt {
+
+// Per-iteration queue counters.  All iterations of a batch get their own slot, so one memset per
+// batch resets everything and no kernel ever has to reset a counter another kernel still reads.
+struct IterCtr {
+    uint32_t ray_count;      // rays in the queue traced at this iteration (written by generate / shade of it-1)
+    uint32_t ray_head;       // persistent-thread work cursor of the trace kernel
+    uint32_t mat_count[3];   // hits appended per material kind by the trace kernel
+    uint32_t shade_head;     // persistent-thread work cursor of the shade kernel
+    uint32_t pad[2];
+};
+
+enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_COUNT = 4 };
+
+struct WaveBuffers {
+    uint32_t cap = 0;            // paths per batch the buffers hold
+    uint32_t depth_cap = 0;      // bounce iterations the history/counter arrays hold
+    float4* q_o[2] = {nullptr, nullptr};   // ray queue: {origin.xyz, bits(path id)}
+    float4* q_d[2] = {nullptr, nullptr};   //            {direction.xyz, 0}
+    uint4* hit = nullptr;        // per queue slot: {bits(t), element, triangle, kind}
+    uint32_t* matq[3] = {nullptr, nullptr, nullptr};   // queue slots grouped by material kind
+    float4* out = nullptr;       // per path: final radiance (zero-initialised per batch)
+    uint16_t* hist = nullptr;    // [iteration][path]: element scattered at, for the attenuation product
+    IterCtr* ctr = nullptr;      // [depth_cap + 2]
+    unsigned long long* stats = nullptr;   // ST_COUNT counters
+    float4* accum = nullptr;     // internal W*H accumulation buffer for the host-pointer entry points
+    size_t accum_px = 0;
+    uint8_t* rgb = nullptr; float* hdr = nullptr; size_t out_px = 0;
+    size_t bytes = 0;
+};
+
+struct Scene {
+    int device = 0;
+    SceneDev dev{};
+    std::vector<MeshDev> meshes_h;
+    std::vector<void*> allocs;   // every cudaMalloc owned by the scene
+    rbrt_scene_info info{};
+    mutable WaveBuffers wb;      // lazily sized by the first render (handle is single-threaded)
+    int sm_count = 148;
+};
+
+// Everything a wavefront kernel needs, passed by value (kernel parameter space).
+struct WaveParams {
+    SceneDev S;
+    CamDev cam;
+    ShardDev sh;
+    uint32_t key0, key1;
+    uint32_t cap;            // queue capacity = paths of a full batch
+    uint32_t paths_px;       // P_r = tiles_mine * 32: path id = s_local * paths_px + j
+    uint32_t s_base;         // first sample index of this batch
+    uint32_t s_count;        // samples in this batch
+    uint32_t max_depth;      // 50 (lib.rs:99)
+    float4* q_o[2]; float4* q_d[2];
+    uint4* hit; uint32_t* matq[3];
+    float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;
+};
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+// render.cu
+int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rbrt_render_opts* opts,
+                 float4* d_accum, cudaStream_t st, rbrt_stats* stats);
+int finalize(const float4* d_accum, uint32_t W, uint32_t H, uint32_t spp, uint8_t* d_rgb, float* d_hdr, cudaStream_t st);
+int trace_rays_device(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, uint32_t mode, rbrt_hit* d_hits,
+                      unsigned long long* d_stats, cudaStream_t st);
+int primary_rays_device(const rbrt_camera& cam, uint64_t seed, uint32_t sample, rbrt_ray* d_rays, cudaStream_t st);
+void free_wave_buffers(WaveBuffers& wb);
+
+}  // namespace rbrt

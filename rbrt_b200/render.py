@@ -1,0 +1,80 @@
+"""render_scene — host mirror of rbrt_lib::render_scene (lib.rs:75-124) over the C-ABI.
+
+`render_scene(cam, num_samples, scene)` is the call a user of rbrt makes (main.rs:82); it returns an
+ImageBuffer (RGB8, row-major, `.save(path)`), like `image::ImageBuffer<Rgb<u8>, Vec<u8>>`.
+All buffers that cross this call are HOST buffers; device copies happen inside the library.
+"""
+import os
+
+import numpy as np
+
+from . import _abi
+from .png import encode_png
+
+
+class ImageBuffer:
+    """Row-major RGB8 image = image::ImageBuffer<Rgb<u8>, Vec<u8>> (lib.rs:116-123)."""
+
+    def __init__(self, pixels):
+        self.pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+
+    @property
+    def height(self):
+        return self.pixels.shape[0]
+
+    @property
+    def width(self):
+        return self.pixels.shape[1]
+
+    def get_pixel(self, x, y):
+        return tuple(int(v) for v in self.pixels[y, x])
+
+    def save(self, path):  # main.rs:86: format chosen by extension
+        ext = os.path.splitext(path)[1].lower()
+        if ext == ".png":
+            data = encode_png(self.pixels)
+        elif ext in (".ppm", ".pnm"):
+            data = b"P6\n%d %d\n255\n" % (self.width, self.height) + self.pixels.tobytes()
+        else:
+            raise ValueError(f"Unable to save target img to {path}! unsupported extension {ext!r}")
+        with open(path, "wb") as f:
+            f.write(data)
+
+
+def make_opts(seed=0, max_depth=0, trace_mode=_abi.TRACE_BVH, shard_mode=_abi.SHARD_NONE, shard_rank=0, shard_count=1,
+              batch_paths=0, integrator=0, count_visits=False):
+    return _abi.RenderOptsC(int(seed) & 0xFFFFFFFFFFFFFFFF, max_depth, trace_mode, shard_mode, shard_rank, shard_count,
+                            batch_paths, integrator, 1 if count_visits else 0)
+
+
+def render_scene(cam, num_samples, scene, stats=None, **opts):
+    """= rbrt_lib::render_scene(cam, num_samples, scene) (lib.rs:75-79)."""
+    print("Starting rendering...")  # lib.rs:80
+    W, H = cam.img_width_pix, cam.img_height_pix
+    rgb = np.empty((H, W, 3), dtype=np.uint8)
+    st = _abi.StatsC()
+    _abi.check(_abi.lib().rbrt_gpu_render(scene.handle(), cam.to_c(), int(num_samples), make_opts(**opts),
+                                          rgb.ctypes.data, st))
+    print("\rRendering 100% complete!")  # lib.rs:114
+    if stats is not None:
+        stats.update(st.as_dict())
+    return ImageBuffer(rgb)
+
+
+def render_scene_hdr(cam, num_samples, scene, stats=None, **opts):
+    """The pre-gamma mean colour `color * (1.0 / num_samples)` (lib.rs:101) as [H,W,3] f32."""
+    W, H = cam.img_width_pix, cam.img_height_pix
+    hdr = np.empty((H, W, 3), dtype=np.float32)
+    st = _abi.StatsC()
+    _abi.check(_abi.lib().rbrt_gpu_render_hdr(scene.handle(), cam.to_c(), int(num_samples), make_opts(**opts),
+                                              hdr.ctypes.data, st))
+    if stats is not None:
+        stats.update(st.as_dict())
+    return hdr
+
+
+def primary_rays(cam, seed=0, sample_idx=0):
+    """The renderer's own primary rays (cam.rs:64-82 with the Philox stream of one sample): [H*W,6] f32."""
+    rays = np.empty((cam.img_width_pix * cam.img_height_pix, 6), dtype=np.float32)
+    _abi.check(_abi.lib().rbrt_gpu_primary_rays(cam.to_c(), int(seed), int(sample_idx), rays.ctypes.data))
+    return rays

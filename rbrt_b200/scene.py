@@ -1,0 +1,58 @@
+"""Scene — host mirror of rbrt_lib::scene::Scene (scene.rs:12-16): `elements` (spheres),
+`triangle_meshes`, `lights` (dead in the reference, scene.rs:7-10).  The GPU scene (flattened SoA buffers
++ one LBVH per mesh) is created lazily on first use and owned by this object."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+class Scene:
+    def __init__(self, elements=None, triangle_meshes=None, lights=None, simd_lanes=8, leaf_size=0, box_pad_rel=0.0):
+        self.elements = list(elements or [])
+        self.triangle_meshes = list(triangle_meshes or [])
+        self.lights = list(lights or [])
+        self.simd_lanes, self.leaf_size, self.box_pad_rel = simd_lanes, leaf_size, box_pad_rel
+        self._handle = None
+
+    # ---- GPU handle -----------------------------------------------------------------------
+    def handle(self):
+        if self._handle is None:
+            lib = _abi.lib()
+            ns, nm = len(self.elements), len(self.triangle_meshes)
+            spheres = (_abi.SphereDescC * max(ns, 1))(*[s.to_c() for s in self.elements])
+            meshes = (_abi.MeshDescC * max(nm, 1))(*[m.to_c() for m in self.triangle_meshes])
+            opts = _abi.SceneOptsC(self.simd_lanes, self.leaf_size, self.box_pad_rel, 0)
+            h = C.c_void_p()
+            _abi.check(lib.rbrt_gpu_scene_create(spheres, ns, meshes, nm, opts, C.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def info(self):
+        out = _abi.SceneInfoC()
+        _abi.check(_abi.lib().rbrt_gpu_scene_info(self.handle(), out))
+        return out.as_dict()
+
+    def close(self):
+        if self._handle is not None:
+            _abi.lib().rbrt_gpu_scene_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Scene::hit (scene.rs:19-43) for caller-supplied rays ----------------------------------
+    def hit(self, rays, trace_mode=_abi.TRACE_BVH, stats=None):
+        """rays: [N,6] f32 (origin xyz, direction xyz). Returns a structured array (HIT_DTYPE)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        hits = np.zeros(len(rays), dtype=_abi.HIT_DTYPE)
+        st = _abi.StatsC()
+        _abi.check(_abi.lib().rbrt_gpu_trace_rays(self.handle(), rays.ctypes.data, len(rays), trace_mode,
+                                                  hits.ctypes.data, st))
+        if stats is not None:
+            stats.update(st.as_dict())
+        return hits
