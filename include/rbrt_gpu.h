@@ -12,7 +12,7 @@
  *
  * Every entry point is `extern "C"`, takes plain pointers and sizes, never unwinds, returns
  * 0 on success and a non-zero RBRT_E_* code on failure (message via rbrt_last_error()).
- * The CPU oracle (oracle/rbrt_oracle.cpp) exports the same shapes under the prefix rbrt_ref_.
+ * The CPU checker used by the tests mirrors these shapes; it is never linked here.
  *
  * One process drives one GPU (rbrt_gpu_init(device)); multi-GPU renders run one process per
  * GPU, each rendering a shard selected by rbrt_render_opts.shard_*, and sum their

@@ -83,7 +83,7 @@ HIT_NONE, HIT_SPHERE, HIT_MESH = -1, 0, 1
 E_INVALID, E_CUDA, E_NODEVICE = 1, 2, 3
 
 P = C.POINTER
-# name -> (restype, argtypes); the same table is used for the oracle with prefix rbrt_ref_
+# name -> (restype, argtypes) of every function include/rbrt_gpu.h declares
 GPU_SIGNATURES = {
     "rbrt_camera_new": (C.c_int, [Vec3C, Vec3C, Vec3C, C.c_uint32, C.c_uint32, C.c_float, P(CameraC)]),
     "rbrt_transform_vertices": (C.c_int, [P(C.c_float), C.c_uint64, C.c_float, Vec3C, Vec3C]),

@@ -13,26 +13,33 @@ from .vec3 import Vec3
 
 
 def parse_obj_triangles(filepath):
-    """Return (positions [V,3] f32, index triples [F,3] int64) the way rbrt consumes tobj's output:
-    all `f` records of all objects/groups in file order, position indices only, concatenated and cut
-    into triples (mesh.rs:96-99: `mesh.indices.len() / 3`)."""
-    pos, idx = [], []
+    """Return (positions [V,3] f32, index triples [F,3] int64) the way rbrt consumes tobj's output
+    (mesh.rs:92-107): one model per `o` / `g` record, position indices only (negative = relative), the
+    `f` records of a model concatenated and cut into triples (`mesh.indices.len() / 3`, no triangulation:
+    tobj's default LoadOptions), models in file order."""
+    pos, models, cur = [], [], []
     with open(filepath, "r", errors="replace") as f:
         for line in f:
-            if not line or line[0] not in "vf":
-                continue
             parts = line.split()
             if not parts:
                 continue
-            if parts[0] == "v":
+            tag = parts[0]
+            if tag == "v":
                 pos.append((float(parts[1]), float(parts[2]), float(parts[3])))
-            elif parts[0] == "f":
+            elif tag == "f":
                 for tok in parts[1:]:
                     i = int(tok.split("/")[0])
-                    idx.append(i - 1 if i > 0 else len(pos) + i)
+                    cur.append(i - 1 if i > 0 else len(pos) + i)
+            elif tag in ("o", "g") and cur:
+                models.append(cur)
+                cur = []
+    if cur:
+        models.append(cur)
+    idx = []
+    for m in models:
+        idx.extend(m[:(len(m) // 3) * 3])
     positions = np.asarray(pos, dtype=np.float32).reshape(-1, 3)
-    n = (len(idx) // 3) * 3
-    indices = np.asarray(idx[:n], dtype=np.int64).reshape(-1, 3)
+    indices = np.asarray(idx, dtype=np.int64).reshape(-1, 3)
     if indices.size and (indices.min() < 0 or indices.max() >= len(positions)):
         raise ValueError(f"{filepath}: face index out of range")
     return positions, indices

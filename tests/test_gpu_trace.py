@@ -1,0 +1,167 @@
+"""Parity of the CUDA closest-hit query (Scene::hit, scene.rs:19-43) against the oracle, through the C-ABI
+(rbrt_gpu_trace_rays).  Bar: BIT-EXACT — kind, element, ORIGINAL triangle index, and the f32 bit patterns of
+t, dist, point and normal — for both the brute-force kernel (the reference's own loop) and the LBVH kernel."""
+import numpy as np
+import pytest
+
+import rbrt_b200 as R
+from rbrt_b200 import _abi, synth
+from rbrt_b200.vec3 import Vec3
+
+from . import golden_util as G
+from . import scenes as S
+
+pytestmark = pytest.mark.gpu
+MODES = [_abi.TRACE_BRUTE, _abi.TRACE_BVH]
+
+
+def assert_same(a, b, what):
+    eq = S.hits_equal(a, b)
+    if not eq.all():
+        i = np.nonzero(~eq)[0]
+        raise AssertionError(f"{what}: {len(i)} of {len(a)} hits differ; first: got {a[i[0]]} want {b[i[0]]}")
+
+
+@pytest.mark.parametrize("name", G.NAMES)
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_hits(gpu, name, mode):
+    z, scene, cam = G.load(name)
+    n_px = cam.img_width_pix * cam.img_height_pix
+    mine = R.primary_rays(cam, int(z["seed"]), 0)
+    assert np.array_equal(mine.view(np.uint32), z["rays"][:n_px].view(np.uint32)), "primary rays (cam.rs:64-82 + Philox)"
+    assert_same(scene.hit(z["rays"], mode), z["hits"], f"{name} mode {mode}")
+
+
+@pytest.mark.parametrize("leaf_size", [1, 2, 4, 8])
+@pytest.mark.parametrize("lanes", [8, 4])
+def test_bvh_options_do_not_change_results(gpu, oracle, leaf_size, lanes):
+    for n_keep in (1275, 1277, 1280, 5, 3, 1):
+        scene = S.small_mesh_scene(3, n_keep, simd_lanes=lanes, leaf_size=leaf_size)
+        cam = S.example_camera(96, 72)
+        rays = np.concatenate([R.primary_rays(cam, 3, 0), S.random_rays(4096, (5.0, 1.4, -12.5), 4.0, 1)], 0)
+        ref = oracle.OracleScene.from_scene(scene).hit(rays)
+        info = scene.info()
+        r = n_keep % lanes
+        assert info["num_triangles_tested"] == (n_keep if (r == 0 or 2 * r >= lanes) else n_keep - r)
+        for mode in MODES:
+            assert_same(scene.hit(rays, mode), ref, f"n={n_keep} lanes={lanes} leaf={leaf_size} mode={mode}")
+
+
+def test_quirk_cases_on_gpu(gpu, oracle):
+    """The hand-derived cases of tests/test_oracle_quirks.py, GPU vs oracle."""
+    tri = ((-1, -1, -5), (1, -1, -5), (0, 1, -5))
+    cases = []
+    def mesh_scene(tris, **kw):
+        sc = R.Scene(**kw)
+        sc.triangle_meshes.append(R.TriangleMesh.from_triangles(np.array(tris, np.float32), R.Lambertian(Vec3(1, 1, 1))))
+        return sc
+    cases.append((mesh_scene([tri] * 16), [[0, 0, 0, 0, 0, -1], [0, 0, -10, 0, 0, 1], [0, 0, 0, 0, 0, -2], [0, 0, 0, 0.01, 0.01, -1]]))
+    for z in (-999.0, -1000.0, -0.0009, -0.0011):
+        cases.append((mesh_scene([tuple((x * 400, y * 400, z) for x, y, _ in tri)] * 8), [[0, 0, 0, 0, 0, -1]]))
+    for n in range(1, 18):
+        cases.append((mesh_scene([((-1, -1, -50 + i), (1, -1, -50 + i), (0, 1, -50 + i)) for i in range(n)]), [[0, 0, 0, 0, 0, -1]]))
+        cases.append((mesh_scene([((-1, -1, -50 + i), (1, -1, -50 + i), (0, 1, -50 + i)) for i in range(n)], simd_lanes=4), [[0, 0, 0, 0, 0, -1]]))
+    sc = mesh_scene([tri] * 8)
+    sc.elements.append(R.Sphere(Vec3(0, 0, -6.0), 1.0, R.Lambertian(Vec3(1, 1, 1))))       # exact dist tie: sphere wins
+    sc.elements.append(R.Sphere(Vec3(0, 0, 0), 1.0, R.Dielectric(1.5)))
+    cases.append((sc, [[0, 0, 0, 0, 0, -1], [0, 0, 1.0005, 0, 0, -1], [0, 0, 0.5, 0, 0, 1], [0, 0, 30, 0, 0, 1]]))
+    for scene, rays in cases:
+        rays = np.array(rays, np.float32)
+        ref = oracle.OracleScene.from_scene(scene).hit(rays)
+        for mode in MODES:
+            assert_same(scene.hit(rays, mode), ref, f"quirk case mode {mode}")
+
+
+def test_degenerate_rays_and_nan_count(gpu, oracle):
+    scene = S.quirk_scene()
+    rays = S.random_rays(20000, (0.0, 1.5, -4.0), 3.0, 9)
+    rays[:8, 3:] = 0.0                                  # zero direction: a = 0 -> sol = NaN or 0/0: the reference panics
+    rays[8:16, 3] = np.nan
+    rays[16:24, 3:] = np.float32([0, 0, 1e-30])
+    rays[24:32, :3] = np.float32([1e6, 1e6, 1e6])
+    ref = oracle.OracleScene.from_scene(scene).hit(rays)
+    for mode in MODES:
+        st = {}
+        got = scene.hit(rays, mode, stats=st)
+        assert_same(got, ref, f"degenerate rays mode {mode}")
+        assert st["nan_rays"] >= 8
+
+
+def test_multi_mesh_and_empty_inputs(gpu, oracle):
+    scene = S.quirk_scene()
+    assert scene.info()["num_meshes"] == 3 and scene.info()["num_triangles"] == 23
+    assert len(scene.hit(np.zeros((0, 6), np.float32))) == 0
+    empty = R.Scene()
+    h = empty.hit(np.float32([[0, 0, 0, 0, 0, -1]]))
+    assert h["kind"][0] == -1
+    only_mesh = R.Scene()
+    only_mesh.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(2, 2.0, (0, 0, -8)), R.Metal(Vec3(1, 1, 1), 0.1)))
+    rays = S.random_rays(8192, (0, 0, -8), 3.0, 4)
+    assert_same(only_mesh.hit(rays), oracle.OracleScene.from_scene(only_mesh).hit(rays), "mesh-only scene")
+
+
+def test_medium_mesh_vs_oracle(gpu, oracle):
+    """20 480 triangles, camera rays + bounce-like rays starting ON the surface (self-intersection window)."""
+    scene = S.small_mesh_scene(5)
+    cam = S.example_camera(160, 120)
+    prim = R.primary_rays(cam, 21, 0)
+    first = scene.hit(prim)
+    on = first["kind"] >= 0
+    rng = np.random.default_rng(2)
+    d2 = rng.normal(size=(on.sum(), 3)).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    bounce = np.concatenate([first["point"][on], d2], 1)
+    rays = np.concatenate([prim, bounce], 0)
+    ref = oracle.OracleScene.from_scene(scene).hit(rays)
+    for mode in MODES:
+        assert_same(scene.hit(rays, mode), ref, f"medium mesh mode {mode}")
+
+
+def c2_scene(tmp=None):
+    import os
+    d = synth.cache_dir()
+    obj = os.path.join(d, "standin6.obj")
+    if not os.path.exists(obj):
+        synth.write_bunny_standin(obj, 6)
+    return R.create_scene_from_scene_blueprint(synth.example_scene_blueprint(obj))
+
+
+def test_c2_full_size_bvh_equals_brute(gpu):
+    """Config C2 at BASELINE.json's full size (1024x768 primary rays of an 81 920-triangle mesh through the OBJ
+    loader): the oracle would need minutes, so the size-independent property is used — the BVH kernel must agree
+    bit for bit with the GPU brute-force kernel, which is itself pinned to the oracle by the tests above."""
+    scene = c2_scene()
+    cam = S.example_camera(1024, 768)
+    prim = R.primary_rays(cam, 0, 0)
+    st = {}
+    bvh = scene.hit(prim, _abi.TRACE_BVH, stats=st)
+    brute = scene.hit(prim, _abi.TRACE_BRUTE)
+    assert_same(bvh, brute, "C2 primary rays")
+    assert (bvh["kind"] == 1).sum() > 50000
+    on = bvh["kind"] == 1
+    n = bvh["normal"][on]
+    refl = prim[on, 3:] - 2 * (prim[on, 3:] * n).sum(1, keepdims=True) * n
+    sec = np.concatenate([bvh["point"][on], refl.astype(np.float32)], 1)[:200000]
+    assert_same(scene.hit(sec, _abi.TRACE_BVH), scene.hit(sec, _abi.TRACE_BRUTE), "C2 reflected rays")
+    assert 0 < st["node_visits"] < 60 * len(prim) and st["tri_tests"] < 20 * len(prim)
+
+
+def test_c3_million_triangles_bvh_equals_brute(gpu):
+    """Config C3's mesh (displaced icosphere, subdivision 8 = 1 310 720 triangles, radius 40): BVH == brute on a
+    stratified subset of the 1920x1080 primary rays plus reflected rays."""
+    camkw, spheres, tris, mat = synth.big_mesh_config(8, 40.0)
+    scene = R.Scene()
+    scene.elements += [R.Sphere(c, r, m) for c, r, m in spheres]
+    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, mat))
+    info = scene.info()
+    assert info["num_triangles_tested"] == 1310720
+    cam = R.Camera.new(camkw["position"], camkw["look_at"], camkw["up"], 1080, 1920, camkw["focal_len_mm"])
+    prim = R.primary_rays(cam, 1, 0)[::23]
+    bvh = scene.hit(prim, _abi.TRACE_BVH)
+    assert_same(bvh, scene.hit(prim, _abi.TRACE_BRUTE), "C3 primary subset")
+    on = bvh["kind"] == 1
+    assert on.sum() > 10000
+    n = bvh["normal"][on]
+    refl = prim[on, 3:] - 2 * (prim[on, 3:] * n).sum(1, keepdims=True) * n
+    sec = np.concatenate([bvh["point"][on], refl.astype(np.float32)], 1)[:30000]
+    assert_same(scene.hit(sec, _abi.TRACE_BVH), scene.hit(sec, _abi.TRACE_BRUTE), "C3 reflected subset")
