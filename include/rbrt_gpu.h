@@ -92,6 +92,10 @@ enum { RBRT_LANES_AVX = 8, RBRT_LANES_SSE = 4 };
 
 enum { RBRT_SHARD_NONE = 0, RBRT_SHARD_TILES = 1, RBRT_SHARD_SAMPLES = 2 };
 enum { RBRT_TRACE_BVH = 0, RBRT_TRACE_BRUTE = 1 };
+enum {
+    RBRT_OPT_COUNT_VISITS = 1,   /* fill rbrt_stats.node_visits / tri_tests (instrumented kernels, slower) */
+    RBRT_OPT_TIME_KERNELS = 2    /* bracket every trace launch with CUDA events -> rbrt_stats.ms_trace */
+};
 
 typedef struct rbrt_scene_opts {
     uint32_t simd_lanes;     /* RBRT_LANES_*; 0 = 8 */
@@ -108,8 +112,8 @@ typedef struct rbrt_render_opts {
     uint32_t shard_rank;
     uint32_t shard_count;    /* 0 or 1 = unsharded */
     uint32_t batch_paths;    /* paths in flight per wavefront batch; 0 = default */
-    uint32_t integrator;     /* 0 = wavefront (default), 1 = persistent megakernel */
-    uint32_t reserved;
+    uint32_t integrator;     /* 0 = wavefront (default); other values are rejected */
+    uint32_t flags;          /* RBRT_OPT_* */
 } rbrt_render_opts;
 
 typedef struct rbrt_stats {

@@ -20,6 +20,7 @@ _SIG = {
     "rbrt_ref_render": (C.c_int, [C.c_void_p, P(_abi.CameraC), C.c_uint32, P(_abi.RenderOptsC), C.c_void_p, P(_abi.StatsC)]),
     "rbrt_ref_render_hdr": (C.c_int, [C.c_void_p, P(_abi.CameraC), C.c_uint32, P(_abi.RenderOptsC), C.c_void_p, P(_abi.StatsC)]),
     "rbrt_ref_render_accum": (C.c_int, [C.c_void_p, P(_abi.CameraC), C.c_uint32, P(_abi.RenderOptsC), C.c_void_p, P(_abi.StatsC)]),
+    "rbrt_ref_render_subset": (C.c_int, [C.c_void_p, P(_abi.CameraC), C.c_uint32, P(_abi.RenderOptsC), C.c_uint32, C.c_uint32, C.c_void_p, P(_abi.StatsC)]),
     "rbrt_ref_finalize": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rbrt_ref_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, P(_abi.StatsC)]),
     "rbrt_ref_primary_rays": (C.c_int, [P(_abi.CameraC), C.c_uint64, C.c_uint32, C.c_void_p]),
@@ -133,6 +134,14 @@ class OracleScene:
         if stats is not None:
             stats.update(st.as_dict())
         return out
+
+
+def render_subset(osc, cam_c, spp, stride_x, stride_y, opts=None, want_image=False):
+    """Render only the pixel lattice (row % stride_y == 0, col % stride_x == 0); returns (stats dict, accum or None)."""
+    out = np.zeros((cam_c.img_height_pix * cam_c.img_width_pix * 4,), np.float32) if want_image else None
+    st = _abi.StatsC()
+    check(lib().rbrt_ref_render_subset(osc._h, cam_c, spp, opts, stride_x, stride_y, out.ctypes.data if want_image else None, st))
+    return st.as_dict(), out
 
 
 def finalize(accum, w, h, spp):

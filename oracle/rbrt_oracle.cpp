@@ -485,7 +485,8 @@ inline bool owns_pixel(const ShardPlan& sp, uint32_t row, uint32_t col, uint32_t
 
 // lib.rs:75-114: threads over image columns (rayon stand-in), rows and samples serial.
 int render_sum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rbrt_render_opts* o,
-               std::vector<V3>& sum /* row-major */, rbrt_stats* stats, unsigned threads_req) {
+               std::vector<V3>& sum /* row-major */, rbrt_stats* stats, unsigned threads_req,
+               uint32_t stride_x = 1, uint32_t stride_y = 1) {
     uint32_t W = cam.img_width_pix, H = cam.img_height_pix;
     if (!W || !H || !spp) return fail(RBRT_E_INVALID, "empty image or zero samples");
     uint64_t seed = o ? o->seed : 0;
@@ -509,9 +510,9 @@ int render_sum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rbrt
         std::vector<float> scratch; Counters cnt; uint64_t np = 0;
         V3 bg = v3(0.05f, 0.05f, 0.8f);                              // lib.rs:89-93
         for (;;) {
-            uint32_t col = next_col.fetch_add(1);
+            uint32_t col = next_col.fetch_add(stride_x);
             if (col >= W) break;
-            for (uint32_t row = 0; row < H; ++row) {
+            for (uint32_t row = 0; row < H; row += stride_y) {
                 if (!owns_pixel(sp, row, col, W)) continue;
                 V3 color = v3(0, 0, 0);
                 for (uint32_t s = sp.s0; s < sp.s1; ++s) {
@@ -608,6 +609,20 @@ int rbrt_ref_render_accum(const rbrt_scene* scene, const rbrt_camera* cam, uint3
     int rc = render_sum(*reinterpret_cast<const Scene*>(scene), *cam, spp, opts, sum, stats, g_threads);
     if (rc) return rc;
     for (size_t i = 0; i < sum.size(); ++i) { out_rgba[4 * i] = sum[i].x; out_rgba[4 * i + 1] = sum[i].y; out_rgba[4 * i + 2] = sum[i].z; out_rgba[4 * i + 3] = 0.0f; }
+    return RBRT_OK;
+}
+
+// CPU-baseline helper for bench.py: the same render restricted to the pixel lattice (row % stride_y == 0,
+// col % stride_x == 0) — a bounded, stratified sample of a workload too slow to render in full on the CPU.
+// Pixels off the lattice stay zero.  Rays, paths and wall time are returned in stats.
+int rbrt_ref_render_subset(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
+                           uint32_t stride_x, uint32_t stride_y, float* out_rgba, rbrt_stats* stats) {
+    if (!scene || !cam || !stride_x || !stride_y) return fail(RBRT_E_INVALID, "null argument or zero stride");
+    std::vector<V3> sum;
+    int rc = render_sum(*reinterpret_cast<const Scene*>(scene), *cam, spp, opts, sum, stats, g_threads, stride_x, stride_y);
+    if (rc) return rc;
+    if (out_rgba)
+        for (size_t i = 0; i < sum.size(); ++i) { out_rgba[4 * i] = sum[i].x; out_rgba[4 * i + 1] = sum[i].y; out_rgba[4 * i + 2] = sum[i].z; out_rgba[4 * i + 3] = 0.0f; }
     return RBRT_OK;
 }
 

@@ -51,7 +51,7 @@ class SceneOptsC(C.Structure):
 class RenderOptsC(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("max_depth", C.c_uint32), ("trace_mode", C.c_uint32),
                 ("shard_mode", C.c_uint32), ("shard_rank", C.c_uint32), ("shard_count", C.c_uint32),
-                ("batch_paths", C.c_uint32), ("integrator", C.c_uint32), ("reserved", C.c_uint32)]
+                ("batch_paths", C.c_uint32), ("integrator", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class StatsC(C.Structure):
@@ -79,6 +79,7 @@ HIT_DTYPE = [("kind", "<i4"), ("elem_idx", "<u4"), ("tri_idx", "<u4"), ("t", "<f
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE = 0, 1
+OPT_COUNT_VISITS, OPT_TIME_KERNELS = 1, 2
 HIT_NONE, HIT_SPHERE, HIT_MESH = -1, 0, 1
 E_INVALID, E_CUDA, E_NODEVICE = 1, 2, 3
 

@@ -33,6 +33,7 @@ struct WaveBuffers {
     float4* accum = nullptr;     // internal W*H accumulation buffer for the host-pointer entry points
     size_t accum_px = 0;
     uint8_t* rgb = nullptr; float* hdr = nullptr; size_t out_px = 0;
+    std::vector<cudaEvent_t> ev;   // event pool for per-kernel timing (RBRT_OPT_TIME_KERNELS)
     size_t bytes = 0;
 };
 

@@ -260,6 +260,7 @@ void free_wave_buffers(WaveBuffers& wb) {
     cudaFree(wb.hit); for (int i = 0; i < 3; ++i) cudaFree(wb.matq[i]);
     cudaFree(wb.out); cudaFree(wb.hist); cudaFree(wb.ctr); cudaFree(wb.stats); cudaFree(wb.accum);
     cudaFree(wb.rgb); cudaFree(wb.hdr);
+    for (cudaEvent_t e : wb.ev) cudaEventDestroy(e);
     wb = WaveBuffers();
 }
 
@@ -268,9 +269,10 @@ void free_wave_buffers(WaveBuffers& wb) {
 static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
     if (wb.cap >= cap && wb.depth_cap >= depth && wb.stats) return RBRT_OK;
     float4* accum = wb.accum; size_t accum_px = wb.accum_px; uint8_t* rgb = wb.rgb; float* hdr = wb.hdr; size_t out_px = wb.out_px;
+    std::vector<cudaEvent_t> ev; ev.swap(wb.ev);
     wb.accum = nullptr; wb.rgb = nullptr; wb.hdr = nullptr;
     free_wave_buffers(wb);
-    wb.accum = accum; wb.accum_px = accum_px; wb.rgb = rgb; wb.hdr = hdr; wb.out_px = out_px;
+    wb.accum = accum; wb.accum_px = accum_px; wb.rgb = rgb; wb.hdr = hdr; wb.out_px = out_px; wb.ev.swap(ev);
     size_t b = 0;
     for (int i = 0; i < 2; ++i) { CKR(cudaMalloc(&wb.q_o[i], 16ull * cap)); CKR(cudaMalloc(&wb.q_d[i], 16ull * cap)); b += 32ull * cap; }
     CKR(cudaMalloc(&wb.hit, 16ull * cap)); b += 16ull * cap;
@@ -291,6 +293,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     rbrt_render_opts o{}; if (opts) o = *opts;
     const uint32_t max_depth = o.max_depth ? o.max_depth : 50;
     if (max_depth > 1024) { set_error("max_depth > 1024"); return RBRT_E_INVALID; }
+    if (o.integrator != 0) { set_error("unknown integrator %u", o.integrator); return RBRT_E_INVALID; }
     ShardDev sh;
     sh.rank = 0; sh.count = 1; sh.s0 = 0; sh.s1 = spp;
     sh.tiles_x = (W + 7) / 8;
@@ -328,16 +331,24 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
         const int grid = sc.sm_count * 8;
         const bool brute = o.trace_mode == RBRT_TRACE_BRUTE;
-        const bool count = (o.reserved & 1u) != 0;
+        const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
+        const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
+        size_t ev_used = 0;
+        auto next_event = [&]() -> cudaEvent_t {
+            if (ev_used == wb.ev.size()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); wb.ev.push_back(e); }
+            return wb.ev[ev_used++];
+        };
         for (uint32_t s_base = sh.s0; s_base < sh.s1; s_base += S_b) {
             wp.s_base = s_base; wp.s_count = (sh.s1 - s_base < S_b) ? sh.s1 - s_base : S_b;
             CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
             CKR(cudaMemsetAsync(wb.out, 0, 16ull * wp.s_count * P, st));
             k_generate<<<grid, 256, 0, st>>>(wp); ++launches;
             for (uint32_t it = 0; it <= max_depth; ++it) {
+                if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (brute) { if (count) k_trace<true, true><<<grid, 256, 0, st>>>(wp, it); else k_trace<true, false><<<grid, 256, 0, st>>>(wp, it); }
                 else { if (count) k_trace<false, true><<<grid, 256, 0, st>>>(wp, it); else k_trace<false, false><<<grid, 256, 0, st>>>(wp, it); }
                 ++launches; ++iterations;
+                if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (it < max_depth) { k_shade<<<grid, 256, 0, st>>>(wp, it); ++launches; }
             }
             k_accumulate<<<(P + 255) / 256, 256, 0, st>>>(wp, d_accum); ++launches;
@@ -359,6 +370,13 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         }
         stats->paths = valid_px * (sh.s1 - sh.s0);
         stats->ms_device = ms; stats->launches = launches; stats->iterations = iterations;
+        if (P && sh.s1 > sh.s0 && (o.flags & RBRT_OPT_TIME_KERNELS)) {
+            double tr = 0;
+            for (size_t i = 0; i + 1 < wb.ev.size() && i + 1 < 2ull * iterations; i += 2) {
+                float t = 0; CKR(cudaEventElapsedTime(&t, wb.ev[i], wb.ev[i + 1])); tr += t;
+            }
+            stats->ms_trace = tr;
+        }
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     return RBRT_OK;

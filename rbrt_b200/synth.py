@@ -121,6 +121,28 @@ def big_mesh_config(subdiv, radius, seed=1234):
     return cam, spheres, tris, Lambertian(Vec3(0.7, 0.35, 0.2))
 
 
+def stress_config(seed=4321):
+    """Config C4: divergence stress — a 6x6 field of glass (ref_idx 1.5-1.8) and low-roughness metal spheres around
+    a glass displaced icosphere (20 480 triangles), on the fixture's ground sphere, seen by the fixture camera.
+    More than half of the frame is covered by specular material, so paths use the 50-bounce budget.
+    Returns (spheres, triangles, mesh material)."""
+    rng = np.random.default_rng(seed)
+    spheres = [(Vec3(0.0, -1000.0, -5.0), 1000.0, Lambertian(Vec3(0.02, 0.2, 0.1)))]
+    for i in range(6):
+        for j in range(6):
+            if (i, j) in ((2, 2), (3, 2), (2, 3), (3, 3)):
+                continue                                  # the mesh stands here
+            r = float(rng.uniform(0.9, 1.3))
+            x, z = -9.0 + 3.6 * i + float(rng.uniform(-0.3, 0.3)), -5.0 - 3.4 * j + float(rng.uniform(-0.3, 0.3))
+            if (i + j) % 2 == 0:
+                mat = Dielectric(float(rng.uniform(1.5, 1.8)))
+            else:
+                mat = Metal(Vec3(*rng.uniform(0.6, 0.95, size=3)), float(rng.uniform(0.0, 0.02)))
+            spheres.append((Vec3(x, r, z), r, mat))
+    tris = displaced_icosphere(5, 3.0, (0.0, 3.0, -13.5), 0.05, seed)
+    return spheres, tris, Dielectric(1.5)
+
+
 def cache_dir():
     d = os.environ.get("RBRT_B200_CACHE", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "synth"))
     os.makedirs(d, exist_ok=True)
