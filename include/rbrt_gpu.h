@@ -111,7 +111,7 @@ typedef struct rbrt_render_opts {
     uint32_t shard_mode;     /* RBRT_SHARD_* */
     uint32_t shard_rank;
     uint32_t shard_count;    /* 0 or 1 = unsharded */
-    uint32_t batch_paths;    /* paths in flight per wavefront batch; 0 = default */
+    uint32_t batch_paths;    /* paths in flight per wavefront batch; 0 = as many as fit (<= 2^27, <= half of free HBM) */
     uint32_t integrator;     /* 0 = wavefront (default); other values are rejected */
     uint32_t flags;          /* RBRT_OPT_* */
 } rbrt_render_opts;

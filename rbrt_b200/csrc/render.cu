@@ -11,6 +11,8 @@
 // After the last iteration k_accumulate adds the batch's per-path radiances to the per-pixel sums in
 // sample order — the reference's `color += colorize(..)` (lib.rs:96-100) — with no float atomics,
 // so an image is bit-reproducible and independent of scheduling.
+#include <cstdio>
+#include <cstdlib>
 #include "engine.cuh"
 #include "intersect.cuh"
 #include "shade.cuh"
@@ -315,7 +317,19 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     WaveBuffers& wb = sc.wb;
     CKR(cudaEventRecord(ev0, st));
     if (P && sh.s1 > sh.s0) {
-        uint32_t target = o.batch_paths ? o.batch_paths : (1u << 21);
+        // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is
+        // bounded below by its slowest ray, so the ~45 sparsely populated tail iterations cost the same for a
+        // small batch as for a large one: the default is therefore "as many paths as fit" — up to 2^27 paths
+        // (108 + 2*max_depth bytes of wavefront state each: 27.9 GB at depth 50) and at most half of the free HBM.
+        uint32_t target = o.batch_paths;
+        if (!target) {
+            size_t free_b = 0, total_b = 0;
+            CKR(cudaMemGetInfo(&free_b, &total_b));
+            free_b += wb.bytes;                                           // what a re-allocation would release first
+            uint64_t per_path = 108ull + 2ull * max_depth;
+            uint64_t fit = (free_b / 2) / per_path;
+            target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
+        }
         uint32_t S_b = target / P; if (S_b < 1) S_b = 1; if (S_b > sh.s1 - sh.s0) S_b = sh.s1 - sh.s0;
         if ((uint64_t)S_b * P > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
         const uint32_t cap = S_b * P;
@@ -376,6 +390,16 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 float t = 0; CKR(cudaEventElapsedTime(&t, wb.ev[i], wb.ev[i + 1])); tr += t;
             }
             stats->ms_trace = tr;
+            if (getenv("RBRT_DEBUG_ITERS")) {                              // per-iteration trace time + queue sizes of the LAST batch
+                std::vector<IterCtr> hc(max_depth + 2);
+                CKR(cudaMemcpy(hc.data(), wb.ctr, sizeof(IterCtr) * (max_depth + 2), cudaMemcpyDeviceToHost));
+                size_t per_batch = max_depth + 1, first = 2 * (iterations - per_batch);
+                for (uint32_t it = 0; it <= max_depth; ++it) {
+                    float t = 0; cudaEventElapsedTime(&t, wb.ev[first + 2 * it], wb.ev[first + 2 * it + 1]);
+                    fprintf(stderr, "it %2u rays %9u  lambert %9u metal %9u glass %9u  trace %8.3f ms\n", it, hc[it].ray_count,
+                            hc[it].mat_count[0], hc[it].mat_count[1], hc[it].mat_count[2], t);
+                }
+            }
         }
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
