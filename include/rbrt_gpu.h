@@ -129,6 +129,7 @@ typedef struct rbrt_stats {
     double   ms_d2h;
     uint32_t launches;       /* kernels launched by this call */
     uint32_t iterations;     /* wavefront bounce iterations executed */
+    uint64_t traversed_rays; /* rays that entered a mesh AABB and were traversed through the LBVH (RBRT_OPT_COUNT_VISITS) */
 } rbrt_stats;
 
 typedef struct rbrt_scene_info {

@@ -10,24 +10,29 @@ namespace rbrt {
 // Per-iteration queue counters.  All iterations of a batch get their own slot, so one memset per
 // batch resets everything and no kernel ever has to reset a counter another kernel still reads.
 struct IterCtr {
-    uint32_t ray_count;      // rays in the queue traced at this iteration (written by generate / shade of it-1)
-    uint32_t ray_head;       // persistent-thread work cursor of the trace kernel
-    uint32_t mat_count[3];   // hits appended per material kind by the trace kernel
+    uint32_t ray_count;      // rays of this iteration = Scene::hit calls (statistics)
+    uint32_t cand_count;     // rays that passed a mesh AABB and are queued for BVH traversal
+    uint32_t cand_head;      // persistent-thread work cursor of the trace kernel
+    uint32_t mat_count[3];   // hits queued for shading, per material kind
     uint32_t shade_head;     // persistent-thread work cursor of the shade kernel
-    uint32_t pad[2];
+    uint32_t pad;
 };
 
-enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_COUNT = 4 };
+enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_CAND = 4, ST_COUNT = 5 };
 
+// Wavefront state.  Every per-path record lives at the path's own index pid (no slot compaction): a
+// path's next ray overwrites its previous one, so one ray buffer serves all bounce iterations.
 struct WaveBuffers {
     uint32_t cap = 0;            // paths per batch the buffers hold
     uint32_t depth_cap = 0;      // bounce iterations the history/counter arrays hold
-    float4* q_o[2] = {nullptr, nullptr};   // ray queue: {origin.xyz, bits(path id)}
-    float4* q_d[2] = {nullptr, nullptr};   //            {direction.xyz, 0}
-    uint4* hit = nullptr;        // per queue slot: {bits(t), element, triangle, kind}
-    uint32_t* matq[3] = {nullptr, nullptr, nullptr};   // queue slots grouped by material kind
-    float4* out = nullptr;       // per path: final radiance (zero-initialised per batch)
-    uint16_t* hist = nullptr;    // [iteration][path]: element scattered at, for the attenuation product
+    float4* ray_o = nullptr;     // [pid] {origin.xyz, -}
+    float4* ray_d = nullptr;     // [pid] {direction.xyz, -}
+    uint4* hit = nullptr;        // [pid] sphere pre-result for queued candidates, final hit for queued shading work
+    uint32_t* candq = nullptr;   // pids queued for BVH traversal
+    uint32_t* matq[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // pids queued for shading, by iteration parity and material kind
+                                 // (k_shade(it) reads parity it&1 while it fills parity (it+1)&1)
+    float4* out = nullptr;       // [pid] final radiance of the path (written exactly once, when the path ends)
+    uint16_t* hist = nullptr;    // [iteration][pid]: element scattered at, for the attenuation product
     IterCtr* ctr = nullptr;      // [depth_cap + 2]
     unsigned long long* stats = nullptr;   // ST_COUNT counters
     float4* accum = nullptr;     // internal W*H accumulation buffer for the host-pointer entry points
@@ -53,13 +58,13 @@ struct WaveParams {
     CamDev cam;
     ShardDev sh;
     uint32_t key0, key1;
-    uint32_t cap;            // queue capacity = paths of a full batch
+    uint32_t cap;            // capacity of the per-path buffers = paths of a full batch
     uint32_t paths_px;       // P_r = tiles_mine * 32: path id = s_local * paths_px + j
     uint32_t s_base;         // first sample index of this batch
     uint32_t s_count;        // samples in this batch
     uint32_t max_depth;      // 50 (lib.rs:99)
-    float4* q_o[2]; float4* q_d[2];
-    uint4* hit; uint32_t* matq[3];
+    float4* ray_o; float4* ray_d;
+    uint4* hit; uint32_t* candq; uint32_t* matq[2][3];
     float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;
 };
 

@@ -1,13 +1,19 @@
 // render.cu — the wavefront path tracer: render_scene + colorize (rbrt_lib/src/lib.rs:43-124).
 //
 // One batch = every pixel of this rank's shard x a run of consecutive samples.  Path id
-// pid = s_local * P + j (j = pixel enumeration of the shard, 8x4 tiles, one warp = one tile).
-// Per bounce iteration `it` (= depth 50-it of the reference's recursion):
-//   k_trace : persistent warps pull 32 rays at a time from queue it&1, run Scene::hit, finish
-//             missed paths (sky + attenuation product, written to out[pid]) and append hit slots to
-//             one of three per-material index queues with ballot + one atomic per warp.
-//   k_shade : persistent warps pull 32 hits of ONE material, run its scatter() and append the
-//             continuation ray to queue (it+1)&1.
+// pid = s_local * P + j (j = pixel enumeration of the shard, 8x4 tiles, one warp = one tile); every
+// per-path record (ray, hit, radiance, scatter history) lives at index pid, queues hold pids.
+//
+// A ray's closest-hit query (Scene::hit, scene.rs:19-43) is split in two stages:
+//   stage A  (coherent, runs in the kernel that PRODUCES the ray: k_generate / k_shade): the sphere
+//            tests and the whole-mesh AABB pre-tests.  Rays that touch no mesh box are resolved on the
+//            spot — sphere hit -> material queue, miss -> sky + attenuation unwinding -> out[pid];
+//            only rays that enter a mesh box are queued for traversal.
+//   stage B  (k_trace): persistent warps traverse the LBVH for queued rays only and re-fill lanes
+//            whose ray has finished from the queue INSIDE the traversal loop (dynamic fetch), so lanes
+//            do not idle behind the longest traversal of their warp.
+// Per bounce iteration `it` (= depth 50-it of the reference's recursion): k_trace(it) -> k_shade(it).
+// k_shade pulls 32 hits of ONE material, runs its scatter() and stage A of the continuation ray.
 // After the last iteration k_accumulate adds the batch's per-path radiances to the per-pixel sums in
 // sample order — the reference's `color += colorize(..)` (lib.rs:96-100) — with no float atomics,
 // so an image is bit-reproducible and independent of scheduling.
@@ -19,135 +25,367 @@
 
 namespace rbrt {
 
+#define FULL_MASK 0xFFFFFFFFu
+#define CLS_CAND 3            // queue classes of a produced ray: 0..2 material queues, 3 traversal queue
+#define CLS_NONE 7            // resolved on the spot (or no ray)
+#define ROUNDS 4              // 32-ray rounds a producer warp handles per queue reservation
+
 // ------------------------------------------------------------------ warp helpers
 // Every lane of a converged warp calls this; lanes with pred get consecutive slots.
 __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
-    uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+    uint32_t mask = __ballot_sync(FULL_MASK, pred);
     if (mask == 0) return 0;
     uint32_t lane = threadIdx.x & 31;
     uint32_t leader = __ffs(mask) - 1;
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    base = __shfl_sync(FULL_MASK, base, leader);
     return base + __popc(mask & ((1u << lane) - 1));
 }
 
-__device__ __forceinline__ uint32_t warp_grab(uint32_t* head) {
+__device__ __forceinline__ uint32_t warp_grab(uint32_t* head, uint32_t count) {
     uint32_t base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(head, 32u);
-    return __shfl_sync(0xFFFFFFFFu, base, 0);
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(head, count);
+    return __shfl_sync(FULL_MASK, base, 0);
 }
 
-// ------------------------------------------------------------------ generate (cam.rs:64-82)
-__global__ void __launch_bounds__(256) k_generate(WaveParams P) {
-    uint32_t n_paths = P.s_count * P.paths_px;
-    uint32_t stride = gridDim.x * blockDim.x;
-    // n_paths is a multiple of 32 (paths_px is), so whole warps stay converged
-    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < n_paths; pid += stride) {
-        uint32_t s_local = pid / P.paths_px, j = pid - s_local * P.paths_px;
-        uint32_t row, col;
-        bool valid = shard_pixel(P.sh, P.cam, j, row, col);
-        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
-        if (valid) {
-            RngKey key; key.k0 = P.key0; key.k1 = P.key1;
-            camera_ray(P.cam, row, col, key, row * P.cam.width + col, P.s_base + s_local, o, d);
-        }
-        uint32_t slot = warp_append(&P.ctr[0].ray_count, valid);
-        if (valid) {
-            P.q_o[0][slot] = make_float4(o.x, o.y, o.z, __uint_as_float(pid));
-            P.q_d[0][slot] = make_float4(d.x, d.y, d.z, 0.0f);
+// Deferred queue appends of a producer warp: each lane remembers the class and pid of the ray it
+// produced in each of ROUNDS rounds; flush() reserves space with ONE atomic per non-empty class for
+// all rounds together (same-address atomics are the scarce resource: ~1 per ns per address).
+struct Deferred {
+    uint32_t cls;            // 3 bits per round
+    uint32_t pid[ROUNDS];
+    __device__ __forceinline__ void clear() { cls = 0; for (int r = 0; r < ROUNDS; ++r) { cls |= (uint32_t)CLS_NONE << (3 * r); pid[r] = 0; } }
+    __device__ __forceinline__ void set(int r, uint32_t c, uint32_t p) { cls = (cls & ~(7u << (3 * r))) | (c << (3 * r)); pid[r] = p; }
+};
+
+__device__ __forceinline__ void flush(const WaveParams& P, uint32_t it, const Deferred& df) {
+    IterCtr* c = P.ctr + it;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+        uint32_t m[ROUNDS], total = 0;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) { m[r] = __ballot_sync(FULL_MASK, ((df.cls >> (3 * r)) & 7u) == k); total += __popc(m[r]); }
+        if (total == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(k == CLS_CAND ? &c->cand_count : &c->mat_count[k], total);
+        base = __shfl_sync(FULL_MASK, base, 0);
+        uint32_t* q = k == CLS_CAND ? P.candq : P.matq[it & 1][k];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            if (m[r] & (1u << lane)) q[base + __popc(m[r] & lt)] = df.pid[r];
+            base += __popc(m[r]);
         }
     }
 }
 
-// ------------------------------------------------------------------ trace (scene.rs:19-43 + the miss arm of lib.rs:68-71)
-template <bool BRUTE, bool COUNT>
-__global__ void __launch_bounds__(256) k_trace(WaveParams P, uint32_t it) {
-    IterCtr* c = P.ctr + it;
-    const uint32_t n = c->ray_count;
-    if (n == 0) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_RAYS], (unsigned long long)n);
-    const float4* __restrict__ qo = P.q_o[it & 1];
-    const float4* __restrict__ qd = P.q_d[it & 1];
-    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
-    uint32_t nan_count = 0;
-    for (;;) {
-        uint32_t base = warp_grab(&c->ray_head);
-        if (base >= n) break;
-        uint32_t i = base + (threadIdx.x & 31);
-        bool active = i < n;
-        int mat_kind = -1;
-        if (active) {
-            float4 a = qo[i], b = qd[i];
-            f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
-            uint32_t pid = __float_as_uint(a.w);
-            Hit h = scene_hit<BRUTE>(P.S, o, d, COUNT ? &cnt : nullptr);
-            if (h.kind >= 0) {
-                if (it < P.max_depth) {                                   // depth > 0: scatter() will run (lib.rs:54)
-                    uint32_t elem = h.kind == 0 ? h.elem : P.S.n_spheres + h.elem;
-                    P.hit[i] = make_uint4(__float_as_uint(h.t), elem, h.tri, (uint32_t)h.kind);
-                    mat_kind = (int)__ldg(P.S.mat_kind + elem);
-                }                                                         // else: depth exhausted -> black (lib.rs:63-66)
-            } else if (h.kind == -1) {
-                // miss: sky, then unwind att_1 * (att_2 * (... * sky)) innermost first (lib.rs:62)
-                f3 col = sky(d);
-                for (int k = (int)it - 1; k >= 0; --k) {
-                    uint32_t e = P.hist[(size_t)k * P.cap + pid];
-                    float4 m = __ldg(P.S.mat + e);
-                    f3 att = __ldg(P.S.mat_kind + e) == 2u ? mk3(1.0f, 1.0f, 1.0f) : mk3(m.x, m.y, m.z);
-                    col = att * col;
-                }
-                P.out[pid] = make_float4(col.x, col.y, col.z, 0.0f);
-            } else {
-                ++nan_count;                                              // reference panics here (sphere.rs:33)
+// att_1 * (att_2 * (... * leaf)): the recursion of lib.rs:62 unwinds innermost first
+__device__ __forceinline__ f3 unwind(const WaveParams& P, f3 col, uint32_t n_scatters, uint32_t pid) {
+    for (int k = (int)n_scatters - 1; k >= 0; --k) {
+        uint32_t e = P.hist[(size_t)k * P.cap + pid];
+        float4 m = __ldg(P.S.mat + e);
+        f3 att = __ldg(P.S.mat_kind + e) == 2u ? mk3(1.0f, 1.0f, 1.0f) : mk3(m.x, m.y, m.z);
+        col = att * col;
+    }
+    return col;
+}
+
+__device__ __forceinline__ void end_path(const WaveParams& P, uint32_t pid, f3 col) { P.out[pid] = make_float4(col.x, col.y, col.z, 0.0f); }
+
+// ------------------------------------------------------------------ stage A of Scene::hit (scene.rs:19-31 + mesh.rs:233)
+// `it` = bounce iteration of the ray (number of scatters before it).  Returns the queue class of the ray.
+__device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, uint32_t pid, f3 o, f3 d, uint32_t& nan_count) {
+    float closest = 3.40282347e+38f;                                     // f32::MAX (scene.rs:21)
+    int kind = -1; uint32_t elem = 0; float t_s = 0.0f;
+    for (uint32_t i = 0; i < P.S.n_spheres; ++i) {                       // spheres first, in order (scene.rs:23-31)
+        float t, dist;
+        int r = sphere_intersect(__ldg(P.S.spheres + i), o, d, t, dist);
+        if (r < 0) { ++nan_count; end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }   // reference panics (sphere.rs:33)
+        if (r && dist < closest) { closest = dist; kind = 0; elem = i; t_s = t; }
+    }
+    for (uint32_t mi = 0; mi < P.S.n_meshes; ++mi) {                     // whole-mesh AABB pre-test (mesh.rs:233)
+        const MeshDev& M = P.S.meshes[mi];
+        if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
+        P.ray_o[pid] = make_float4(o.x, o.y, o.z, 0.0f);
+        P.ray_d[pid] = make_float4(d.x, d.y, d.z, 0.0f);
+        P.hit[pid] = make_uint4(__float_as_uint(t_s), elem, __float_as_uint(closest), (mi << 8) | (uint32_t)(kind & 0xFF));
+        return CLS_CAND;
+    }
+    if (kind == 0) {
+        if (it < P.max_depth) {                                           // depth > 0: scatter() will run (lib.rs:54)
+            P.ray_o[pid] = make_float4(o.x, o.y, o.z, 0.0f);
+            P.ray_d[pid] = make_float4(d.x, d.y, d.z, 0.0f);
+            P.hit[pid] = make_uint4(__float_as_uint(t_s), elem, 0u, 0u);
+            return __ldg(P.S.mat_kind + elem);
+        }
+        end_path(P, pid, mk3(0, 0, 0));                                   // depth exhausted -> black (lib.rs:63-66)
+        return CLS_NONE;
+    }
+    end_path(P, pid, unwind(P, sky(d), it, pid));                         // miss: sky (lib.rs:68-71)
+    return CLS_NONE;
+}
+
+// ------------------------------------------------------------------ generate (cam.rs:64-82) + stage A
+__global__ void __launch_bounds__(256) k_generate(WaveParams P) {
+    const uint32_t n_paths = P.s_count * P.paths_px;                      // multiple of 32
+    const uint32_t n_groups = n_paths >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
+    uint32_t nan_count = 0, rays = 0;
+    for (uint32_t g0 = warp * ROUNDS; g0 < n_groups; g0 += n_warps * ROUNDS) {
+        Deferred df; df.clear();
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            uint32_t g = g0 + r;
+            if (g >= n_groups) break;
+            uint32_t pid = (g << 5) + lane;
+            uint32_t s_local = pid / P.paths_px, j = pid - s_local * P.paths_px;
+            uint32_t row, col;
+            if (shard_pixel(P.sh, P.cam, j, row, col)) {
+                f3 o, d;
+                camera_ray(P.cam, row, col, key, row * P.cam.width + col, P.s_base + s_local, o, d);
+                ++rays;
+                df.set(r, stage_a(P, 0, pid, o, d, nan_count), pid);
             }
+        }
+        flush(P, 0, df);
+    }
+    for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
+    if (lane == 0) {
+        if (rays) atomicAdd(&P.ctr[0].ray_count, rays);
+        if (nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
+    }
+}
+
+// ------------------------------------------------------------------ stage B: BVH traversal with dynamic fetch
+// Resolution of a queued ray once all its meshes are done: the rest of Scene::hit + the miss arm of colorize.
+__device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_t pid, f3 d, int kind, uint32_t elem, uint32_t tri, float t) {
+    if (kind >= 0) {
+        if (it < P.max_depth) {
+            uint32_t e = kind == 0 ? elem : P.S.n_spheres + elem;
+            P.hit[pid] = make_uint4(__float_as_uint(t), e, tri, (uint32_t)kind);
+            return (int)__ldg(P.S.mat_kind + e);
+        }
+        end_path(P, pid, mk3(0, 0, 0));
+        return -1;
+    }
+    end_path(P, pid, unwind(P, sky(d), it, pid));
+    return -1;
+}
+
+#define TRACE_THREADS 128
+#define FETCH_THRESHOLD 20     // re-fill the warp when fewer lanes than this are still traversing
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t it) {
+    IterCtr* c = P.ctr + it;
+    const uint32_t n = c->cand_count;
+    if (n == 0) return;
+    if (COUNT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_CAND], (unsigned long long)n);
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const int32_t SENTINEL = 0x7FFFFFFF;
+    int32_t stack[RBRT_STACK];
+    // ---- ray state
+    bool has_ray = false;
+    uint32_t pid = 0, mi = 0;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+    float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
+    float closest = 0.0f, bt = 0.0f; int bkind = -1; uint32_t belem = 0, btri = 0;   // best over spheres + finished meshes
+    // ---- traversal state of the current mesh
+    int32_t cur = SENTINEL; int sp = 0;
+    float best_t = 0.0f, t_prune = 0.0f, t_limit = 0.0f; uint32_t best_idx = 0xFFFFFFFFu;
+    const float4* __restrict__ nodes = P.S.nodes; uint32_t tri_base = 0;
+    bool exhausted = false;                                               // warp-uniform: the queue has no more rays
+    uint32_t n_nodes = 0, n_tris = 0;
+
+    auto start_mesh = [&](const MeshDev& M) {
+        // A mesh hit only matters if its dist beats `closest` (strict <).  dist is monotone in t and ~ t*|d|;
+        // convert with a generous margin so the bound never cuts a winning hit.
+        t_limit = RBRT_T_CAP;
+        if (closest < 3.0e38f) {
+            float dl = len3(d);
+            float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+            float lim = (closest * 1.001f + 1e-5f * (omax + closest) + 1e-6f) / dl;
+            if (lim == lim) t_limit = fminf(t_limit, lim);
+        }
+        t_prune = t_limit; best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;     // min_param init (triangle.rs:398)
+        nodes = P.S.nodes + 4 * (size_t)M.node_base; tri_base = M.tri_base;
+        sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
+    };
+
+    for (;;) {
+        // ---- lanes whose traversal ended: close the mesh, move to the next one or resolve the ray
+        bool want_fetch = (cur == SENTINEL);
+        int done_kind = -1;
+        if (want_fetch && has_ray) {
+            if (best_idx != 0xFFFFFFFFu) {
+                f3 p = o + best_t * d;                                    // ray.point_at (mesh.rs:247)
+                float dist = len3(o - p);                                 // mesh.rs:248
+                if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) {   // mesh.rs:249 + scene.rs:36
+                    closest = dist; bkind = 1; belem = mi; btri = best_idx; bt = best_t;
+                }
+            }
+            while (++mi < P.S.n_meshes) {                                 // later meshes, in order (scene.rs:33-41)
+                const MeshDev& M = P.S.meshes[mi];
+                if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
+                start_mesh(M); want_fetch = false; break;
+            }
+            if (want_fetch) { done_kind = resolve(P, it, pid, d, bkind, belem, btri, bt); has_ray = false; }
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            uint32_t slot = warp_append(&c->mat_count[k], mat_kind == k);
-            if (mat_kind == k) P.matq[k][slot] = i;
+            uint32_t slot = warp_append(&c->mat_count[k], done_kind == k);
+            if (done_kind == k) P.matq[it & 1][k][slot] = pid;
+        }
+        // ---- dynamic fetch: idle lanes take the next rays of the queue (one atomic per warp)
+        if (!exhausted) {
+            uint32_t m = __ballot_sync(FULL_MASK, want_fetch);
+            if (m) {
+                uint32_t base = warp_grab(&c->cand_head, __popc(m));
+                if (want_fetch) {
+                    uint32_t qi = base + __popc(m & lt);
+                    if (qi < n) {
+                        pid = P.candq[qi];
+                        float4 a = P.ray_o[pid], b = P.ray_d[pid];
+                        uint4 h = P.hit[pid];
+                        o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
+                        bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
+                        bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
+                        const float big = 1e30f;
+                        idx = fabsf(d.x) > 1e-30f ? __fdividef(1.0f, d.x) : copysignf(big, d.x);
+                        idy = fabsf(d.y) > 1e-30f ? __fdividef(1.0f, d.y) : copysignf(big, d.y);
+                        idz = fabsf(d.z) > 1e-30f ? __fdividef(1.0f, d.z) : copysignf(big, d.z);
+                        oox = o.x * idx; ooy = o.y * idy; ooz = o.z * idz;
+                        has_ray = true;
+                        start_mesh(P.S.meshes[mi]);                       // stage A found this mesh's box hit
+                    }
+                }
+                if (base + __popc(m) >= n) exhausted = true;
+            }
+        }
+        uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
+        if (active == 0) { if (exhausted) break; continue; }
+        const int threshold = exhausted ? 1 : FETCH_THRESHOLD;
+        // ---- while-while traversal: every lane descends to its next leaf, then the leaves are processed together
+        for (;;) {
+            while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node
+                const float4* nd = nodes + 4 * (size_t)cur;
+                float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                if (COUNT) ++n_nodes;
+                float c0lox = __fmaf_rn(n0.x, idx, -oox), c0hix = __fmaf_rn(n0.y, idx, -oox);
+                float c0loy = __fmaf_rn(n0.z, idy, -ooy), c0hiy = __fmaf_rn(n0.w, idy, -ooy);
+                float c0loz = __fmaf_rn(n2.x, idz, -ooz), c0hiz = __fmaf_rn(n2.y, idz, -ooz);
+                float c1lox = __fmaf_rn(n1.x, idx, -oox), c1hix = __fmaf_rn(n1.y, idx, -oox);
+                float c1loy = __fmaf_rn(n1.z, idy, -ooy), c1hiy = __fmaf_rn(n1.w, idy, -ooy);
+                float c1loz = __fmaf_rn(n2.z, idz, -ooz), c1hiz = __fmaf_rn(n2.w, idz, -ooz);
+                float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+                float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), t_prune));
+                float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+                float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), t_prune));
+                bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+                int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    bool swap = t1n < t0n;
+                    stack[sp++] = swap ? r0 : r1;
+                    cur = swap ? r1 : r0;
+                } else if (h0) cur = r0;
+                else if (h1) cur = r1;
+                else cur = stack[--sp];
+            }
+            if (cur < 0) {                                                // leaf: <= 8 contiguous triangles
+                uint32_t code = (uint32_t)(~cur);
+                uint32_t first = code >> 3, count = (code & 7) + 1;
+                for (uint32_t k = 0; k < count; ++k) {
+                    f3 v0, e1, e2; uint32_t orig; float t;
+                    load_tri(P.S.tris, tri_base + first + k, v0, e1, e2, orig);
+                    if (tri_intersect(v0, e1, e2, o, d, t)) {
+                        keep_min(t, orig, best_t, best_idx);
+                        t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
+                    }
+                }
+                if (COUNT) n_tris += count;
+                cur = stack[--sp];
+            }
+            if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
         }
     }
-    if (nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
     if (COUNT) {
-        atomicAdd(&P.stats[ST_NODES], (unsigned long long)cnt.nodes);
-        atomicAdd(&P.stats[ST_TRIS], (unsigned long long)cnt.tris);
+        for (int off = 16; off; off >>= 1) { n_nodes += __shfl_down_sync(FULL_MASK, n_nodes, off); n_tris += __shfl_down_sync(FULL_MASK, n_tris, off); }
+        if (lane == 0) { atomicAdd(&P.stats[ST_NODES], (unsigned long long)n_nodes); atomicAdd(&P.stats[ST_TRIS], (unsigned long long)n_tris); }
     }
 }
 
-// ------------------------------------------------------------------ shade (lib.rs:54-62 + the scatter impls)
+// Brute-force stage B (RBRT_TRACE_BRUTE): the reference's own every-triangle loop, no dynamic fetch.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) {
+    IterCtr* c = P.ctr + it;
+    const uint32_t n = c->cand_count;
+    if (n == 0) return;
+    if (COUNT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_CAND], (unsigned long long)n);
+    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    for (;;) {
+        uint32_t base = warp_grab(&c->cand_head, 32u);
+        if (base >= n) break;
+        uint32_t qi = base + (threadIdx.x & 31);
+        int done_kind = -1; uint32_t pid = 0;
+        if (qi < n) {
+            pid = P.candq[qi];
+            float4 a = P.ray_o[pid], b = P.ray_d[pid];
+            uint4 h = P.hit[pid];
+            f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+            float bt = __uint_as_float(h.x), closest = __uint_as_float(h.z);
+            uint32_t belem = h.y, btri = 0; int bkind = (h.w & 0xFFu) == 0u ? 0 : -1;
+            for (uint32_t mi = h.w >> 8; mi < P.S.n_meshes; ++mi) {
+                const MeshDev& M = P.S.meshes[mi];
+                if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
+                float t; uint32_t ti;
+                if (!mesh_closest_brute(P.S, M, o, d, t, ti, COUNT ? &cnt : nullptr)) continue;
+                f3 p = o + t * d;
+                float dist = len3(o - p);
+                if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) { closest = dist; bkind = 1; belem = mi; btri = ti; bt = t; }
+            }
+            done_kind = resolve(P, it, pid, d, bkind, belem, btri, bt);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint32_t slot = warp_append(&c->mat_count[k], done_kind == k);
+            if (done_kind == k) P.matq[it & 1][k][slot] = pid;
+        }
+    }
+    if (COUNT) { atomicAdd(&P.stats[ST_NODES], (unsigned long long)cnt.nodes); atomicAdd(&P.stats[ST_TRIS], (unsigned long long)cnt.tris); }
+}
+
+// ------------------------------------------------------------------ shade (lib.rs:54-62 + the scatter impls) + stage A
 __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n0 = c->mat_count[0], n1 = c->mat_count[1], n2 = c->mat_count[2];
-    // virtual index space: each material's run is padded to a multiple of 32 so a warp never mixes kinds
+    // virtual index space: each material's run is padded to a multiple of 32 so a warp round never mixes kinds
     const uint32_t a0 = (n0 + 31u) & ~31u, a1 = a0 + ((n1 + 31u) & ~31u), total = a1 + ((n2 + 31u) & ~31u);
     if (total == 0) return;
-    const float4* __restrict__ qo = P.q_o[it & 1];
-    const float4* __restrict__ qd = P.q_d[it & 1];
-    float4* __restrict__ no = P.q_o[(it + 1) & 1];
-    float4* __restrict__ nd = P.q_d[(it + 1) & 1];
+    const uint32_t lane = threadIdx.x & 31;
     RngKey key; key.k0 = P.key0; key.k1 = P.key1;
+    uint32_t nan_count = 0, rays = 0;
     for (;;) {
-        uint32_t base = warp_grab(&c->shade_head);
+        uint32_t base = warp_grab(&c->shade_head, 32u * ROUNDS);
         if (base >= total) break;
-        uint32_t w = base + (threadIdx.x & 31);
-        uint32_t kind, j, nk;
-        if (w < a0) { kind = 0; j = w; nk = n0; }
-        else if (w < a1) { kind = 1; j = w - a0; nk = n1; }
-        else { kind = 2; j = w - a1; nk = n2; }
-        bool active = j < nk;
-        bool cont = false;
-        f3 point = mk3(0, 0, 0), out_d = mk3(0, 0, 0);
-        uint32_t pid = 0;
-        if (active) {
-            uint32_t i = P.matq[kind][j];
-            float4 a = qo[i], b = qd[i];
-            uint4 h = P.hit[i];
+        Deferred df; df.clear();
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            uint32_t w = base + 32u * r + lane;
+            if (w >= total) break;
+            uint32_t kind, j, nk;
+            if (w < a0) { kind = 0; j = w; nk = n0; }
+            else if (w < a1) { kind = 1; j = w - a0; nk = n1; }
+            else { kind = 2; j = w - a1; nk = n2; }
+            if (j >= nk) continue;
+            uint32_t pid = P.matq[it & 1][kind][j];
+            float4 a = P.ray_o[pid], b = P.ray_d[pid];
+            uint4 h = P.hit[pid];
             f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
-            pid = __float_as_uint(a.w);
             float t = __uint_as_float(h.x);
             uint32_t elem = h.y;
-            point = o + t * d;                                            // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
+            f3 point = o + t * d;                                         // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
             f3 normal;
             if (h.w == 0u) {                                              // sphere: p - c, un-normalised (sphere.rs:56)
                 float4 s = __ldg(P.S.spheres + elem);
@@ -160,16 +398,30 @@ __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
             uint32_t s_local = pid / P.paths_px, jp = pid - s_local * P.paths_px;
             uint32_t row, col;
             shard_pixel(P.sh, P.cam, jp, row, col);
-            cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam.width + col,
-                           P.s_base + s_local, it + 1, out_d);
-            if (cont) P.hist[(size_t)it * P.cap + pid] = (uint16_t)elem;
+            f3 out_d;
+            bool cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam.width + col,
+                                P.s_base + s_local, it + 1, out_d);
+            if (cont) {
+                P.hist[(size_t)it * P.cap + pid] = (uint16_t)elem;
+                ++rays;
+                df.set(r, stage_a(P, it + 1, pid, point, out_d, nan_count), pid);
+            } else end_path(P, pid, mk3(0, 0, 0));                        // absorbed (metal.rs:24) -> black
         }
-        uint32_t slot = warp_append(&P.ctr[it + 1].ray_count, cont);
-        if (cont) {
-            no[slot] = make_float4(point.x, point.y, point.z, __uint_as_float(pid));
-            nd[slot] = make_float4(out_d.x, out_d.y, out_d.z, 0.0f);
-        }
+        flush(P, it + 1, df);
     }
+    for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
+    if (lane == 0) {
+        if (rays) atomicAdd(&P.ctr[it + 1].ray_count, rays);
+        if (nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
+    }
+}
+
+// statistics: rays = sum over iterations of ray_count (one tiny launch per batch)
+__global__ void k_sum_rays(WaveParams P) {
+    unsigned long long r = 0;
+    for (uint32_t it = threadIdx.x; it <= P.max_depth; it += blockDim.x) r += P.ctr[it].ray_count;
+    for (int off = 16; off; off >>= 1) r += __shfl_down_sync(FULL_MASK, r, off);
+    if ((threadIdx.x & 31) == 0 && r) atomicAdd(&P.stats[ST_RAYS], r);
 }
 
 // ------------------------------------------------------------------ accumulate (lib.rs:95-100)
@@ -258,8 +510,8 @@ static CamDev make_cam(const rbrt_camera& c) {
 }
 
 void free_wave_buffers(WaveBuffers& wb) {
-    for (int i = 0; i < 2; ++i) { cudaFree(wb.q_o[i]); cudaFree(wb.q_d[i]); }
-    cudaFree(wb.hit); for (int i = 0; i < 3; ++i) cudaFree(wb.matq[i]);
+    cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.candq);
+    cudaFree(wb.hit); for (int i = 0; i < 6; ++i) cudaFree(wb.matq[i / 3][i % 3]);
     cudaFree(wb.out); cudaFree(wb.hist); cudaFree(wb.ctr); cudaFree(wb.stats); cudaFree(wb.accum);
     cudaFree(wb.rgb); cudaFree(wb.hdr);
     for (cudaEvent_t e : wb.ev) cudaEventDestroy(e);
@@ -276,9 +528,10 @@ static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
     free_wave_buffers(wb);
     wb.accum = accum; wb.accum_px = accum_px; wb.rgb = rgb; wb.hdr = hdr; wb.out_px = out_px; wb.ev.swap(ev);
     size_t b = 0;
-    for (int i = 0; i < 2; ++i) { CKR(cudaMalloc(&wb.q_o[i], 16ull * cap)); CKR(cudaMalloc(&wb.q_d[i], 16ull * cap)); b += 32ull * cap; }
+    CKR(cudaMalloc(&wb.ray_o, 16ull * cap)); CKR(cudaMalloc(&wb.ray_d, 16ull * cap)); b += 32ull * cap;
+    CKR(cudaMalloc(&wb.candq, 4ull * cap)); b += 4ull * cap;
     CKR(cudaMalloc(&wb.hit, 16ull * cap)); b += 16ull * cap;
-    for (int i = 0; i < 3; ++i) { CKR(cudaMalloc(&wb.matq[i], 4ull * cap)); b += 4ull * cap; }
+    for (int i = 0; i < 6; ++i) { CKR(cudaMalloc(&wb.matq[i / 3][i % 3], 4ull * cap)); b += 4ull * cap; }
     CKR(cudaMalloc(&wb.out, 16ull * cap)); b += 16ull * cap;
     CKR(cudaMalloc(&wb.hist, 2ull * cap * depth)); b += 2ull * cap * depth;
     CKR(cudaMalloc(&wb.ctr, sizeof(IterCtr) * (depth + 2)));
@@ -320,13 +573,13 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is
         // bounded below by its slowest ray, so the ~45 sparsely populated tail iterations cost the same for a
         // small batch as for a large one: the default is therefore "as many paths as fit" — up to 2^27 paths
-        // (108 + 2*max_depth bytes of wavefront state each: 27.9 GB at depth 50) and at most half of the free HBM.
+        // (92 + 2*max_depth bytes of wavefront state each: 25.8 GB at depth 50) and at most half of the free HBM.
         uint32_t target = o.batch_paths;
         if (!target) {
             size_t free_b = 0, total_b = 0;
             CKR(cudaMemGetInfo(&free_b, &total_b));
             free_b += wb.bytes;                                           // what a re-allocation would release first
-            uint64_t per_path = 108ull + 2ull * max_depth;
+            uint64_t per_path = 92ull + 2ull * max_depth;
             uint64_t fit = (free_b / 2) / per_path;
             target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
         }
@@ -340,10 +593,13 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         wp.S = sc.dev; wp.cam = make_cam(cam); wp.sh = sh;
         wp.key0 = (uint32_t)o.seed; wp.key1 = (uint32_t)(o.seed >> 32);
         wp.cap = wb.cap; wp.paths_px = P; wp.max_depth = max_depth;
-        for (int i = 0; i < 2; ++i) { wp.q_o[i] = wb.q_o[i]; wp.q_d[i] = wb.q_d[i]; }
-        wp.hit = wb.hit; for (int i = 0; i < 3; ++i) wp.matq[i] = wb.matq[i];
+        wp.ray_o = wb.ray_o; wp.ray_d = wb.ray_d; wp.candq = wb.candq;
+        wp.hit = wb.hit; for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
-        const int grid = sc.sm_count * 8;
+        const int grid = sc.sm_count * 8;                                  // producers / brute: 256-thread blocks
+        int per_sm = 0;                                                   // k_trace: persistent blocks, exactly one resident wave
+        CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, TRACE_THREADS, 0));
+        const int grid_trace = sc.sm_count * (per_sm > 0 ? per_sm : 4);
         const bool brute = o.trace_mode == RBRT_TRACE_BRUTE;
         const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
         const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
@@ -355,17 +611,17 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         for (uint32_t s_base = sh.s0; s_base < sh.s1; s_base += S_b) {
             wp.s_base = s_base; wp.s_count = (sh.s1 - s_base < S_b) ? sh.s1 - s_base : S_b;
             CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
-            CKR(cudaMemsetAsync(wb.out, 0, 16ull * wp.s_count * P, st));
             k_generate<<<grid, 256, 0, st>>>(wp); ++launches;
             for (uint32_t it = 0; it <= max_depth; ++it) {
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
-                if (brute) { if (count) k_trace<true, true><<<grid, 256, 0, st>>>(wp, it); else k_trace<true, false><<<grid, 256, 0, st>>>(wp, it); }
-                else { if (count) k_trace<false, true><<<grid, 256, 0, st>>>(wp, it); else k_trace<false, false><<<grid, 256, 0, st>>>(wp, it); }
+                if (brute) { if (count) k_trace_brute<true><<<grid, 256, 0, st>>>(wp, it); else k_trace_brute<false><<<grid, 256, 0, st>>>(wp, it); }
+                else { if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it); else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it); }
                 ++launches; ++iterations;
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (it < max_depth) { k_shade<<<grid, 256, 0, st>>>(wp, it); ++launches; }
             }
             k_accumulate<<<(P + 255) / 256, 256, 0, st>>>(wp, d_accum); ++launches;
+            k_sum_rays<<<1, 64, 0, st>>>(wp); ++launches;
             CKR(cudaGetLastError());
         }
     }
@@ -373,9 +629,9 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     if (stats) {
         CKR(cudaEventSynchronize(ev1));
         float ms = 0; CKR(cudaEventElapsedTime(&ms, ev0, ev1));
-        unsigned long long h[ST_COUNT] = {0, 0, 0, 0};
+        unsigned long long h[ST_COUNT] = {0, 0, 0, 0, 0};
         if (wb.stats && P && sh.s1 > sh.s0) CKR(cudaMemcpy(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost));
-        stats->rays = h[ST_RAYS]; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS];
+        stats->rays = h[ST_RAYS]; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS]; stats->traversed_rays = h[ST_CAND];
         uint64_t valid_px = 0;
         for (uint32_t tj = 0; tj < sh.tiles_mine; ++tj) {
             uint32_t T = tj * sh.count + sh.rank, ty = T / sh.tiles_x, tx = T - ty * sh.tiles_x;
@@ -396,8 +652,8 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 size_t per_batch = max_depth + 1, first = 2 * (iterations - per_batch);
                 for (uint32_t it = 0; it <= max_depth; ++it) {
                     float t = 0; cudaEventElapsedTime(&t, wb.ev[first + 2 * it], wb.ev[first + 2 * it + 1]);
-                    fprintf(stderr, "it %2u rays %9u  lambert %9u metal %9u glass %9u  trace %8.3f ms\n", it, hc[it].ray_count,
-                            hc[it].mat_count[0], hc[it].mat_count[1], hc[it].mat_count[2], t);
+                    fprintf(stderr, "it %2u rays %9u traversed %9u  lambert %9u metal %9u glass %9u  trace %8.3f ms\n", it, hc[it].ray_count,
+                            hc[it].cand_count, hc[it].mat_count[0], hc[it].mat_count[1], hc[it].mat_count[2], t);
                 }
             }
         }
