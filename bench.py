@@ -15,8 +15,8 @@ path) — the reference's `render_scene(cam, spp, scene)` (lib.rs:75-124).  Rays
              triangle soup from pinned host memory (rbrt_gpu_scene_create: H2D + LBVH build), renders
              (rbrt_gpu_render / the multi-rank building blocks) and copies the RGB8 image back to the host.
   roofline   the trace kernel (BVH traversal + intersection tests): algorithmic bytes per step from an
-             instrumented counting pass (64 B per node visit, 48 B per triangle test, 16 B per sphere test, 24 B
-             per mesh-AABB test, 52 B of queue traffic per ray) / the summed CUDA-event durations of that kernel's
+             instrumented counting pass (64 B per node visit, 48 B per triangle test, 72 B of queue traffic per
+             traversed ray) / the summed CUDA-event durations of that kernel's
              launches inside the timed region, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline / --impl reference
              the CPU oracle (C++/AVX restatement of the reference; the Rust reference cannot be built here) on all
@@ -155,15 +155,16 @@ def peaks():
 
 
 def algorithmic_bytes(st, n_spheres, n_meshes):
-    """bytes/step = 64 V + 48 T + 16 S + 24 M + 52 R (Q = 32 B ray read + 16 B hit/radiance write
-    + 4 B material-queue index, the trace kernel's own queue traffic)."""
-    R = st["rays"]
-    return 64 * st["node_visits"] + 48 * st["tri_tests"] + 16 * n_spheres * R + 24 * n_meshes * R + 52 * R
+    """Trace kernel (stage B: LBVH traversal of the rays that entered a mesh AABB), DESIGN.md section 4:
+    bytes/step = 64 V + 48 T + 72 C   (V node visits x 64-B node, T triangle tests x 48-B record, C traversed rays x
+    72 B of queue traffic: 4 B queue index + 32 B ray + 16 B sphere pre-result read, 16 B hit record + 4 B material-queue
+    index written).  The sphere and mesh-AABB tests of SURVEY.md section 8(d) (16 S + 24 M per ray) now run in the
+    producing kernels (k_generate / k_shade) and are not charged to this kernel."""
+    return 64 * st["node_visits"] + 48 * st["tri_tests"] + 72 * st["traversed_rays"]
 
 
 def algorithmic_flops(st, n_spheres, n_meshes):
-    R = st["rays"]
-    return 48 * st["node_visits"] + 46 * st["tri_tests"] + 32 * n_spheres * R + 22 * n_meshes * R
+    return 48 * st["node_visits"] + 46 * st["tri_tests"]
 
 
 # ------------------------------------------------------------------------------------------- CPU legs
@@ -312,14 +313,14 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([sum(s["rays"] for s in stats), sum(s["paths"] for s in stats), sum(s["launches"] for s in stats) + (args.steps if rank == 0 else 0),
-                        counts["node_visits"], counts["tri_tests"], counts["rays"]], dtype=torch.float64, device="cuda")
+                        counts["node_visits"], counts["tri_tests"], counts["rays"], counts["traversed_rays"]], dtype=torch.float64, device="cuda")
     trace_ms = torch.tensor([sum(s["ms_trace"] for s in stats)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         dist.all_reduce(trace_ms, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    rays, paths, launches, V, T, Rc = (float(x) for x in agg.tolist())
+    rays, paths, launches, V, T, Rc, Cc = (float(x) for x in agg.tolist())
     trace_ms = float(trace_ms.item())
     clocks = clk.summary()
 
@@ -330,18 +331,21 @@ def run_gpu(args):
     d2h = H * W * 3
 
     def step_e2e():
+        t_a = time.perf_counter()
         sc = make_scene(spheres, meshes, pinned)
         try:
+            h = sc.handle()                                   # rbrt_gpu_scene_create: H2D of the triangle soup + LBVH build
+            t_b = time.perf_counter()
+            st = _abi.StatsC()
             if world == 1:
                 out = np.frombuffer(host_rgb.numpy(), np.uint8)
-                st = _abi.StatsC()
-                _abi.check(lib.rbrt_gpu_render(sc.handle(), cam_c, spp, make_opts(seed=SEED), out.ctypes.data, st))
-                return st.rays
-            st = _abi.StatsC()
-            step_resident(sc.handle(), {}, st)
-            if rank == 0:
-                host_rgb.copy_(rgb, non_blocking=False)
-            return st.rays
+                _abi.check(lib.rbrt_gpu_render(h, cam_c, spp, make_opts(seed=SEED), out.ctypes.data, st))
+            else:
+                step_resident(h, {}, st)
+                if rank == 0:
+                    host_rgb.copy_(rgb, non_blocking=False)
+            t_c = time.perf_counter()
+            return st.rays, (t_b - t_a) * 1e3, (t_c - t_b) * 1e3
         finally:
             sc.close()
 
@@ -353,7 +357,9 @@ def run_gpu(args):
     e0.record(stream)
     e_rays = 0
     for _ in range(e_steps):
-        e_rays += step_e2e()
+        r_, ms_create, ms_render = step_e2e()
+        e_rays += r_
+        print(f"[e2e rank {rank}] scene_create {ms_create:.1f} ms, render+readback {ms_render:.1f} ms", file=sys.stderr)
     e1.record(stream)
     barrier()
     e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # host-side work (malloc, sync copies) counts too
@@ -371,7 +377,7 @@ def run_gpu(args):
 
     peak, peak_src = peaks()
     ns, nm = len(spheres), len(meshes)
-    cstep = {"rays": Rc, "node_visits": V, "tri_tests": T}
+    cstep = {"rays": Rc, "node_visits": V, "tri_tests": T, "traversed_rays": Cc}
     bytes_step = algorithmic_bytes(cstep, ns, nm)
     flops_step = algorithmic_flops(cstep, ns, nm)
     trace_ms_step = trace_ms / args.steps          # max over ranks of the per-rank sum; ranks run concurrently
@@ -390,10 +396,11 @@ def run_gpu(args):
         "e2e": {"value": e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
                 "ms_per_step": float(te.item()) / e_steps, "includes": "scene upload from pinned host memory + LBVH build + render + RGB8 image to host, per step"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_trace (BVH traversal + Moeller-Trumbore / sphere / mesh-AABB tests)",
+        "roofline": {"bound": "hbm", "kernel": "k_trace (stage B: persistent LBVH traversal with dynamic fetch + Moeller-Trumbore tests)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_ray": bytes_step / max(Rc, 1),
-                     "node_visits_per_ray": V / max(Rc, 1), "tri_tests_per_ray": T / max(Rc, 1),
+                     "peak_source": peak_src, "algorithmic_bytes_per_traversed_ray": bytes_step / max(Cc, 1),
+                     "traversed_rays_per_step": Cc, "traversed_share_of_rays": Cc / max(Rc, 1),
+                     "node_visits_per_traversed_ray": V / max(Cc, 1), "tri_tests_per_traversed_ray": T / max(Cc, 1),
                      "trace_ms_per_step": trace_ms_step, "trace_share_of_step": trace_ms_step / (ms / args.steps),
                      "fp32_achieved_tflops": flops_step / max(world, 1) / (trace_ms_step / 1e3) / 1e12 if trace_ms_step > 0 else None,
                      "note": "achieved = per-GPU algorithmic bytes of all trace launches of a step / their summed CUDA-event time (per-launch "

@@ -217,6 +217,10 @@ int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t 
 int rbrt_gpu_primary_rays(const rbrt_camera* cam, uint64_t seed, uint32_t sample_idx,
                           rbrt_ray* rays_out);
 
+/* The wavefront state (ray / hit / queue buffers, tens of GB at full batch size) is pooled per device and kept
+ * between renders and across scenes; this releases it.  Renders on one device must not run concurrently. */
+int rbrt_gpu_release_cache(void);
+
 /* Thread-local message of the last failing call on this thread. */
 const char* rbrt_last_error(void);
 

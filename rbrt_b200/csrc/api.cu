@@ -53,7 +53,6 @@ static int dev_alloc(Scene* sc, T** p, size_t count) {
 
 static void destroy_scene(Scene* sc) {
     if (!sc) return;
-    free_wave_buffers(sc->wb);
     for (void* p : sc->allocs) cudaFree(p);
     delete sc;
 }
@@ -229,6 +228,11 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
     return RBRT_OK;
 }
 
+int rbrt_gpu_release_cache(void) {
+    release_device_wave_buffers();
+    return RBRT_OK;
+}
+
 int rbrt_gpu_finalize_device(const void* d_accum, uint32_t W, uint32_t H, uint32_t spp, void* d_rgb, void* d_hdr, void* stream) {
     if (!d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
     int rc = ensure_device();
@@ -244,7 +248,7 @@ static int render_host(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t
     double t0 = now_ms();
     size_t n = (size_t)cam->img_width_pix * cam->img_height_pix;
     if (!n || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
-    WaveBuffers& wb = sc.wb;
+    WaveBuffers& wb = device_wave_buffers(sc.device);
     if (wb.accum_px < n) { cudaFree(wb.accum); wb.accum = nullptr; wb.accum_px = 0; CKA(cudaMalloc(&wb.accum, 16 * n)); wb.accum_px = n; }
     if (wb.out_px < n) {
         cudaFree(wb.rgb); cudaFree(wb.hdr); wb.rgb = nullptr; wb.hdr = nullptr; wb.out_px = 0;

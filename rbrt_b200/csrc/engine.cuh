@@ -48,7 +48,6 @@ struct Scene {
     std::vector<MeshDev> meshes_h;
     std::vector<void*> allocs;   // every cudaMalloc owned by the scene
     rbrt_scene_info info{};
-    mutable WaveBuffers wb;      // lazily sized by the first render (handle is single-threaded)
     int sm_count = 148;
 };
 
@@ -79,5 +78,9 @@ int trace_rays_device(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, uint3
                       unsigned long long* d_stats, cudaStream_t st);
 int primary_rays_device(const rbrt_camera& cam, uint64_t seed, uint32_t sample, rbrt_ray* d_rays, cudaStream_t st);
 void free_wave_buffers(WaveBuffers& wb);
+// Per-device pool of wavefront state, shared by every scene of the process and kept between renders (allocating and
+// freeing tens of GB per render would cost more than the render).  The library is single-threaded per device.
+WaveBuffers& device_wave_buffers(int device);
+void release_device_wave_buffers();
 
 }  // namespace rbrt

@@ -198,6 +198,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
     const float4* __restrict__ nodes = P.S.nodes; uint32_t tri_base = 0;
     bool exhausted = false;                                               // warp-uniform: the queue has no more rays
     uint32_t n_nodes = 0, n_tris = 0;
+    // With few rays (tail iterations) a warp must not take 32 of them while others idle: every ray is a
+    // latency-bound chain, so spread them over all resident warps.
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t quota = min(32u, max(1u, (n + n_warps - 1) / n_warps));
 
     auto start_mesh = [&](const MeshDev& M) {
         // A mesh hit only matters if its dist beats `closest` (strict <).  dist is monotone in t and ~ t*|d|;
@@ -241,6 +245,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
         // ---- dynamic fetch: idle lanes take the next rays of the queue (one atomic per warp)
         if (!exhausted) {
             uint32_t m = __ballot_sync(FULL_MASK, want_fetch);
+            if (quota < 32u) {                                            // keep at most `quota` lanes of this warp busy
+                uint32_t busy = 32u - __popc(m);
+                uint32_t allow = busy < quota ? quota - busy : 0u;
+                if (allow == 0u) m = 0u;
+                else if (allow < (uint32_t)__popc(m)) m &= (1u << __fns(m, 0, allow + 1)) - 1u;
+                want_fetch = want_fetch && ((m >> lane) & 1u);
+            }
             if (m) {
                 uint32_t base = warp_grab(&c->cand_head, __popc(m));
                 if (want_fetch) {
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
         }
         uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
         if (active == 0) { if (exhausted) break; continue; }
-        const int threshold = exhausted ? 1 : FETCH_THRESHOLD;
+        const int threshold = exhausted ? 1 : min(FETCH_THRESHOLD, (int)quota);
         // ---- while-while traversal: every lane descends to its next leaf, then the leaves are processed together
         for (;;) {
             while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node
@@ -366,14 +377,16 @@ __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
     const uint32_t lane = threadIdx.x & 31;
     RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     uint32_t nan_count = 0, rays = 0;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t rounds = min((uint32_t)ROUNDS, max(1u, (total / 32u + n_warps - 1) / n_warps));   // tail iterations: spread the work
     for (;;) {
-        uint32_t base = warp_grab(&c->shade_head, 32u * ROUNDS);
+        uint32_t base = warp_grab(&c->shade_head, 32u * rounds);
         if (base >= total) break;
         Deferred df; df.clear();
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             uint32_t w = base + 32u * r + lane;
-            if (w >= total) break;
+            if ((uint32_t)r >= rounds || w >= total) break;
             uint32_t kind, j, nk;
             if (w < a0) { kind = 0; j = w; nk = n0; }
             else if (w < a1) { kind = 1; j = w - a0; nk = n1; }
@@ -509,6 +522,14 @@ static CamDev make_cam(const rbrt_camera& c) {
     return d;
 }
 
+static WaveBuffers g_wave[64];
+WaveBuffers& device_wave_buffers(int device) { return g_wave[(device >= 0 && device < 64) ? device : 0]; }
+void release_device_wave_buffers() {
+    int cur = 0; cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) if (g_wave[d].cap || g_wave[d].accum || g_wave[d].rgb) { cudaSetDevice(d); free_wave_buffers(g_wave[d]); }
+    cudaSetDevice(cur);
+}
+
 void free_wave_buffers(WaveBuffers& wb) {
     cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.candq);
     cudaFree(wb.hit); for (int i = 0; i < 6; ++i) cudaFree(wb.matq[i / 3][i % 3]);
@@ -567,7 +588,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     CKR(cudaEventCreate(&ev0)); CKR(cudaEventCreate(&ev1));
     CKR(cudaMemsetAsync(d_accum, 0, 16ull * W * H, st));
     uint32_t launches = 0, iterations = 0;
-    WaveBuffers& wb = sc.wb;
+    WaveBuffers& wb = device_wave_buffers(sc.device);
     CKR(cudaEventRecord(ev0, st));
     if (P && sh.s1 > sh.s0) {
         // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is
