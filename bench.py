@@ -431,8 +431,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     # exactly ONE line goes to stdout (the JSON); the host mirror's progress prints (lib.rs:80,114, mesh.rs:115) go to stderr
+    # (NCCL and the host mirror also write to fd 1 from C: redirect the descriptor itself, keep a private duplicate for the JSON)
     global _STDOUT
-    _STDOUT, sys.stdout = sys.stdout, sys.stderr
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -94,7 +94,8 @@ enum { RBRT_SHARD_NONE = 0, RBRT_SHARD_TILES = 1, RBRT_SHARD_SAMPLES = 2 };
 enum { RBRT_TRACE_BVH = 0, RBRT_TRACE_BRUTE = 1 };
 enum {
     RBRT_OPT_COUNT_VISITS = 1,   /* fill rbrt_stats.node_visits / tri_tests (instrumented kernels, slower) */
-    RBRT_OPT_TIME_KERNELS = 2    /* bracket every trace launch with CUDA events -> rbrt_stats.ms_trace */
+    RBRT_OPT_TIME_KERNELS = 2,   /* bracket every trace launch with CUDA events -> rbrt_stats.ms_trace */
+    RBRT_OPT_NO_TAIL_KERNEL = 4  /* run all 51 bounce iterations as wavefront launches (no single-launch tail) */
 };
 
 typedef struct rbrt_scene_opts {

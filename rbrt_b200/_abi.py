@@ -80,7 +80,7 @@ HIT_DTYPE = [("kind", "<i4"), ("elem_idx", "<u4"), ("tri_idx", "<u4"), ("t", "<f
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE = 0, 1
-OPT_COUNT_VISITS, OPT_TIME_KERNELS = 1, 2
+OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL = 1, 2, 4
 HIT_NONE, HIT_SPHERE, HIT_MESH = -1, 0, 1
 E_INVALID, E_CUDA, E_NODEVICE = 1, 2, 3
 

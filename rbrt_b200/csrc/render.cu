@@ -181,7 +181,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n = c->cand_count;
-    if (n == 0) return;
+    if (n == 0 || P.ctr[0].pad) return;
     if (COUNT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_CAND], (unsigned long long)n);
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const int32_t SENTINEL = 0x7FFFFFFF;
@@ -327,12 +327,45 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
     }
 }
 
+// One queued ray, start to finish, by one lane (no dynamic fetch): the rest of Scene::hit for the meshes from the
+// first one whose box it entered.  Used by the brute-force integrator and by the tail kernel.  Returns the
+// material kind to shade, or -1 when the path ended.
+template <bool BRUTE>
+__device__ __forceinline__ int process_candidate(const WaveParams& P, uint32_t it, uint32_t pid, TraceCounters* cnt) {
+    float4 a = P.ray_o[pid], b = P.ray_d[pid];
+    uint4 h = P.hit[pid];
+    f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+    float bt = __uint_as_float(h.x), closest = __uint_as_float(h.z);
+    uint32_t belem = h.y, btri = 0; int bkind = (h.w & 0xFFu) == 0u ? 0 : -1;
+    for (uint32_t mi = h.w >> 8; mi < P.S.n_meshes; ++mi) {
+        const MeshDev& M = P.S.meshes[mi];
+        if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
+        float t; uint32_t ti; bool ok;
+        if (BRUTE) ok = mesh_closest_brute(P.S, M, o, d, t, ti, cnt);
+        else {
+            float t_limit = RBRT_T_CAP;
+            if (closest < 3.0e38f) {
+                float dl = len3(d);
+                float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+                float lim = (closest * 1.001f + 1e-5f * (omax + closest) + 1e-6f) / dl;
+                if (lim == lim) t_limit = fminf(t_limit, lim);
+            }
+            ok = mesh_closest_bvh(P.S, M, o, d, t_limit, t, ti, cnt);
+        }
+        if (!ok) continue;
+        f3 p = o + t * d;
+        float dist = len3(o - p);
+        if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) { closest = dist; bkind = 1; belem = mi; btri = ti; bt = t; }
+    }
+    return resolve(P, it, pid, d, bkind, belem, btri, bt);
+}
+
 // Brute-force stage B (RBRT_TRACE_BRUTE): the reference's own every-triangle loop, no dynamic fetch.
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n = c->cand_count;
-    if (n == 0) return;
+    if (n == 0 || P.ctr[0].pad) return;
     if (COUNT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_CAND], (unsigned long long)n);
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     for (;;) {
@@ -340,24 +373,7 @@ __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) 
         if (base >= n) break;
         uint32_t qi = base + (threadIdx.x & 31);
         int done_kind = -1; uint32_t pid = 0;
-        if (qi < n) {
-            pid = P.candq[qi];
-            float4 a = P.ray_o[pid], b = P.ray_d[pid];
-            uint4 h = P.hit[pid];
-            f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
-            float bt = __uint_as_float(h.x), closest = __uint_as_float(h.z);
-            uint32_t belem = h.y, btri = 0; int bkind = (h.w & 0xFFu) == 0u ? 0 : -1;
-            for (uint32_t mi = h.w >> 8; mi < P.S.n_meshes; ++mi) {
-                const MeshDev& M = P.S.meshes[mi];
-                if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
-                float t; uint32_t ti;
-                if (!mesh_closest_brute(P.S, M, o, d, t, ti, COUNT ? &cnt : nullptr)) continue;
-                f3 p = o + t * d;
-                float dist = len3(o - p);
-                if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) { closest = dist; bkind = 1; belem = mi; btri = ti; bt = t; }
-            }
-            done_kind = resolve(P, it, pid, d, bkind, belem, btri, bt);
-        }
+        if (qi < n) { pid = P.candq[qi]; done_kind = process_candidate<true>(P, it, pid, COUNT ? &cnt : nullptr); }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             uint32_t slot = warp_append(&c->mat_count[k], done_kind == k);
@@ -368,12 +384,42 @@ __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) 
 }
 
 // ------------------------------------------------------------------ shade (lib.rs:54-62 + the scatter impls) + stage A
+// One hit of material `kind` at iteration `it`: scatter, then stage A of the continuation ray.  Returns its queue class.
+__device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid, RngKey key,
+                                               uint32_t& rays, uint32_t& nan_count) {
+    float4 a = P.ray_o[pid], b = P.ray_d[pid];
+    uint4 h = P.hit[pid];
+    f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+    float t = __uint_as_float(h.x);
+    uint32_t elem = h.y;
+    f3 point = o + t * d;                                                 // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
+    f3 normal;
+    if (h.w == 0u) {                                                      // sphere: p - c, un-normalised (sphere.rs:56)
+        float4 s = __ldg(P.S.spheres + elem);
+        normal = point - mk3(s.x, s.y, s.z);
+    } else {                                                              // mesh: stored unit normal (mesh.rs:253-257)
+        const MeshDev& M = P.S.meshes[elem - P.S.n_spheres];
+        float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
+        normal = mk3(nn.x, nn.y, nn.z);
+    }
+    uint32_t s_local = pid / P.paths_px, jp = pid - s_local * P.paths_px;
+    uint32_t row, col;
+    shard_pixel(P.sh, P.cam, jp, row, col);
+    f3 out_d;
+    bool cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam.width + col,
+                        P.s_base + s_local, it + 1, out_d);
+    if (!cont) { end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }       // absorbed (metal.rs:24) -> black
+    P.hist[(size_t)it * P.cap + pid] = (uint16_t)elem;
+    ++rays;
+    return stage_a(P, it + 1, pid, point, out_d, nan_count);
+}
+
 __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n0 = c->mat_count[0], n1 = c->mat_count[1], n2 = c->mat_count[2];
     // virtual index space: each material's run is padded to a multiple of 32 so a warp round never mixes kinds
     const uint32_t a0 = (n0 + 31u) & ~31u, a1 = a0 + ((n1 + 31u) & ~31u), total = a1 + ((n2 + 31u) & ~31u);
-    if (total == 0) return;
+    if (total == 0 || P.ctr[0].pad) return;
     const uint32_t lane = threadIdx.x & 31;
     RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     uint32_t nan_count = 0, rays = 0;
@@ -393,32 +439,7 @@ __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
             else { kind = 2; j = w - a1; nk = n2; }
             if (j >= nk) continue;
             uint32_t pid = P.matq[it & 1][kind][j];
-            float4 a = P.ray_o[pid], b = P.ray_d[pid];
-            uint4 h = P.hit[pid];
-            f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
-            float t = __uint_as_float(h.x);
-            uint32_t elem = h.y;
-            f3 point = o + t * d;                                         // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
-            f3 normal;
-            if (h.w == 0u) {                                              // sphere: p - c, un-normalised (sphere.rs:56)
-                float4 s = __ldg(P.S.spheres + elem);
-                normal = point - mk3(s.x, s.y, s.z);
-            } else {                                                      // mesh: stored unit normal (mesh.rs:253-257)
-                const MeshDev& M = P.S.meshes[elem - P.S.n_spheres];
-                float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
-                normal = mk3(nn.x, nn.y, nn.z);
-            }
-            uint32_t s_local = pid / P.paths_px, jp = pid - s_local * P.paths_px;
-            uint32_t row, col;
-            shard_pixel(P.sh, P.cam, jp, row, col);
-            f3 out_d;
-            bool cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam.width + col,
-                                P.s_base + s_local, it + 1, out_d);
-            if (cont) {
-                P.hist[(size_t)it * P.cap + pid] = (uint16_t)elem;
-                ++rays;
-                df.set(r, stage_a(P, it + 1, pid, point, out_d, nan_count), pid);
-            } else end_path(P, pid, mk3(0, 0, 0));                        // absorbed (metal.rs:24) -> black
+            df.set(r, shade_item(P, it, kind, pid, key, rays, nan_count), pid);
         }
         flush(P, it + 1, df);
     }
@@ -429,10 +450,61 @@ __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
     }
 }
 
+// ------------------------------------------------------------------ tail: finish every surviving path in ONE launch
+// Each bounce iteration costs a trace and a shade launch whose durations are bounded below by their slowest ray
+// (~0.2 ms together), however few rays are left, and paths trapped between surfaces use all 50 bounces.  Once the
+// rays of iteration `it` fit the lanes of one resident grid, this kernel takes every queued item (traversal
+// candidates and pending hits of iteration `it`) and runs each path to its end inside one lane — colorize's own
+// loop (lib.rs:43-73) — with the same device functions as the wavefront kernels, so results are bit-identical.
+// It raises ctr[0].pad; the remaining trace / shade / finish launches of the batch return at once.
+template <bool BRUTE, bool COUNT>
+__global__ void __launch_bounds__(256) k_finish(WaveParams P, uint32_t it0, uint32_t max_rays) {
+    if (P.ctr[0].pad) return;
+    const IterCtr c = P.ctr[it0];
+    if (c.ray_count > max_rays) return;
+    const uint32_t nc = c.cand_count, n0 = c.mat_count[0], n1 = c.mat_count[1], n2 = c.mat_count[2];
+    const uint32_t total = nc + n0 + n1 + n2;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
+    uint32_t nan_count = 0, rays = 0;
+    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    uint32_t n_cand = 0;
+    for (uint32_t w = tid; w < total; w += stride) {
+        uint32_t it = it0, pid; int kind;                                 // kind: 0..2 pending hit of that material, CLS_CAND queued ray
+        if (w < nc) { pid = P.candq[w]; kind = CLS_CAND; }
+        else if (w < nc + n0) { pid = P.matq[it0 & 1][0][w - nc]; kind = 0; }
+        else if (w < nc + n0 + n1) { pid = P.matq[it0 & 1][1][w - nc - n0]; kind = 1; }
+        else { pid = P.matq[it0 & 1][2][w - nc - n0 - n1]; kind = 2; }
+        for (;;) {
+            if (kind == CLS_CAND) { ++n_cand; kind = process_candidate<BRUTE>(P, it, pid, COUNT ? &cnt : nullptr); }
+            if (kind < 0) break;                                          // path ended (miss / depth exhausted)
+            uint32_t cls = shade_item(P, it, (uint32_t)kind, pid, key, rays, nan_count);
+            if (cls == CLS_NONE) break;                                   // absorbed / resolved on the spot
+            kind = (int)cls; ++it;
+        }
+    }
+    for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
+    if ((threadIdx.x & 31) == 0) {
+        if (rays) atomicAdd(&P.ctr[P.max_depth + 1].ray_count, rays);     // statistics slot past the last iteration
+        if (nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
+    }
+    if (COUNT) {
+        atomicAdd(&P.stats[ST_NODES], (unsigned long long)cnt.nodes); atomicAdd(&P.stats[ST_TRIS], (unsigned long long)cnt.tris);
+        atomicAdd(&P.stats[ST_CAND], (unsigned long long)n_cand);
+    }
+    // Raise the flag only when EVERY block of this launch has finished (blocks that become resident late must still
+    // pass the entry check above): the last block to leave sets it; later launches see it (stream order).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&P.ctr[1].pad, 1u) == gridDim.x - 1) P.ctr[0].pad = 1u + it0;
+    }
+}
+
 // statistics: rays = sum over iterations of ray_count (one tiny launch per batch)
 __global__ void k_sum_rays(WaveParams P) {
     unsigned long long r = 0;
-    for (uint32_t it = threadIdx.x; it <= P.max_depth; it += blockDim.x) r += P.ctr[it].ray_count;
+    for (uint32_t it = threadIdx.x; it <= P.max_depth + 1; it += blockDim.x) r += P.ctr[it].ray_count;
     for (int off = 16; off; off >>= 1) r += __shfl_down_sync(FULL_MASK, r, off);
     if ((threadIdx.x & 31) == 0 && r) atomicAdd(&P.stats[ST_RAYS], r);
 }
@@ -621,6 +693,11 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         int per_sm = 0;                                                   // k_trace: persistent blocks, exactly one resident wave
         CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, TRACE_THREADS, 0));
         const int grid_trace = sc.sm_count * (per_sm > 0 ? per_sm : 4);
+        int fin_per_sm = 0;                                               // k_finish: one resident wave of 256-thread blocks
+        CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm, k_finish<false, false>, 256, 0));
+        const int grid_fin = sc.sm_count * (fin_per_sm > 0 ? fin_per_sm : 2);
+        const char* tail_env = getenv("RBRT_TAIL_RAYS");                  // tuning knob; default = one ray per resident lane
+        const uint32_t tail_rays = (o.flags & RBRT_OPT_NO_TAIL_KERNEL) ? 0u : (tail_env ? (uint32_t)atoi(tail_env) : (uint32_t)grid_fin * 256u);
         const bool brute = o.trace_mode == RBRT_TRACE_BRUTE;
         const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
         const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
@@ -634,6 +711,11 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
             CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
             k_generate<<<grid, 256, 0, st>>>(wp); ++launches;
             for (uint32_t it = 0; it <= max_depth; ++it) {
+                if (it >= 1 && tail_rays) {                                // see k_finish
+                    if (brute) { if (count) k_finish<true, true><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); else k_finish<true, false><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); }
+                    else { if (count) k_finish<false, true><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); else k_finish<false, false><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); }
+                    ++launches;
+                }
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (brute) { if (count) k_trace_brute<true><<<grid, 256, 0, st>>>(wp, it); else k_trace_brute<false><<<grid, 256, 0, st>>>(wp, it); }
                 else { if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it); else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it); }

@@ -66,7 +66,8 @@ def test_mesh_scene_and_batching(gpu, oracle):
     the per-pixel summation order) and the brute-force integrator."""
     scene, cam = S.small_mesh_scene(4), S.example_camera(128, 96)
     ref = oracle.OracleScene.from_scene(scene).render_hdr(cam.to_c(), 6, _abi.RenderOptsC(seed=9))
-    for kw in [{}, {"batch_paths": 128 * 96}, {"batch_paths": 5 * 128 * 96}, {"batch_paths": 1}, {"trace_mode": _abi.TRACE_BRUTE}]:
+    for kw in [{}, {"batch_paths": 128 * 96}, {"batch_paths": 5 * 128 * 96}, {"batch_paths": 1}, {"trace_mode": _abi.TRACE_BRUTE},
+               {"no_tail_kernel": True}, {"no_tail_kernel": True, "trace_mode": _abi.TRACE_BRUTE}, {"no_tail_kernel": True, "batch_paths": 1}]:
         assert_images_equal(R.render_scene_hdr(cam, 6, scene, seed=9, **kw), ref, f"opts {kw}")
 
 
@@ -179,6 +180,20 @@ def test_c2_full_size_properties(gpu):
     a = R.render_scene_hdr(cam, 2, scene, seed=0)
     b = R.render_scene_hdr(cam, 2, scene, seed=0, trace_mode=_abi.TRACE_BRUTE)
     assert_images_equal(a, b, "C2 BVH vs brute integrator")
+    sa, sb = {}, {}
+    a = R.render_scene_hdr(cam, 8, scene, seed=1, stats=sa)                          # tail finished by k_finish
+    b = R.render_scene_hdr(cam, 8, scene, seed=1, stats=sb, no_tail_kernel=True)     # all 51 iterations as wavefront launches
+    assert_images_equal(a, b, "C2 tail kernel vs pure wavefront")
+    assert sa["rays"] == sb["rays"] and sa["paths"] == sb["paths"]
+    import os
+    os.environ["RBRT_TAIL_RAYS"] = "3000000"                                         # early hand-over: many paths per lane, grid-stride
+    try:
+        sc_ = {}
+        c = R.render_scene_hdr(cam, 8, scene, seed=1, stats=sc_)
+    finally:
+        del os.environ["RBRT_TAIL_RAYS"]
+    assert_images_equal(c, b, "C2 early tail kernel vs pure wavefront")
+    assert sc_["rays"] == sb["rays"]
 
 
 def test_invalid_arguments(gpu):
