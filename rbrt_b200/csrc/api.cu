@@ -140,7 +140,7 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
     }
     float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals; uint32_t* d_kind; MeshDev* d_meshes;
     CKS(dev_alloc(sc, &d_sph, ns)); CKS(dev_alloc(sc, &d_mat, ns + nm)); CKS(dev_alloc(sc, &d_kind, ns + nm));
-    CKS(dev_alloc(sc, &d_tris, 3 * total_eff)); CKS(dev_alloc(sc, &d_nodes, 4 * total_eff)); CKS(dev_alloc(sc, &d_normals, total_eff));
+    CKS(dev_alloc(sc, &d_tris, 3 * total_eff)); CKS(dev_alloc(sc, &d_nodes, 2 * total_eff)); CKS(dev_alloc(sc, &d_normals, total_eff));
     CKS(dev_alloc(sc, &d_meshes, nm));
     if (ns) CKSC(cudaMemcpy(d_sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
     if (ns + nm) {
@@ -178,7 +178,7 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
             uint64_t live = 0; int height = 0;
             if (ce == cudaSuccess)
                 ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, d_tris + 3 * tri_off, d_normals + tri_off,
-                                    d_nodes + 4 * tri_off, &md.root_ref, &live, &height, 0);
+                                    d_nodes + 2 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
             cudaFree(d_raw);
             if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
             if (height + 2 > 96) { set_error("mesh %u: BVH height %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }

@@ -5,8 +5,8 @@
 // (triangle.rs:30-34) are computed with the same individually rounded f32 ops, then the
 // triangles are put in Morton order and a binary LBVH is built over them:
 //   63-bit Morton code of the triangle-box centre -> radix sort (CUB) -> Karras 2012 topology
-//   -> bottom-up AABB refit with atomic arrival flags -> emission of 64-byte traversal nodes with
-//   subtrees of <= leaf_size triangles collapsed into leaves.
+//   -> bottom-up AABB refit with atomic arrival flags -> emission of 32-byte traversal nodes (child boxes on a
+//   16-bit grid over the mesh box) with subtrees of <= leaf_size triangles collapsed into leaves.
 #include "bvh_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
@@ -125,45 +125,69 @@ __global__ void k_refit(int n, const int2* __restrict__ children, const int* __r
     }
 }
 
-// traversal node emission with leaf collapse
-__global__ void k_emit_nodes(int n, uint32_t leaf_size, const int2* __restrict__ children, const int2* __restrict__ range,
+// traversal node emission with leaf collapse: 32-byte nodes, child boxes quantised OUTWARD (plus one step of margin,
+// see intersect.cuh) onto the mesh's 16-bit grid  bound = qorg + q * qstep
+struct QGrid { float org[3], step[3]; };
+
+__device__ __forceinline__ uint32_t quant_lo(float v, float org, float step) {
+    float q = floorf((v - org) / step) - 1.0f;
+    while (q > 0.0f && __fmaf_rn(q, step, org) > v) q -= 1.0f;             // never above the true bound
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+__device__ __forceinline__ uint32_t quant_hi(float v, float org, float step) {
+    float q = ceilf((v - org) / step) + 1.0f;
+    while (q < 65535.0f && __fmaf_rn(q, step, org) < v) q += 1.0f;         // never below the true bound
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+
+__global__ void k_emit_nodes(int n, uint32_t leaf_size, QGrid g, const int2* __restrict__ children, const int2* __restrict__ range,
                              const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                              const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
-                             float4* __restrict__ out, unsigned long long* __restrict__ live) {
+                             uint4* __restrict__ out, unsigned long long* __restrict__ live) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int2 rg = range[i];
     uint32_t cnt = (uint32_t)(rg.y - rg.x + 1);
     if (i != 0 && cnt <= leaf_size) {                                     // swallowed by an ancestor's leaf
-        out[4 * (size_t)i] = out[4 * (size_t)i + 1] = out[4 * (size_t)i + 2] = out[4 * (size_t)i + 3] = make_float4(0, 0, 0, 0);
+        out[2 * (size_t)i] = out[2 * (size_t)i + 1] = make_uint4(0, 0, 0, 0);
         return;
     }
     atomicAdd(live, 1ull);
     int2 ch = children[i];
-    float4 lo[2], hi[2]; int32_t ref[2];
+    uint32_t q[2][3]; int32_t ref[2];
     int c[2] = {ch.x, ch.y};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        if (c[k] < 0) { lo[k] = leaf_lo[~c[k]]; hi[k] = leaf_hi[~c[k]]; ref[k] = make_leaf_ref((uint32_t)(~c[k]), 1); }
+        float4 lo, hi;
+        if (c[k] < 0) { lo = leaf_lo[~c[k]]; hi = leaf_hi[~c[k]]; ref[k] = make_leaf_ref((uint32_t)(~c[k]), 1); }
         else {
-            lo[k] = node_lo[c[k]]; hi[k] = node_hi[c[k]];
+            lo = node_lo[c[k]]; hi = node_hi[c[k]];
             int2 r = range[c[k]];
             uint32_t cc = (uint32_t)(r.y - r.x + 1);
             ref[k] = cc <= leaf_size ? make_leaf_ref((uint32_t)r.x, cc) : c[k];
         }
+        q[k][0] = quant_lo(lo.x, g.org[0], g.step[0]) | (quant_hi(hi.x, g.org[0], g.step[0]) << 16);
+        q[k][1] = quant_lo(lo.y, g.org[1], g.step[1]) | (quant_hi(hi.y, g.org[1], g.step[1]) << 16);
+        q[k][2] = quant_lo(lo.z, g.org[2], g.step[2]) | (quant_hi(hi.z, g.org[2], g.step[2]) << 16);
     }
-    out[4 * (size_t)i] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
-    out[4 * (size_t)i + 1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
-    out[4 * (size_t)i + 2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
-    out[4 * (size_t)i + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.0f, 0.0f);
+    out[2 * (size_t)i] = make_uint4(q[0][0], q[0][1], q[0][2], q[1][0]);
+    out[2 * (size_t)i + 1] = make_uint4(q[1][1], q[1][2], (uint32_t)ref[0], (uint32_t)ref[1]);
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size,
                            float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
-                           int* tree_height, cudaStream_t st) {
+                           int* tree_height, float qorg[3], float qstep[3], cudaStream_t st) {
     *live_nodes = 0; *tree_height = 0;
+    QGrid grid;
+    for (int k = 0; k < 3; ++k) {                                          // 16-bit grid over the padded mesh box, 8 steps of slack per side
+        float ext = (hi[k] + pad) - (lo[k] - pad);
+        float step = ext / 65500.0f;
+        if (!(step > 1e-30f)) step = 1e-30f;
+        grid.step[k] = qstep[k] = step;
+        grid.org[k] = qorg[k] = (lo[k] - pad) - 8.0f * step;
+    }
     if (n == 0) { *root_ref = make_leaf_ref(0, 1); return cudaSuccess; }
     const int B = 256;
     uint32_t g = (n + B - 1) / B;
@@ -208,7 +232,8 @@ cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], co
     CKC(cudaGetLastError());
     k_refit<<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
     CKC(cudaGetLastError());
-    k_emit_nodes<<<(ni + B - 1) / B, B, 0, st>>>((int)n, leaf_size, children, range, leaf_lo, leaf_hi, node_lo, node_hi, d_nodes, d_live);
+    k_emit_nodes<<<(ni + B - 1) / B, B, 0, st>>>((int)n, leaf_size, grid, children, range, leaf_lo, leaf_hi, node_lo, node_hi,
+                                                 reinterpret_cast<uint4*>(d_nodes), d_live);
     CKC(cudaGetLastError());
     unsigned long long live = 0; int h = 0;
     CKC(cudaMemcpyAsync(&live, d_live, 8, cudaMemcpyDeviceToHost, st));

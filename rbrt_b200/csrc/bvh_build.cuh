@@ -6,9 +6,10 @@ namespace rbrt {
 
 // d_raw: n triangles x 9 floats on the device (world space, original order).
 // Writes n triangle records (3 float4 each) in Morton order to d_tris, n unit normals in ORIGINAL
-// order to d_normals and up to n-1 64-byte nodes to d_nodes.  lo/hi = exact mesh AABB.
+// order to d_normals and up to n-1 32-byte nodes to d_nodes; qorg/qstep = the 16-bit grid the node boxes are
+// quantised on.  lo/hi = exact mesh AABB.
 cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size,
                            float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
-                           int* tree_height, cudaStream_t st);
+                           int* tree_height, float qorg[3], float qstep[3], cudaStream_t st);
 
 }  // namespace rbrt

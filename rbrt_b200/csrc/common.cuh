@@ -78,12 +78,13 @@ struct MeshDev {
     int32_t  root_ref;         // >=0 node index (relative to node_base), <0 leaf reference
     uint32_t nrm_base;         // first normal of this mesh in SceneDev::normals (original order)
     uint32_t elem;             // element id = num_spheres + mesh index (material lookup)
+    float qorg[3], qstep[3];   // 16-bit grid of this mesh's BVH node boxes: bound = qorg + q * qstep (bvh_build.cu)
 };
 
 struct SceneDev {
     const float4* spheres;     // {cx, cy, cz, r}
     const float4* tris;        // 3 x float4 per triangle: {v0.xyz, bits(orig idx)}, {e1.xyz, 0}, {e2.xyz, 0}
-    const float4* nodes;       // 4 x float4 per BVH2 node (see bvh.cuh)
+    const float4* nodes;       // 2 x 16 B per BVH2 node: child boxes on the mesh's 16-bit grid + 2 child refs (intersect.cuh)
     const float4* normals;     // {n.xyz, 0} per triangle, original order
     const float4* mat;         // per element: {albedo.xyz, param}
     const uint32_t* mat_kind;  // per element: RBRT_MAT_*

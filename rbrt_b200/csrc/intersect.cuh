@@ -107,73 +107,101 @@ __device__ __forceinline__ bool mesh_closest_brute(const SceneDev& S, const Mesh
     return best_idx != 0xFFFFFFFFu;
 }
 
-// ------------------------------------------------------------------ BVH2 traversal
-// Node = 4 x float4 (64 B):
-//   n0 = {c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y}
-//   n1 = {c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y}
-//   n2 = {c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z}
-//   n3 = {bits(ref0), bits(ref1), -, -}     ref >= 0: node index; ref < 0: leaf (make_leaf_ref)
-// Child boxes are padded at build time (bvh_build.cu) so that the FMA slab test below can never
-// reject a box whose triangle the exact Moeller-Trumbore arithmetic above would accept.
+// ------------------------------------------------------------------ BVH2 traversal, 32-byte nodes
+// Node = 2 x uint4:  w0 = {c0.x, c0.y, c0.z, c1.x}   each word = qlo | qhi << 16 on the mesh's 16-bit grid
+//                    w1 = {c1.y, c1.z, ref0, ref1}    ref >= 0: node index; ref < 0: leaf (make_leaf_ref)
+// One 32-byte sector and two 16-byte loads per visit (the first version fetched 64 bytes in four loads and was bound
+// by L1 tag wavefronts).  A 16-bit value becomes the float 2^23 + q with ONE byte-permute (PRMT builds 0x4B00hhll);
+// the permute selector also picks the near or the far bound for the ray's direction sign, so there is no per-axis
+// min/max either:   t = fma(2^23 + q, A, B')  with  A = step * (1/d),  B' = (org - o) * (1/d) - 2^23 * A.
+// B' is rounded once at magnitude ~2^23 |A|, i.e. by up to half a grid step of t; bvh_build.cu therefore quantises
+// child boxes outward AND adds one more step of margin, so the slab test can never reject a box whose triangle
+// the exact Moeller-Trumbore arithmetic above would accept.
+#define RBRT_SENTINEL 0x7FFFFFFF
+#define RBRT_SEL_LO 0x7610u           // PRMT selectors: bytes {0,1} / {2,3} of the node word under 0x4B00....
+#define RBRT_SEL_HI 0x7632u
+
+struct RaySlabs {
+    float ax, ay, az, bx, by, bz;     // per-axis t = fma(m, a, b)
+    uint32_t nx, ny, nz;              // selector of the NEAR bound per axis (far = near ^ 0x22)
+};
+
+__device__ __forceinline__ RaySlabs ray_slabs(const MeshDev& M, f3 o, f3 d) {
+    const float big = 1e25f;
+    float idx = fabsf(d.x) > 1e-25f ? __fdividef(1.0f, d.x) : copysignf(big, d.x);
+    float idy = fabsf(d.y) > 1e-25f ? __fdividef(1.0f, d.y) : copysignf(big, d.y);
+    float idz = fabsf(d.z) > 1e-25f ? __fdividef(1.0f, d.z) : copysignf(big, d.z);
+    RaySlabs r;
+    r.ax = M.qstep[0] * idx; r.ay = M.qstep[1] * idy; r.az = M.qstep[2] * idz;
+    r.bx = __fmaf_rn(-8388608.0f, r.ax, (M.qorg[0] - o.x) * idx);
+    r.by = __fmaf_rn(-8388608.0f, r.ay, (M.qorg[1] - o.y) * idy);
+    r.bz = __fmaf_rn(-8388608.0f, r.az, (M.qorg[2] - o.z) * idz);
+    r.nx = idx >= 0.0f ? RBRT_SEL_LO : RBRT_SEL_HI;
+    r.ny = idy >= 0.0f ? RBRT_SEL_LO : RBRT_SEL_HI;
+    r.nz = idz >= 0.0f ? RBRT_SEL_LO : RBRT_SEL_HI;
+    return r;
+}
+
+__device__ __forceinline__ float q16(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+
+// One node visit: returns the next reference to process (near child, or the popped stack top).
+__device__ __forceinline__ int32_t bvh2_step(const uint4* __restrict__ nd, const RaySlabs& R, float t_prune, int32_t* stack, int& sp) {
+    const uint4 w0 = __ldg(nd), w1 = __ldg(nd + 1);
+    const uint32_t fx = R.nx ^ 0x22u, fy = R.ny ^ 0x22u, fz = R.nz ^ 0x22u;
+    float t0n = fmaxf(fmaxf(__fmaf_rn(q16(w0.x, R.nx), R.ax, R.bx), __fmaf_rn(q16(w0.y, R.ny), R.ay, R.by)),
+                      fmaxf(__fmaf_rn(q16(w0.z, R.nz), R.az, R.bz), 0.0f));
+    float t0f = fminf(fminf(__fmaf_rn(q16(w0.x, fx), R.ax, R.bx), __fmaf_rn(q16(w0.y, fy), R.ay, R.by)),
+                      fminf(__fmaf_rn(q16(w0.z, fz), R.az, R.bz), t_prune));
+    float t1n = fmaxf(fmaxf(__fmaf_rn(q16(w0.w, R.nx), R.ax, R.bx), __fmaf_rn(q16(w1.x, R.ny), R.ay, R.by)),
+                      fmaxf(__fmaf_rn(q16(w1.y, R.nz), R.az, R.bz), 0.0f));
+    float t1f = fminf(fminf(__fmaf_rn(q16(w0.w, fx), R.ax, R.bx), __fmaf_rn(q16(w1.x, fy), R.ay, R.by)),
+                      fminf(__fmaf_rn(q16(w1.y, fz), R.az, R.bz), t_prune));
+    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    const int32_t r0 = (int32_t)w1.z, r1 = (int32_t)w1.w;
+    if (h0 && h1) {
+        const bool swap = t1n < t0n;
+        stack[sp++] = swap ? r0 : r1;
+        return swap ? r1 : r0;
+    }
+    if (h0) return r0;
+    if (h1) return r1;
+    return stack[--sp];
+}
+
+// Leaf: <= 8 contiguous triangle records, exact test, running lexicographic minimum.
+__device__ __forceinline__ void leaf_step(const float4* __restrict__ tris, uint32_t tri_base, int32_t cur, f3 o, f3 d, float t_limit,
+                                          float& best_t, uint32_t& best_idx, float& t_prune, uint32_t& n_tris) {
+    uint32_t code = (uint32_t)(~cur);
+    uint32_t first = code >> 3, count = (code & 7) + 1;
+    for (uint32_t k = 0; k < count; ++k) {
+        f3 v0, e1, e2; uint32_t orig; float t;
+        load_tri(tris, tri_base + first + k, v0, e1, e2, orig);
+        if (tri_intersect(v0, e1, e2, o, d, t)) {
+            keep_min(t, orig, best_t, best_idx);
+            // prune bound in t: nothing beyond min(best so far, caller's limit) can win; the slack keeps the prune
+            // conservative against the rounding of the exact test's t.
+            t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
+        }
+    }
+    n_tris += count;
+}
+
+// Simple one-lane-one-ray traversal (parity hook, tail kernel); the wavefront trace kernel (render.cu) runs the same
+// two steps in while-while form with dynamic fetch.
 __device__ __forceinline__ bool mesh_closest_bvh(const SceneDev& S, const MeshDev& M, f3 o, f3 d, float t_limit,
                                                  float& best_t, uint32_t& best_idx, TraceCounters* cnt) {
-    best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;
-    // prune bound in t: nothing beyond min(best so far, caller's limit) can win; slack keeps the
-    // prune conservative against the rounding of the exact test's t.
+    best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;                         // min_param init (triangle.rs:398)
     float t_prune = t_limit;
-    const float big = 1e30f;
-    float idx = fabsf(d.x) > 1e-30f ? __fdividef(1.0f, d.x) : copysignf(big, d.x);
-    float idy = fabsf(d.y) > 1e-30f ? __fdividef(1.0f, d.y) : copysignf(big, d.y);
-    float idz = fabsf(d.z) > 1e-30f ? __fdividef(1.0f, d.z) : copysignf(big, d.z);
-    float oox = o.x * idx, ooy = o.y * idy, ooz = o.z * idz;
-
-    const float4* __restrict__ nodes = S.nodes + 4 * (size_t)M.node_base;
+    const RaySlabs R = ray_slabs(M, o, d);
+    const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(S.nodes) + 2 * (size_t)M.node_base;
     int32_t stack[RBRT_STACK];
     int sp = 0;
     int32_t cur = M.root_ref;
-    const int32_t SENTINEL = 0x7FFFFFFF;
-    stack[sp++] = SENTINEL;
+    stack[sp++] = RBRT_SENTINEL;
     uint32_t n_nodes = 0, n_tris = 0;
-
-    while (cur != SENTINEL) {
-        if (cur >= 0) {
-            const float4* n = nodes + 4 * (size_t)cur;
-            float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-            ++n_nodes;
-            float c0lox = __fmaf_rn(n0.x, idx, -oox), c0hix = __fmaf_rn(n0.y, idx, -oox);
-            float c0loy = __fmaf_rn(n0.z, idy, -ooy), c0hiy = __fmaf_rn(n0.w, idy, -ooy);
-            float c0loz = __fmaf_rn(n2.x, idz, -ooz), c0hiz = __fmaf_rn(n2.y, idz, -ooz);
-            float c1lox = __fmaf_rn(n1.x, idx, -oox), c1hix = __fmaf_rn(n1.y, idx, -oox);
-            float c1loy = __fmaf_rn(n1.z, idy, -ooy), c1hiy = __fmaf_rn(n1.w, idy, -ooy);
-            float c1loz = __fmaf_rn(n2.z, idz, -ooz), c1hiz = __fmaf_rn(n2.w, idz, -ooz);
-            float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-            float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), t_prune));
-            float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-            float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), t_prune));
-            bool h0 = t0n <= t0f, h1 = t1n <= t1f;
-            int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                bool swap = t1n < t0n;
-                int32_t nearr = swap ? r1 : r0, farr = swap ? r0 : r1;
-                stack[sp++] = farr;
-                cur = nearr;
-            } else if (h0) cur = r0;
-            else if (h1) cur = r1;
-            else cur = stack[--sp];
-        } else {
-            uint32_t code = (uint32_t)(~cur);
-            uint32_t first = code >> 3, count = (code & 7) + 1;
-            for (uint32_t k = 0; k < count; ++k) {
-                f3 v0, e1, e2; uint32_t orig; float t;
-                load_tri(S.tris, M.tri_base + first + k, v0, e1, e2, orig);
-                if (tri_intersect(v0, e1, e2, o, d, t)) {
-                    keep_min(t, orig, best_t, best_idx);
-                    t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
-                }
-            }
-            n_tris += count;
-            cur = stack[--sp];
-        }
+    while (cur != RBRT_SENTINEL) {
+        if (cur >= 0) { cur = bvh2_step(nodes + 2 * (size_t)cur, R, t_prune, stack, sp); ++n_nodes; }
+        else { leaf_step(S.tris, M.tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, n_tris); cur = stack[--sp]; }
     }
     if (cnt) { cnt->nodes += n_nodes; cnt->tris += n_tris; }
     return best_idx != 0xFFFFFFFFu;

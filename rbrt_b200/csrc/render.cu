@@ -190,12 +190,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
     bool has_ray = false;
     uint32_t pid = 0, mi = 0;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
-    float idx = 0, idy = 0, idz = 0, oox = 0, ooy = 0, ooz = 0;
+    RaySlabs R = {0, 0, 0, 0, 0, 0, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_LO};
     float closest = 0.0f, bt = 0.0f; int bkind = -1; uint32_t belem = 0, btri = 0;   // best over spheres + finished meshes
     // ---- traversal state of the current mesh
     int32_t cur = SENTINEL; int sp = 0;
     float best_t = 0.0f, t_prune = 0.0f, t_limit = 0.0f; uint32_t best_idx = 0xFFFFFFFFu;
-    const float4* __restrict__ nodes = P.S.nodes; uint32_t tri_base = 0;
+    const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(P.S.nodes); uint32_t tri_base = 0;
     bool exhausted = false;                                               // warp-uniform: the queue has no more rays
     uint32_t n_nodes = 0, n_tris = 0;
     // With few rays (tail iterations) a warp must not take 32 of them while others idle: every ray is a
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
             if (lim == lim) t_limit = fminf(t_limit, lim);
         }
         t_prune = t_limit; best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;     // min_param init (triangle.rs:398)
-        nodes = P.S.nodes + 4 * (size_t)M.node_base; tri_base = M.tri_base;
+        nodes = reinterpret_cast<const uint4*>(P.S.nodes) + 2 * (size_t)M.node_base; tri_base = M.tri_base;
+        R = ray_slabs(M, o, d);
         sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
     };
 
@@ -263,11 +264,6 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
                         o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
                         bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
                         bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
-                        const float big = 1e30f;
-                        idx = fabsf(d.x) > 1e-30f ? __fdividef(1.0f, d.x) : copysignf(big, d.x);
-                        idy = fabsf(d.y) > 1e-30f ? __fdividef(1.0f, d.y) : copysignf(big, d.y);
-                        idz = fabsf(d.z) > 1e-30f ? __fdividef(1.0f, d.z) : copysignf(big, d.z);
-                        oox = o.x * idx; ooy = o.y * idy; ooz = o.z * idz;
                         has_ray = true;
                         start_mesh(P.S.meshes[mi]);                       // stage A found this mesh's box hit
                     }
@@ -280,42 +276,14 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t 
         const int threshold = exhausted ? 1 : min(FETCH_THRESHOLD, (int)quota);
         // ---- while-while traversal: every lane descends to its next leaf, then the leaves are processed together
         for (;;) {
-            while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node
-                const float4* nd = nodes + 4 * (size_t)cur;
-                float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+            while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node (intersect.cuh)
+                cur = bvh2_step(nodes + 2 * (size_t)cur, R, t_prune, stack, sp);
                 if (COUNT) ++n_nodes;
-                float c0lox = __fmaf_rn(n0.x, idx, -oox), c0hix = __fmaf_rn(n0.y, idx, -oox);
-                float c0loy = __fmaf_rn(n0.z, idy, -ooy), c0hiy = __fmaf_rn(n0.w, idy, -ooy);
-                float c0loz = __fmaf_rn(n2.x, idz, -ooz), c0hiz = __fmaf_rn(n2.y, idz, -ooz);
-                float c1lox = __fmaf_rn(n1.x, idx, -oox), c1hix = __fmaf_rn(n1.y, idx, -oox);
-                float c1loy = __fmaf_rn(n1.z, idy, -ooy), c1hiy = __fmaf_rn(n1.w, idy, -ooy);
-                float c1loz = __fmaf_rn(n2.z, idz, -ooz), c1hiz = __fmaf_rn(n2.w, idz, -ooz);
-                float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-                float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), t_prune));
-                float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-                float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), t_prune));
-                bool h0 = t0n <= t0f, h1 = t1n <= t1f;
-                int32_t r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    bool swap = t1n < t0n;
-                    stack[sp++] = swap ? r0 : r1;
-                    cur = swap ? r1 : r0;
-                } else if (h0) cur = r0;
-                else if (h1) cur = r1;
-                else cur = stack[--sp];
             }
             if (cur < 0) {                                                // leaf: <= 8 contiguous triangles
-                uint32_t code = (uint32_t)(~cur);
-                uint32_t first = code >> 3, count = (code & 7) + 1;
-                for (uint32_t k = 0; k < count; ++k) {
-                    f3 v0, e1, e2; uint32_t orig; float t;
-                    load_tri(P.S.tris, tri_base + first + k, v0, e1, e2, orig);
-                    if (tri_intersect(v0, e1, e2, o, d, t)) {
-                        keep_min(t, orig, best_t, best_idx);
-                        t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
-                    }
-                }
-                if (COUNT) n_tris += count;
+                uint32_t nt = 0;
+                leaf_step(P.S.tris, tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, nt);
+                if (COUNT) n_tris += nt;
                 cur = stack[--sp];
             }
             if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
