@@ -40,16 +40,18 @@ static int ensure_device() {
     return RBRT_OK;
 }
 
-template <typename T>
-static int dev_alloc(Scene* sc, T** p, size_t count) {
+// All device buffers of a scene are carved from ONE allocation (one cudaMalloc at creation, one cudaFree at
+// destruction: each of those calls synchronises the device).
+static int arena_alloc(Scene* sc, size_t bytes, char** base) {
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count ? count * sizeof(T) : 16);
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 256);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     sc->allocs.push_back(q);
-    sc->info.device_bytes += count * sizeof(T);
-    *p = (T*)q;
+    sc->info.device_bytes += bytes;
+    *base = (char*)q;
     return RBRT_OK;
 }
+static inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 static void destroy_scene(Scene* sc) {
     if (!sc) return;
@@ -139,9 +141,19 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
         kind[ns + i] = meshes[i].material.kind;
     }
     float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals; uint32_t* d_kind; MeshDev* d_meshes;
-    CKS(dev_alloc(sc, &d_sph, ns)); CKS(dev_alloc(sc, &d_mat, ns + nm)); CKS(dev_alloc(sc, &d_kind, ns + nm));
-    CKS(dev_alloc(sc, &d_tris, 3 * total_eff)); CKS(dev_alloc(sc, &d_nodes, 2 * total_eff)); CKS(dev_alloc(sc, &d_normals, total_eff));
-    CKS(dev_alloc(sc, &d_meshes, nm));
+    {
+        const size_t b_sph = a256(16ull * ns), b_mat = a256(16ull * (ns + nm)), b_kind = a256(4ull * (ns + nm)), b_tris = a256(48ull * total_eff),
+                     b_nodes = a256(32ull * total_eff), b_nrm = a256(16ull * total_eff), b_mesh = a256(sizeof(MeshDev) * nm);
+        char* base = nullptr;
+        CKS(arena_alloc(sc, b_nodes + b_tris + b_nrm + b_sph + b_mat + b_kind + b_mesh, &base));
+        d_nodes = (float4*)base; base += b_nodes;                          // nodes and triangles adjacent: the data every ray re-reads
+        d_tris = (float4*)base; base += b_tris;
+        d_normals = (float4*)base; base += b_nrm;
+        d_sph = (float4*)base; base += b_sph;
+        d_mat = (float4*)base; base += b_mat;
+        d_kind = (uint32_t*)base; base += b_kind;
+        d_meshes = (MeshDev*)base;
+    }
     if (ns) CKSC(cudaMemcpy(d_sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
     if (ns + nm) {
         CKSC(cudaMemcpy(d_mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice));
@@ -156,35 +168,27 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
         const rbrt_mesh_desc& m = meshes[i];
         MeshDev md; memset(&md, 0, sizeof(md));
         float lo[3] = {3.40282347e+38f, 3.40282347e+38f, 3.40282347e+38f}, hi[3] = {-3.40282347e+38f, -3.40282347e+38f, -3.40282347e+38f};
-        for (uint64_t v = 0; v < m.num_triangles * 3; ++v)
-            for (int k = 0; k < 3; ++k) {
-                float x = m.tri_vertices[3 * v + k];
-                if (x < lo[k]) lo[k] = x;
-                if (x > hi[k]) hi[k] = x;
-            }
         uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
+        const float* d_raw = nullptr;
+        double t1 = now_ms();
+        // upload + exact AABB over ALL real triangles, including those the SIMD tail rule drops (aabbox.rs:62-88, mesh.rs:61)
+        CKSC(upload_mesh(m.tri_vertices, m.num_triangles, lo, hi, &d_raw, 0));
+        double t2 = now_ms();
         for (int k = 0; k < 3; ++k) { md.lo[k] = lo[k]; md.hi[k] = hi[k]; }
         md.tri_base = (uint32_t)tri_off; md.n_tris = (uint32_t)n_eff; md.node_base = (uint32_t)tri_off;
         md.nrm_base = (uint32_t)tri_off; md.elem = ns + i; md.root_ref = make_leaf_ref(0, 1);
         if (n_eff) {
-            double t1 = now_ms();
-            float* d_raw = nullptr;
-            CKSC(cudaMalloc(&d_raw, 36ull * n_eff));
-            cudaError_t ce = cudaMemcpy(d_raw, m.tri_vertices, 36ull * n_eff, cudaMemcpyHostToDevice);
-            double t2 = now_ms();
             float mx = 0.0f;
             for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]); }
             float pad = pad_rel * mx;
             uint64_t live = 0; int height = 0;
-            if (ce == cudaSuccess)
-                ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, d_tris + 3 * tri_off, d_normals + tri_off,
-                                    d_nodes + 2 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
-            cudaFree(d_raw);
+            cudaError_t ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, d_tris + 3 * tri_off, d_normals + tri_off,
+                                            d_nodes + 2 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
             if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
             if (height + 2 > 96) { set_error("mesh %u: BVH height %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
             live_total += live;
-            ms_upload += t2 - t1; ms_build += now_ms() - t2;
         }
+        ms_upload += t2 - t1; ms_build += now_ms() - t2;
         sc->meshes_h[i] = md;
         tri_off += n_eff;
     }
@@ -230,6 +234,7 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
 
 int rbrt_gpu_release_cache(void) {
     release_device_wave_buffers();
+    release_build_scratch();
     return RBRT_OK;
 }
 

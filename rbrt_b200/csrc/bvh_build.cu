@@ -9,6 +9,7 @@
 //   16-bit grid over the mesh box) with subtrees of <= leaf_size triangles collapsed into leaves.
 #include "bvh_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cstring>
 
 namespace rbrt {
 
@@ -174,7 +175,72 @@ __global__ void k_emit_nodes(int n, uint32_t leaf_size, QGrid g, const int2* __r
     out[2 * (size_t)i + 1] = make_uint4(q[1][1], q[1][2], (uint32_t)ref[0], (uint32_t)ref[1]);
 }
 
+// ------------------------------------------------------------------ exact mesh AABB (aabbox.rs:62-88) on the device
+// min / max are exact whatever the order, so a parallel reduction gives the reference's bounds bit for bit
+// (NaN coordinates are ignored like the reference's `<` / `>` comparisons ignore them).
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__host__ __device__ __forceinline__ float ord2f(int i) {
+    int b = i >= 0 ? i : i ^ 0x7FFFFFFF;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+__global__ void k_aabb_init(int* mm) { if (threadIdx.x < 3) mm[threadIdx.x] = 0x7F7FFFFF; else if (threadIdx.x < 6) mm[threadIdx.x] = (int)0xFF7FFFFF ^ 0x7FFFFFFF; }
+
+__global__ void k_aabb(const float* __restrict__ raw, uint64_t n_vertices, int* __restrict__ mm) {
+    float lo[3] = {3.40282347e+38f, 3.40282347e+38f, 3.40282347e+38f}, hi[3] = {-3.40282347e+38f, -3.40282347e+38f, -3.40282347e+38f};
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vertices; v += (uint64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { float x = raw[3 * v + k]; lo[k] = fminf(lo[k], x); hi[k] = fmaxf(hi[k], x); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int off = 16; off; off >>= 1) { lo[k] = fminf(lo[k], __shfl_down_sync(0xFFFFFFFFu, lo[k], off)); hi[k] = fmaxf(hi[k], __shfl_down_sync(0xFFFFFFFFu, hi[k], off)); }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&mm[k], f2ord(lo[k])); atomicMax(&mm[3 + k], f2ord(hi[k])); }
+    }
+}
+
+// Grow-only device scratch shared by all builds of the process (one allocation instead of ~16 per build).
+static void* g_scratch[64] = {nullptr};
+static size_t g_scratch_bytes[64] = {0};
+void release_build_scratch() {
+    int cur = 0; cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) if (g_scratch[d]) { cudaSetDevice(d); cudaFree(g_scratch[d]); g_scratch[d] = nullptr; g_scratch_bytes[d] = 0; }
+    cudaSetDevice(cur);
+}
+static cudaError_t scratch(size_t bytes, char** out) {
+    int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (g_scratch_bytes[dev] < bytes) {
+        cudaFree(g_scratch[dev]); g_scratch[dev] = nullptr; g_scratch_bytes[dev] = 0;
+        e = cudaMalloc(&g_scratch[dev], bytes); if (e != cudaSuccess) return e;
+        g_scratch_bytes[dev] = bytes;
+    }
+    *out = (char*)g_scratch[dev];
+    return cudaSuccess;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+// Upload one mesh's triangle soup (host pointer, n_all triangles) into the scratch and return its exact AABB.
+cudaError_t upload_mesh(const float* h_tris, uint64_t n_all, float lo[3], float hi[3], const float** d_raw_out, cudaStream_t st) {
+    char* base = nullptr;
+    size_t raw_bytes = (36ull * n_all + 255) & ~255ull;
+    CK(scratch(raw_bytes + 256 + 160ull * (n_all + 64) + (64ull << 20), &base));     // raw + AABB cell + build arrays + sort temp (see build_mesh_bvh)
+    CK(cudaMemcpyAsync(base, h_tris, 36ull * n_all, cudaMemcpyHostToDevice, st));
+    int* mm = (int*)(base + raw_bytes);
+    k_aabb_init<<<1, 32, 0, st>>>(mm);
+    if (n_all) k_aabb<<<148 * 4, 256, 0, st>>>((const float*)base, n_all * 3, mm);
+    int h[6];
+    CK(cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) { lo[k] = ord2f(h[k]); hi[k] = ord2f(h[3 + k]); }
+    *d_raw_out = (const float*)base;
+    return cudaSuccess;
+}
 
 cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size,
                            float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
@@ -190,59 +256,54 @@ cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], co
     }
     if (n == 0) { *root_ref = make_leaf_ref(0, 1); return cudaSuccess; }
     const int B = 256;
-    uint32_t g = (n + B - 1) / B;
-    uint64_t *keys = nullptr, *keys_s = nullptr; uint32_t *vals = nullptr, *vals_s = nullptr;
-    float4 *leaf_lo = nullptr, *leaf_hi = nullptr, *node_lo = nullptr, *node_hi = nullptr;
-    int2 *children = nullptr, *range = nullptr; int *parent_int = nullptr, *parent_leaf = nullptr, *flags = nullptr, *height = nullptr;
-    unsigned long long* d_live = nullptr; void* tmp = nullptr;
-    cudaError_t err = cudaSuccess;
-    auto cleanup = [&]() {
-        cudaFree(keys); cudaFree(keys_s); cudaFree(vals); cudaFree(vals_s); cudaFree(leaf_lo); cudaFree(leaf_hi);
-        cudaFree(node_lo); cudaFree(node_hi); cudaFree(children); cudaFree(range); cudaFree(parent_int);
-        cudaFree(parent_leaf); cudaFree(flags); cudaFree(height); cudaFree(d_live); cudaFree(tmp);
-    };
-#define CKC(x) do { err = (x); if (err != cudaSuccess) { cleanup(); return err; } } while (0)
-    CKC(cudaMalloc(&keys, 8ull * n)); CKC(cudaMalloc(&keys_s, 8ull * n));
-    CKC(cudaMalloc(&vals, 4ull * n)); CKC(cudaMalloc(&vals_s, 4ull * n));
-    CKC(cudaMalloc(&leaf_lo, 16ull * n)); CKC(cudaMalloc(&leaf_hi, 16ull * n));
+    const uint32_t g = (n + B - 1) / B, ni = n > 1 ? n - 1 : 1;
+    // carve the scratch: d_raw sits at its start (upload_mesh), the AABB cell after it
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 63, st));
+    char* base = nullptr;
+    int dev = 0; CK(cudaGetDevice(&dev));
+    base = (char*)g_scratch[dev & 63];
+    if (!base || (const char*)d_raw != base) return cudaErrorInvalidValue;                 // build_mesh_bvh follows upload_mesh
+    size_t off = ((36ull * n + 36ull * 8 + 255) & ~255ull) + 256;                           // raw (n_eff <= n_all <= n_eff + 7) + AABB cell
+    auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 255) & ~255ull; return p; };
+    uint64_t* keys = (uint64_t*)take(8ull * n); uint64_t* keys_s = (uint64_t*)take(8ull * n);
+    uint32_t* vals = (uint32_t*)take(4ull * n); uint32_t* vals_s = (uint32_t*)take(4ull * n);
+    float4* leaf_lo = (float4*)take(16ull * n); float4* leaf_hi = (float4*)take(16ull * n);
+    float4* node_lo = (float4*)take(16ull * ni); float4* node_hi = (float4*)take(16ull * ni);
+    int2* children = (int2*)take(8ull * ni); int2* range = (int2*)take(8ull * ni);
+    int* parent_int = (int*)take(4ull * ni); int* parent_leaf = (int*)take(4ull * n);
+    int* flags = (int*)take(4ull * ni); int* height = (int*)take(4ull * ni);
+    unsigned long long* d_live = (unsigned long long*)take(8);
+    void* tmp = take(tmp_bytes ? tmp_bytes : 16);
+    if (off > g_scratch_bytes[dev & 63]) return cudaErrorMemoryAllocation;
+
     float3 flo = make_float3(lo[0], lo[1], lo[2]);
     float3 inv = make_float3(hi[0] > lo[0] ? 1.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1.0f / (hi[1] - lo[1]) : 0.0f,
                              hi[2] > lo[2] ? 1.0f / (hi[2] - lo[2]) : 0.0f);
     k_prepare<<<g, B, 0, st>>>(d_raw, n, flo, inv, d_normals, keys, vals);
-    CKC(cudaGetLastError());
-    size_t tmp_bytes = 0;
-    CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
-    CKC(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    CKC(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
+    CK(cudaGetLastError());
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
     k_emit_tris<<<g, B, 0, st>>>(d_raw, vals_s, n, pad, d_tris, leaf_lo, leaf_hi);
-    CKC(cudaGetLastError());
+    CK(cudaGetLastError());
     if (n <= leaf_size || n == 1) {
         *root_ref = make_leaf_ref(0, n);
-        CKC(cudaStreamSynchronize(st));
-        cleanup();
+        CK(cudaStreamSynchronize(st));
         return cudaSuccess;
     }
-    uint32_t ni = n - 1;
-    CKC(cudaMalloc(&node_lo, 16ull * ni)); CKC(cudaMalloc(&node_hi, 16ull * ni));
-    CKC(cudaMalloc(&children, 8ull * ni)); CKC(cudaMalloc(&range, 8ull * ni));
-    CKC(cudaMalloc(&parent_int, 4ull * ni)); CKC(cudaMalloc(&parent_leaf, 4ull * n));
-    CKC(cudaMalloc(&flags, 4ull * ni)); CKC(cudaMalloc(&height, 4ull * ni)); CKC(cudaMalloc(&d_live, 8));
-    CKC(cudaMemsetAsync(flags, 0, 4ull * ni, st)); CKC(cudaMemsetAsync(d_live, 0, 8, st));
+    CK(cudaMemsetAsync(flags, 0, 4ull * ni, st)); CK(cudaMemsetAsync(d_live, 0, 8, st));
     k_karras<<<(ni + B - 1) / B, B, 0, st>>>(keys_s, (int)n, children, range, parent_int, parent_leaf);
-    CKC(cudaGetLastError());
+    CK(cudaGetLastError());
     k_refit<<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
-    CKC(cudaGetLastError());
+    CK(cudaGetLastError());
     k_emit_nodes<<<(ni + B - 1) / B, B, 0, st>>>((int)n, leaf_size, grid, children, range, leaf_lo, leaf_hi, node_lo, node_hi,
                                                  reinterpret_cast<uint4*>(d_nodes), d_live);
-    CKC(cudaGetLastError());
+    CK(cudaGetLastError());
     unsigned long long live = 0; int h = 0;
-    CKC(cudaMemcpyAsync(&live, d_live, 8, cudaMemcpyDeviceToHost, st));
-    CKC(cudaMemcpyAsync(&h, height, 4, cudaMemcpyDeviceToHost, st));
-    CKC(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(&live, d_live, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h, height, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     *live_nodes = live; *tree_height = h; *root_ref = 0;
-    cleanup();
     return cudaSuccess;
-#undef CKC
 }
 
 }  // namespace rbrt

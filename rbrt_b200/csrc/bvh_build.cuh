@@ -4,6 +4,12 @@
 
 namespace rbrt {
 
+// upload_mesh copies a mesh's n_all x 9 floats (HOST pointer, world space, original order) into the process-wide build
+// scratch and returns the exact AABB over ALL of them (aabbox.rs:62-88, computed on the device); build_mesh_bvh must
+// follow it directly with d_raw = the pointer it returned and n = the triangles the reference actually tests.
+cudaError_t upload_mesh(const float* h_tris, uint64_t n_all, float lo[3], float hi[3], const float** d_raw_out, cudaStream_t st);
+void release_build_scratch();
+
 // d_raw: n triangles x 9 floats on the device (world space, original order).
 // Writes n triangle records (3 float4 each) in Morton order to d_tris, n unit normals in ORIGINAL
 // order to d_normals and up to n-1 32-byte nodes to d_nodes; qorg/qstep = the 16-bit grid the node boxes are

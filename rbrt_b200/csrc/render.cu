@@ -18,6 +18,7 @@
 // sample order — the reference's `color += colorize(..)` (lib.rs:96-100) — with no float atomics,
 // so an image is bit-reproducible and independent of scheduling.
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include "engine.cuh"
 #include "intersect.cuh"
@@ -178,7 +179,7 @@ __device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_
 #define FETCH_THRESHOLD 20     // re-fill the warp when fewer lanes than this are still traversing
 
 template <bool COUNT>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(WaveParams P, uint32_t it) {
+__global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32_t it) {   // 8 blocks/SM = 64 registers
     IterCtr* c = P.ctr + it;
     const uint32_t n = c->cand_count;
     if (n == 0 || P.ctr[0].pad) return;
@@ -637,12 +638,16 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         // (92 + 2*max_depth bytes of wavefront state each: 25.8 GB at depth 50) and at most half of the free HBM.
         uint32_t target = o.batch_paths;
         if (!target) {
-            size_t free_b = 0, total_b = 0;
-            CKR(cudaMemGetInfo(&free_b, &total_b));
-            free_b += wb.bytes;                                           // what a re-allocation would release first
-            uint64_t per_path = 92ull + 2ull * max_depth;
-            uint64_t fit = (free_b / 2) / per_path;
-            target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
+            const uint64_t per_path = 92ull + 2ull * max_depth;
+            const uint64_t want = std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * P, 1ull << 27);
+            if (wb.cap >= want && wb.depth_cap >= max_depth) target = (uint32_t)want;      // the pool already holds it: no driver query
+            else {
+                size_t free_b = 0, total_b = 0;
+                CKR(cudaMemGetInfo(&free_b, &total_b));
+                free_b += wb.bytes;                                       // what a re-allocation would release first
+                uint64_t fit = (free_b / 2) / per_path;
+                target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
+            }
         }
         uint32_t S_b = target / P; if (S_b < 1) S_b = 1; if (S_b > sh.s1 - sh.s0) S_b = sh.s1 - sh.s0;
         if ((uint64_t)S_b * P > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
@@ -659,10 +664,12 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
         const int grid = sc.sm_count * 8;                                  // producers / brute: 256-thread blocks
         int per_sm = 0;                                                   // k_trace: persistent blocks, exactly one resident wave
-        CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, TRACE_THREADS, 0));
+        static int per_sm_cached = 0, fin_per_sm_cached = 0;             // occupancy queries are pure functions of the kernels
+        if (!per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_trace<false>, TRACE_THREADS, 0));
+        per_sm = per_sm_cached;
         const int grid_trace = sc.sm_count * (per_sm > 0 ? per_sm : 4);
-        int fin_per_sm = 0;                                               // k_finish: one resident wave of 256-thread blocks
-        CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm, k_finish<false, false>, 256, 0));
+        if (!fin_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm_cached, k_finish<false, false>, 256, 0));
+        const int fin_per_sm = fin_per_sm_cached;                         // k_finish: one resident wave of 256-thread blocks
         const int grid_fin = sc.sm_count * (fin_per_sm > 0 ? fin_per_sm : 2);
         const char* tail_env = getenv("RBRT_TAIL_RAYS");                  // tuning knob; default = one ray per resident lane
         const uint32_t tail_rays = (o.flags & RBRT_OPT_NO_TAIL_KERNEL) ? 0u : (tail_env ? (uint32_t)atoi(tail_env) : (uint32_t)grid_fin * 256u);
@@ -686,7 +693,8 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 }
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (brute) { if (count) k_trace_brute<true><<<grid, 256, 0, st>>>(wp, it); else k_trace_brute<false><<<grid, 256, 0, st>>>(wp, it); }
-                else { if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it); else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it); }
+                else if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
+                else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
                 ++launches; ++iterations;
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (it < max_depth) { k_shade<<<grid, 256, 0, st>>>(wp, it); ++launches; }
@@ -721,10 +729,14 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 std::vector<IterCtr> hc(max_depth + 2);
                 CKR(cudaMemcpy(hc.data(), wb.ctr, sizeof(IterCtr) * (max_depth + 2), cudaMemcpyDeviceToHost));
                 size_t per_batch = max_depth + 1, first = 2 * (iterations - per_batch);
+                float t_first = 0; cudaEventElapsedTime(&t_first, ev0, wb.ev[first]);
+                fprintf(stderr, "setup + generate (ev0 -> first trace): %.3f ms; tail kernel ran at it %d\n", t_first, (int)hc[0].pad - 1);
                 for (uint32_t it = 0; it <= max_depth; ++it) {
-                    float t = 0; cudaEventElapsedTime(&t, wb.ev[first + 2 * it], wb.ev[first + 2 * it + 1]);
-                    fprintf(stderr, "it %2u rays %9u traversed %9u  lambert %9u metal %9u glass %9u  trace %8.3f ms\n", it, hc[it].ray_count,
-                            hc[it].cand_count, hc[it].mat_count[0], hc[it].mat_count[1], hc[it].mat_count[2], t);
+                    float t = 0, g = 0; cudaEventElapsedTime(&t, wb.ev[first + 2 * it], wb.ev[first + 2 * it + 1]);
+                    if (it < max_depth) cudaEventElapsedTime(&g, wb.ev[first + 2 * it + 1], wb.ev[first + 2 * it + 2]);
+                    else cudaEventElapsedTime(&g, wb.ev[first + 2 * it + 1], ev1);
+                    fprintf(stderr, "it %2u rays %9u traversed %9u  lambert %9u metal %9u glass %9u  trace %8.3f ms  then shade+finish %8.3f ms\n", it, hc[it].ray_count,
+                            hc[it].cand_count, hc[it].mat_count[0], hc[it].mat_count[1], hc[it].mat_count[2], t, g);
                 }
             }
         }
