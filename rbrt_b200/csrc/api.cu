@@ -143,7 +143,7 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
     float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals; uint32_t* d_kind; MeshDev* d_meshes;
     {
         const size_t b_sph = a256(16ull * ns), b_mat = a256(16ull * (ns + nm)), b_kind = a256(4ull * (ns + nm)), b_tris = a256(48ull * total_eff),
-                     b_nodes = a256(32ull * total_eff), b_nrm = a256(16ull * total_eff), b_mesh = a256(sizeof(MeshDev) * nm);
+                     b_nodes = a256(64ull * total_eff), b_nrm = a256(16ull * total_eff), b_mesh = a256(sizeof(MeshDev) * nm);
         char* base = nullptr;
         CKS(arena_alloc(sc, b_nodes + b_tris + b_nrm + b_sph + b_mat + b_kind + b_mesh, &base));
         d_nodes = (float4*)base; base += b_nodes;                          // nodes and triangles adjacent: the data every ray re-reads
@@ -183,9 +183,9 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
             float pad = pad_rel * mx;
             uint64_t live = 0; int height = 0;
             cudaError_t ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, d_tris + 3 * tri_off, d_normals + tri_off,
-                                            d_nodes + 2 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
+                                            d_nodes + 4 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
             if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
-            if (height + 2 > 96) { set_error("mesh %u: BVH height %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
+            if (3 * height + 2 > 192) { set_error("mesh %u: BVH depth %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
             live_total += live;
         }
         ms_upload += t2 - t1; ms_build += now_ms() - t2;

@@ -5,8 +5,8 @@
 // (triangle.rs:30-34) are computed with the same individually rounded f32 ops, then the
 // triangles are put in Morton order and a binary LBVH is built over them:
 //   63-bit Morton code of the triangle-box centre -> radix sort (CUB) -> Karras 2012 topology
-//   -> bottom-up AABB refit with atomic arrival flags -> emission of 32-byte traversal nodes (child boxes on a
-//   16-bit grid over the mesh box) with subtrees of <= leaf_size triangles collapsed into leaves.
+//   -> bottom-up AABB refit with atomic arrival flags -> top-down collapse into 4-wide nodes of 64 bytes (child
+//   boxes on a 16-bit grid over the mesh box), subtrees of <= leaf_size triangles collapsed into leaves.
 #include "bvh_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cstring>
@@ -126,8 +126,8 @@ __global__ void k_refit(int n, const int2* __restrict__ children, const int* __r
     }
 }
 
-// traversal node emission with leaf collapse: 32-byte nodes, child boxes quantised OUTWARD (plus one step of margin,
-// see intersect.cuh) onto the mesh's 16-bit grid  bound = qorg + q * qstep
+// traversal node emission: child boxes quantised OUTWARD (plus one step of margin, see intersect.cuh) onto the mesh's
+// 16-bit grid  bound = qorg + q * qstep
 struct QGrid { float org[3], step[3]; };
 
 __device__ __forceinline__ uint32_t quant_lo(float v, float org, float step) {
@@ -141,38 +141,74 @@ __device__ __forceinline__ uint32_t quant_hi(float v, float org, float step) {
     return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
 }
 
-__global__ void k_emit_nodes(int n, uint32_t leaf_size, QGrid g, const int2* __restrict__ children, const int2* __restrict__ range,
-                             const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                             const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
-                             uint4* __restrict__ out, unsigned long long* __restrict__ live) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int2 rg = range[i];
-    uint32_t cnt = (uint32_t)(rg.y - rg.x + 1);
-    if (i != 0 && cnt <= leaf_size) {                                     // swallowed by an ancestor's leaf
-        out[2 * (size_t)i] = out[2 * (size_t)i + 1] = make_uint4(0, 0, 0, 0);
-        return;
-    }
-    atomicAdd(live, 1ull);
-    int2 ch = children[i];
-    uint32_t q[2][3]; int32_t ref[2];
-    int c[2] = {ch.x, ch.y};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        float4 lo, hi;
-        if (c[k] < 0) { lo = leaf_lo[~c[k]]; hi = leaf_hi[~c[k]]; ref[k] = make_leaf_ref((uint32_t)(~c[k]), 1); }
-        else {
-            lo = node_lo[c[k]]; hi = node_hi[c[k]];
-            int2 r = range[c[k]];
-            uint32_t cc = (uint32_t)(r.y - r.x + 1);
-            ref[k] = cc <= leaf_size ? make_leaf_ref((uint32_t)r.x, cc) : c[k];
+// ------------------------------------------------------------------ binary LBVH -> 4-wide nodes (64 bytes)
+// Level-synchronous top-down collapse.  `queue[j]` = the binary node that becomes wide node j (its position in the
+// queue IS its output slot); every launch handles one BFS level [begin, end) and appends the internal children it
+// keeps to the tail.  A binary node's two children are expanded greedily — largest surface area first — until there
+// are four (subtrees of <= leaf_size triangles count as leaves and are never expanded).
+struct CollapseState { uint32_t begin[2], end[2], tail, done, depth, pad; };
+
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_collapse4(uint32_t level, uint32_t leaf_size, QGrid g, const int2* __restrict__ children, const int2* __restrict__ range,
+                            const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                            const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                            uint32_t* __restrict__ queue, CollapseState* st, uint4* __restrict__ out) {
+    const uint32_t begin = st->begin[level & 1], end = st->end[level & 1];
+    for (uint32_t j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
+        const int i = (int)queue[j];
+        int src[4]; int32_t ref[4]; int nc = 2;
+        auto effective = [&](int c, int k) {                               // binary child -> (source of its box, traversal ref)
+            src[k] = c;
+            if (c < 0) { ref[k] = make_leaf_ref((uint32_t)(~c), 1); return; }
+            int2 r = range[c];
+            uint32_t cnt = (uint32_t)(r.y - r.x + 1);
+            ref[k] = cnt <= leaf_size ? make_leaf_ref((uint32_t)r.x, cnt) : c;
+        };
+        int2 ch = children[i];
+        effective(ch.x, 0); effective(ch.y, 1);
+        for (int round = 0; round < 2; ++round) {
+            int best = -1; float best_a = -1.0f;
+            for (int k = 0; k < nc; ++k)
+                if (ref[k] >= 0) { float a = half_area(node_lo[src[k]], node_hi[src[k]]); if (a > best_a) { best_a = a; best = k; } }
+            if (best < 0) break;
+            int2 c2 = children[src[best]];
+            effective(c2.x, best); effective(c2.y, nc); ++nc;
         }
-        q[k][0] = quant_lo(lo.x, g.org[0], g.step[0]) | (quant_hi(hi.x, g.org[0], g.step[0]) << 16);
-        q[k][1] = quant_lo(lo.y, g.org[1], g.step[1]) | (quant_hi(hi.y, g.org[1], g.step[1]) << 16);
-        q[k][2] = quant_lo(lo.z, g.org[2], g.step[2]) | (quant_hi(hi.z, g.org[2], g.step[2]) << 16);
+        uint32_t q[4][3]; int32_t refs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < nc) {
+                float4 lo, hi;
+                if (src[k] < 0) { lo = leaf_lo[~src[k]]; hi = leaf_hi[~src[k]]; } else { lo = node_lo[src[k]]; hi = node_hi[src[k]]; }
+                q[k][0] = quant_lo(lo.x, g.org[0], g.step[0]) | (quant_hi(hi.x, g.org[0], g.step[0]) << 16);
+                q[k][1] = quant_lo(lo.y, g.org[1], g.step[1]) | (quant_hi(hi.y, g.org[1], g.step[1]) << 16);
+                q[k][2] = quant_lo(lo.z, g.org[2], g.step[2]) | (quant_hi(hi.z, g.org[2], g.step[2]) << 16);
+                if (ref[k] >= 0) { uint32_t pos = atomicAdd(&st->tail, 1u); queue[pos] = (uint32_t)src[k]; refs[k] = (int32_t)pos; }
+                else refs[k] = ref[k];
+            } else {                                                       // unused slot: inverted box (lo 65535, hi 0), never hit
+                q[k][0] = q[k][1] = q[k][2] = 0x0000FFFFu;
+                refs[k] = make_leaf_ref(0, 1);
+            }
+        }
+        out[4 * (size_t)j] = make_uint4(q[0][0], q[0][1], q[0][2], q[1][0]);
+        out[4 * (size_t)j + 1] = make_uint4(q[1][1], q[1][2], q[2][0], q[2][1]);
+        out[4 * (size_t)j + 2] = make_uint4(q[2][2], q[3][0], q[3][1], q[3][2]);
+        out[4 * (size_t)j + 3] = make_uint4((uint32_t)refs[0], (uint32_t)refs[1], (uint32_t)refs[2], (uint32_t)refs[3]);
     }
-    out[2 * (size_t)i] = make_uint4(q[0][0], q[0][1], q[0][2], q[1][0]);
-    out[2 * (size_t)i + 1] = make_uint4(q[1][1], q[1][2], (uint32_t)ref[0], (uint32_t)ref[1]);
+    // the last block to finish publishes the next level (in the other parity slot: blocks of THIS launch that become
+    // resident late still read the current one)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&st->done, 1u) == gridDim.x - 1) {
+            st->begin[(level + 1) & 1] = end; st->end[(level + 1) & 1] = st->tail; st->done = 0;
+            if (end > begin) st->depth = level + 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ exact mesh AABB (aabbox.rs:62-88) on the device
@@ -273,7 +309,7 @@ cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], co
     int2* children = (int2*)take(8ull * ni); int2* range = (int2*)take(8ull * ni);
     int* parent_int = (int*)take(4ull * ni); int* parent_leaf = (int*)take(4ull * n);
     int* flags = (int*)take(4ull * ni); int* height = (int*)take(4ull * ni);
-    unsigned long long* d_live = (unsigned long long*)take(8);
+    uint32_t* queue = (uint32_t*)take(4ull * ni); CollapseState* cstate = (CollapseState*)take(sizeof(CollapseState));
     void* tmp = take(tmp_bytes ? tmp_bytes : 16);
     if (off > g_scratch_bytes[dev & 63]) return cudaErrorMemoryAllocation;
 
@@ -290,19 +326,30 @@ cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], co
         CK(cudaStreamSynchronize(st));
         return cudaSuccess;
     }
-    CK(cudaMemsetAsync(flags, 0, 4ull * ni, st)); CK(cudaMemsetAsync(d_live, 0, 8, st));
+    CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
     k_karras<<<(ni + B - 1) / B, B, 0, st>>>(keys_s, (int)n, children, range, parent_int, parent_leaf);
     CK(cudaGetLastError());
     k_refit<<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
     CK(cudaGetLastError());
-    k_emit_nodes<<<(ni + B - 1) / B, B, 0, st>>>((int)n, leaf_size, grid, children, range, leaf_lo, leaf_hi, node_lo, node_hi,
-                                                 reinterpret_cast<uint4*>(d_nodes), d_live);
-    CK(cudaGetLastError());
-    unsigned long long live = 0; int h = 0;
-    CK(cudaMemcpyAsync(&live, d_live, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&h, height, 4, cudaMemcpyDeviceToHost, st));
+    int hbin = 0;                                                          // binary height bounds the number of BFS levels
+    CK(cudaMemcpyAsync(&hbin, height, 4, cudaMemcpyDeviceToHost, st));
+    {
+        CollapseState init; memset(&init, 0, sizeof(init));
+        init.end[0] = 1; init.tail = 1;
+        const uint32_t root = 0;
+        CK(cudaMemcpyAsync(cstate, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(queue, &root, 4, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaStreamSynchronize(st));
-    *live_nodes = live; *tree_height = h; *root_ref = 0;
+    uint32_t gcol = (ni + B - 1) / B; if (gcol > 148u * 8u) gcol = 148u * 8u;
+    for (int level = 0; level < hbin; ++level)
+        k_collapse4<<<gcol, B, 0, st>>>((uint32_t)level, leaf_size, grid, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate,
+                                        reinterpret_cast<uint4*>(d_nodes));
+    CK(cudaGetLastError());
+    CollapseState fin;
+    CK(cudaMemcpyAsync(&fin, cstate, sizeof(fin), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *live_nodes = fin.tail; *tree_height = (int)fin.depth; *root_ref = 0;
     return cudaSuccess;
 }
 

@@ -84,7 +84,7 @@ struct MeshDev {
 struct SceneDev {
     const float4* spheres;     // {cx, cy, cz, r}
     const float4* tris;        // 3 x float4 per triangle: {v0.xyz, bits(orig idx)}, {e1.xyz, 0}, {e2.xyz, 0}
-    const float4* nodes;       // 2 x 16 B per BVH2 node: child boxes on the mesh's 16-bit grid + 2 child refs (intersect.cuh)
+    const float4* nodes;       // 4 x 16 B per 4-wide BVH node: child boxes on the mesh's 16-bit grid + 4 child refs (intersect.cuh)
     const float4* normals;     // {n.xyz, 0} per triangle, original order
     const float4* mat;         // per element: {albedo.xyz, param}
     const uint32_t* mat_kind;  // per element: RBRT_MAT_*

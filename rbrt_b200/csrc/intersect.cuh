@@ -12,7 +12,7 @@ namespace rbrt {
 #define RBRT_MIN_DIST 0.001f       // lib.rs:44
 #define RBRT_MAX_DIST 2000.0f      // lib.rs:45
 #define RBRT_T_CAP 999.99994f      // 1.0f / 0.001f as f32 (triangle.rs:146): triangle t must be < this
-#define RBRT_STACK 96
+#define RBRT_STACK 192            // traversal stack entries per lane: <= 3 per level of the 4-wide tree + sentinel (checked at build)
 
 struct Hit {
     int kind;            // -1 none, 0 sphere, 1 mesh, -2 NaN (reference panics, sphere.rs:33)
@@ -107,19 +107,22 @@ __device__ __forceinline__ bool mesh_closest_brute(const SceneDev& S, const Mesh
     return best_idx != 0xFFFFFFFFu;
 }
 
-// ------------------------------------------------------------------ BVH2 traversal, 32-byte nodes
-// Node = 2 x uint4:  w0 = {c0.x, c0.y, c0.z, c1.x}   each word = qlo | qhi << 16 on the mesh's 16-bit grid
-//                    w1 = {c1.y, c1.z, ref0, ref1}    ref >= 0: node index; ref < 0: leaf (make_leaf_ref)
-// One 32-byte sector and two 16-byte loads per visit (the first version fetched 64 bytes in four loads and was bound
-// by L1 tag wavefronts).  A 16-bit value becomes the float 2^23 + q with ONE byte-permute (PRMT builds 0x4B00hhll);
-// the permute selector also picks the near or the far bound for the ray's direction sign, so there is no per-axis
-// min/max either:   t = fma(2^23 + q, A, B')  with  A = step * (1/d),  B' = (org - o) * (1/d) - 2^23 * A.
+// ------------------------------------------------------------------ 4-wide BVH traversal, 64-byte nodes
+// Node = 4 x uint4: twelve words {child k: x, y, z}, each word = qlo | qhi << 16 on the mesh's 16-bit grid, then the four
+// child refs (ref >= 0: node index; ref < 0: leaf, make_leaf_ref); unused slots hold an inverted box.
+//   w0 = {c0.x, c0.y, c0.z, c1.x}  w1 = {c1.y, c1.z, c2.x, c2.y}  w2 = {c2.z, c3.x, c3.y, c3.z}  w3 = {ref0..ref3}
+// The trace kernel is bound by the LATENCY of dependent node fetches (profiles/), so the tree is 4 wide: half as
+// many dependent visits per ray as the binary tree it is collapsed from, for the same 16 bytes per child.
+// A 16-bit value becomes the float 2^23 + q with ONE byte-permute (PRMT builds 0x4B00hhll); the permute selector
+// also picks the near or the far bound for the ray's direction sign, so there is no per-axis min/max either:
+//   t = fma(2^23 + q, A, B')  with  A = step * (1/d),  B' = (org - o) * (1/d) - 2^23 * A.
 // B' is rounded once at magnitude ~2^23 |A|, i.e. by up to half a grid step of t; bvh_build.cu therefore quantises
 // child boxes outward AND adds one more step of margin, so the slab test can never reject a box whose triangle
 // the exact Moeller-Trumbore arithmetic above would accept.
 #define RBRT_SENTINEL 0x7FFFFFFF
 #define RBRT_SEL_LO 0x7610u           // PRMT selectors: bytes {0,1} / {2,3} of the node word under 0x4B00....
 #define RBRT_SEL_HI 0x7632u
+#define RBRT_MISS_T 3.0e38f
 
 struct RaySlabs {
     float ax, ay, az, bx, by, bz;     // per-axis t = fma(m, a, b)
@@ -144,28 +147,28 @@ __device__ __forceinline__ RaySlabs ray_slabs(const MeshDev& M, f3 o, f3 d) {
 
 __device__ __forceinline__ float q16(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
 
-// One node visit: returns the next reference to process (near child, or the popped stack top).
-__device__ __forceinline__ int32_t bvh2_step(const uint4* __restrict__ nd, const RaySlabs& R, float t_prune, int32_t* stack, int& sp) {
-    const uint4 w0 = __ldg(nd), w1 = __ldg(nd + 1);
+// One node visit: returns the next reference to process (nearest hit child, or the popped stack top); the other
+// hit children are pushed far-to-near.
+__device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const RaySlabs& R, float t_prune, int32_t* stack, int& sp) {
+    const uint4 w0 = __ldg(nd), w1 = __ldg(nd + 1), w2 = __ldg(nd + 2), w3 = __ldg(nd + 3);
     const uint32_t fx = R.nx ^ 0x22u, fy = R.ny ^ 0x22u, fz = R.nz ^ 0x22u;
-    float t0n = fmaxf(fmaxf(__fmaf_rn(q16(w0.x, R.nx), R.ax, R.bx), __fmaf_rn(q16(w0.y, R.ny), R.ay, R.by)),
-                      fmaxf(__fmaf_rn(q16(w0.z, R.nz), R.az, R.bz), 0.0f));
-    float t0f = fminf(fminf(__fmaf_rn(q16(w0.x, fx), R.ax, R.bx), __fmaf_rn(q16(w0.y, fy), R.ay, R.by)),
-                      fminf(__fmaf_rn(q16(w0.z, fz), R.az, R.bz), t_prune));
-    float t1n = fmaxf(fmaxf(__fmaf_rn(q16(w0.w, R.nx), R.ax, R.bx), __fmaf_rn(q16(w1.x, R.ny), R.ay, R.by)),
-                      fmaxf(__fmaf_rn(q16(w1.y, R.nz), R.az, R.bz), 0.0f));
-    float t1f = fminf(fminf(__fmaf_rn(q16(w0.w, fx), R.ax, R.bx), __fmaf_rn(q16(w1.x, fy), R.ay, R.by)),
-                      fminf(__fmaf_rn(q16(w1.y, fz), R.az, R.bz), t_prune));
-    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
-    const int32_t r0 = (int32_t)w1.z, r1 = (int32_t)w1.w;
-    if (h0 && h1) {
-        const bool swap = t1n < t0n;
-        stack[sp++] = swap ? r0 : r1;
-        return swap ? r1 : r0;
-    }
-    if (h0) return r0;
-    if (h1) return r1;
-    return stack[--sp];
+    float t[4]; int32_t r[4];
+#define RBRT_CHILD(k, X, Y, Z) { \
+        float tn = fmaxf(fmaxf(__fmaf_rn(q16(X, R.nx), R.ax, R.bx), __fmaf_rn(q16(Y, R.ny), R.ay, R.by)), fmaxf(__fmaf_rn(q16(Z, R.nz), R.az, R.bz), 0.0f)); \
+        float tf = fminf(fminf(__fmaf_rn(q16(X, fx), R.ax, R.bx), __fmaf_rn(q16(Y, fy), R.ay, R.by)), fminf(__fmaf_rn(q16(Z, fz), R.az, R.bz), t_prune)); \
+        t[k] = tn <= tf ? tn : RBRT_MISS_T; }
+    RBRT_CHILD(0, w0.x, w0.y, w0.z) RBRT_CHILD(1, w0.w, w1.x, w1.y) RBRT_CHILD(2, w1.z, w1.w, w2.x) RBRT_CHILD(3, w2.y, w2.z, w2.w)
+#undef RBRT_CHILD
+    r[0] = (int32_t)w3.x; r[1] = (int32_t)w3.y; r[2] = (int32_t)w3.z; r[3] = (int32_t)w3.w;
+    // sort the four (entry distance, ref) pairs ascending; misses end up last
+#define RBRT_CSWAP(a, b) { const bool sw = t[b] < t[a]; const float tl = fminf(t[a], t[b]), th = fmaxf(t[a], t[b]); \
+        const int32_t ra = sw ? r[b] : r[a], rb = sw ? r[a] : r[b]; t[a] = tl; t[b] = th; r[a] = ra; r[b] = rb; }
+    RBRT_CSWAP(0, 1) RBRT_CSWAP(2, 3) RBRT_CSWAP(0, 2) RBRT_CSWAP(1, 3) RBRT_CSWAP(1, 2)
+#undef RBRT_CSWAP
+    if (t[3] < RBRT_MISS_T) stack[sp++] = r[3];
+    if (t[2] < RBRT_MISS_T) stack[sp++] = r[2];
+    if (t[1] < RBRT_MISS_T) stack[sp++] = r[1];
+    return t[0] < RBRT_MISS_T ? r[0] : stack[--sp];
 }
 
 // Leaf: <= 8 contiguous triangle records, exact test, running lexicographic minimum.
@@ -193,14 +196,14 @@ __device__ __forceinline__ bool mesh_closest_bvh(const SceneDev& S, const MeshDe
     best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;                         // min_param init (triangle.rs:398)
     float t_prune = t_limit;
     const RaySlabs R = ray_slabs(M, o, d);
-    const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(S.nodes) + 2 * (size_t)M.node_base;
+    const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(S.nodes) + 4 * (size_t)M.node_base;
     int32_t stack[RBRT_STACK];
     int sp = 0;
     int32_t cur = M.root_ref;
     stack[sp++] = RBRT_SENTINEL;
     uint32_t n_nodes = 0, n_tris = 0;
     while (cur != RBRT_SENTINEL) {
-        if (cur >= 0) { cur = bvh2_step(nodes + 2 * (size_t)cur, R, t_prune, stack, sp); ++n_nodes; }
+        if (cur >= 0) { cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp); ++n_nodes; }
         else { leaf_step(S.tris, M.tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, n_tris); cur = stack[--sp]; }
     }
     if (cnt) { cnt->nodes += n_nodes; cnt->tris += n_tris; }

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32
             if (lim == lim) t_limit = fminf(t_limit, lim);
         }
         t_prune = t_limit; best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;     // min_param init (triangle.rs:398)
-        nodes = reinterpret_cast<const uint4*>(P.S.nodes) + 2 * (size_t)M.node_base; tri_base = M.tri_base;
+        nodes = reinterpret_cast<const uint4*>(P.S.nodes) + 4 * (size_t)M.node_base; tri_base = M.tri_base;
         R = ray_slabs(M, o, d);
         sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
     };
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32
         // ---- while-while traversal: every lane descends to its next leaf, then the leaves are processed together
         for (;;) {
             while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node (intersect.cuh)
-                cur = bvh2_step(nodes + 2 * (size_t)cur, R, t_prune, stack, sp);
+                cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp);
                 if (COUNT) ++n_nodes;
             }
             if (cur < 0) {                                                // leaf: <= 8 contiguous triangles
