@@ -40,13 +40,32 @@ static int ensure_device() {
     return RBRT_OK;
 }
 
-// All device buffers of a scene are carved from ONE allocation (one cudaMalloc at creation, one cudaFree at
-// destruction: each of those calls synchronises the device).
+// All device buffers of a scene are carved from ONE allocation, and a destroyed scene's block is kept for the next
+// scene of the same device (cudaMalloc / cudaFree synchronise the device and occasionally take tens to hundreds of ms;
+// an application that re-creates its scene every frame should not pay that).  rbrt_gpu_release_cache() frees them.
+struct ArenaBlock { void* p; size_t bytes; int device; };
+static std::vector<ArenaBlock> g_arena_pool;
+static void arena_release_all() {
+    int cur = 0; cudaGetDevice(&cur);
+    for (auto& b : g_arena_pool) { cudaSetDevice(b.device); cudaFree(b.p); }
+    g_arena_pool.clear();
+    cudaSetDevice(cur);
+}
 static int arena_alloc(Scene* sc, size_t bytes, char** base) {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 256);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if (!bytes) bytes = 256;
+    int best = -1;
+    for (size_t i = 0; i < g_arena_pool.size(); ++i)
+        if (g_arena_pool[i].device == sc->device && g_arena_pool[i].bytes >= bytes && g_arena_pool[i].bytes <= bytes + bytes / 4 + (1u << 20) &&
+            (best < 0 || g_arena_pool[i].bytes < g_arena_pool[best].bytes)) best = (int)i;
+    void* q = nullptr; size_t got = bytes;
+    if (best >= 0) { q = g_arena_pool[best].p; got = g_arena_pool[best].bytes; g_arena_pool.erase(g_arena_pool.begin() + best); }
+    else {
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) { arena_release_all(); e = cudaMalloc(&q, bytes); }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    }
     sc->allocs.push_back(q);
+    sc->arena_bytes = got;
     sc->info.device_bytes += bytes;
     *base = (char*)q;
     return RBRT_OK;
@@ -55,7 +74,10 @@ static inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 static void destroy_scene(Scene* sc) {
     if (!sc) return;
-    for (void* p : sc->allocs) cudaFree(p);
+    for (void* p : sc->allocs) {
+        if (g_arena_pool.size() < 4) g_arena_pool.push_back(ArenaBlock{p, sc->arena_bytes, sc->device});
+        else cudaFree(p);
+    }
     delete sc;
 }
 
@@ -235,6 +257,7 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
 int rbrt_gpu_release_cache(void) {
     release_device_wave_buffers();
     release_build_scratch();
+    arena_release_all();
     return RBRT_OK;
 }
 

@@ -46,7 +46,8 @@ struct Scene {
     int device = 0;
     SceneDev dev{};
     std::vector<MeshDev> meshes_h;
-    std::vector<void*> allocs;   // every cudaMalloc owned by the scene
+    std::vector<void*> allocs;   // every cudaMalloc owned by the scene (one arena)
+    size_t arena_bytes = 0;
     rbrt_scene_info info{};
     int sm_count = 148;
 };
