@@ -46,7 +46,9 @@ WORKLOADS = {
     "c2": ("C2: scenes/example_scene.yaml with an 81920-triangle displaced icosphere (.obj) for bunny.obj, 1024x768, 50 spp", 1024, 768, 50),
     "c3": ("C3: 1310720-triangle displaced icosphere (radius 40) + 4 spheres, 1920x1080, 64 spp, tile-sharded", 1920, 1080, 64),
     "c4": ("C4: dielectric/metal-heavy scene (36 glass/metal spheres + 20480-triangle glass mesh), depth 50, 1024x768, 256 spp", 1024, 768, 256),
+    "c5": ("C5: 5242880-triangle displaced icosphere (radius 100) + 4 spheres, 3840x2160, 1024 spp, sample-range sharded + NCCL reduce", 3840, 2160, 1024),
 }
+SAMPLE_SHARDED = {"c5"}
 SEED = 0x5EED
 _STDOUT = sys.stdout
 
@@ -74,6 +76,9 @@ def build_workload(name, pinned=False):
                 [(m.triangles, m.material) for m in sc.triangle_meshes], cam_ex)
     if name == "c3":
         cam, spheres, tris, mat = synth.big_mesh_config(8, 40.0)
+        return spheres, [(tris, mat)], cam
+    if name == "c5":
+        cam, spheres, tris, mat = synth.big_mesh_config(9, 100.0)
         return spheres, [(tris, mat)], cam
     if name == "c4":
         spheres, tris, mat = synth.stress_config()
@@ -105,46 +110,74 @@ def pin_meshes(meshes):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons of one GPU (B200_PROFILING.md).  nvidia-smi needs a few hundred ms before its first
+    sample, longer than a whole timed region of this benchmark, so the sampler is started BEFORE the warm-up steps and the
+    samples are filtered by their timestamps: those inside [mark_begin, mark_end] (the timed region, padded by one sampling
+    period) are used; if the region was too short to catch any, the samples of the warm-up steps (same load) are used and
+    `window` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 20
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t_begin, self.t_end, self.t_start = index, None, [], None, None, time.time()
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
         return self
 
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(2.5 * self.PERIOD_MS / 1e3)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons, power = [], [], set(), []
+        import datetime
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+                vals = (float(f[1]), float(f[2]), float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            ts = None
+            for fmt in ("%Y/%m/%d %H:%M:%S.%f", "%Y-%m-%d %H:%M:%S.%f", "%Y/%m/%d %H:%M:%S"):
+                try:
+                    ts = datetime.datetime.strptime(f[0], fmt).timestamp()
+                    break
+                except ValueError:
+                    pass
+            rows.append((ts if ts is not None else (self.t_begin or 0.0), *vals, f[4:8]))
+        pad = self.PERIOD_MS / 1e3
+        inside = [r for r in rows if self.t_begin is not None and self.t_begin - pad <= r[0] <= (self.t_end or time.time()) + pad]
+        window = "timed region"
+        if not inside:
+            inside = [r for r in rows if r[0] <= (self.t_end or time.time()) + pad]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(power)}
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside), "reasons": sorted(reasons),
+                "samples": len(inside), "power_w_max": max(r[3] for r in inside), "window": window}
 
 
 def peaks():
@@ -238,7 +271,8 @@ def workload_config(name, spheres, meshes, n_gpus):
     desc, W, H, spp = WORKLOADS[name]
     return {"workload": desc, "width": W, "height": H, "spp": spp, "max_depth": 50, "spheres": len(spheres),
             "triangles": int(sum(len(t) for t, _ in meshes)), "seed": SEED,
-            "sharding": "none" if n_gpus == 1 else f"interleaved 8x4-pixel tiles over {n_gpus} ranks + one NCCL reduce of the f32 accumulator",
+            "sharding": "none" if n_gpus == 1 else (f"sample ranges over {n_gpus} ranks + one NCCL reduce (sum) of the f32 accumulator" if name in SAMPLE_SHARDED
+                                                    else f"interleaved 8x4-pixel tiles over {n_gpus} ranks + one NCCL reduce of the f32 accumulator"),
             "l2_policy": "no explicit flush: per step the wavefront streams >400 MB of ray/hit queues and the scene (nodes+triangles+normals) "
                          "is larger than or comparable to L2; inputs larger than L2"}
 
@@ -274,7 +308,8 @@ def run_gpu(args):
     stream = torch.cuda.current_stream()
     accum = torch.empty(H * W * 4, dtype=torch.float32, device="cuda")
     rgb = torch.empty(H * W * 3, dtype=torch.uint8, device="cuda")
-    shard = dict(shard_mode=_abi.SHARD_TILES, shard_rank=rank, shard_count=world) if world > 1 else {}
+    shard_mode = _abi.SHARD_SAMPLES if args.workload in SAMPLE_SHARDED else _abi.SHARD_TILES
+    shard = dict(shard_mode=shard_mode, shard_rank=rank, shard_count=world) if world > 1 else {}
 
     def barrier():
         if world > 1:
@@ -296,13 +331,14 @@ def run_gpu(args):
     counts = cst.as_dict()
 
     # ---- resident arm
-    for _ in range(max(args.warmup, 3)):
-        step_resident(scene.handle(), dict(time_kernels=True), _abi.StatsC())
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
     with ClockSampler(local) as clk:
+        time.sleep(0.3)                                       # let nvidia-smi deliver its first samples
+        for _ in range(max(args.warmup, 3)):
+            step_resident(scene.handle(), dict(time_kernels=True), _abi.StatsC())
         barrier()
+        clk.mark_begin()
         e0.record(stream)
         for _ in range(args.steps):
             st = _abi.StatsC()
@@ -310,6 +346,7 @@ def run_gpu(args):
             stats.append(st.as_dict())
         e1.record(stream)
         barrier()
+        clk.mark_end()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([sum(s["rays"] for s in stats), sum(s["paths"] for s in stats), sum(s["launches"] for s in stats) + (args.steps if rank == 0 else 0),

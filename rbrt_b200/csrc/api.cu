@@ -139,10 +139,14 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
 
     Scene* sc = new Scene();
     sc->device = g_device;
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, g_device);
-    if (e != cudaSuccess) { destroy_scene(sc); return cuda_fail(e, "cudaGetDeviceProperties"); }
-    sc->sm_count = prop.multiProcessorCount;
+    static int sm_count_cached[64] = {0};                                  // cudaGetDeviceProperties is slow (tens of ms at times)
+    if (!sm_count_cached[g_device & 63]) {
+        int smc = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, g_device);
+        if (e != cudaSuccess) { destroy_scene(sc); return cuda_fail(e, "cudaDeviceGetAttribute"); }
+        sm_count_cached[g_device & 63] = smc;
+    }
+    sc->sm_count = sm_count_cached[g_device & 63];
     sc->info.num_spheres = ns; sc->info.num_meshes = nm;
     sc->info.num_triangles = total_tris; sc->info.num_triangles_tested = total_eff;
     double t0 = now_ms();
