@@ -1,0 +1,80 @@
+//! Raw bindings of include/rbrt_gpu.h (SOURCE ONLY, uncompiled: see Cargo.toml) plus the safe twins of
+//! `create_scene_from_scene_blueprint` (rbrt_lib/src/blueprints.rs:132) and `render_scene` (rbrt_lib/src/lib.rs:75)
+//! that `rbrt_lib` would re-export.  Struct layouts are `#[repr(C)]` mirrors of the header; `RbrtCamera` has the field
+//! order of `rbrt_lib::cam::Camera` (cam.rs:4-19).
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] #[derive(Copy, Clone, Debug, Default)] pub struct RbrtVec3 { pub x: f32, pub y: f32, pub z: f32 }
+#[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtRay { pub origin: RbrtVec3, pub direction: RbrtVec3 }
+#[repr(C)] #[derive(Copy, Clone, Debug)]
+pub struct RbrtCamera {
+    pub hor_fov_rad: f32, pub img_width_pix: u32, pub img_height_mm: f32, pub vert_fov_rad: f32,
+    pub img_height_pix: u32, pub img_width_mm: f32, pub position: RbrtVec3, pub focal_len_mm: f32,
+    pub look_at: RbrtVec3, pub up: RbrtVec3, pub right: RbrtVec3, pub img_center_point: RbrtVec3,
+    pub mm_per_pix_hor: f32, pub mm_per_pix_vert: f32,
+}
+pub const RBRT_MAT_LAMBERTIAN: u32 = 0;
+pub const RBRT_MAT_METAL: u32 = 1;
+pub const RBRT_MAT_DIELECTRIC: u32 = 2;
+#[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtMaterial { pub kind: u32, pub albedo: RbrtVec3, pub param: f32 }
+#[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtSphereDesc { pub center: RbrtVec3, pub radius: f32, pub material: RbrtMaterial }
+#[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtMeshDesc { pub tri_vertices: *const f32, pub num_triangles: u64, pub material: RbrtMaterial }
+#[repr(C)] #[derive(Copy, Clone, Debug, Default)]
+pub struct RbrtRenderOpts { pub seed: u64, pub max_depth: u32, pub trace_mode: u32, pub shard_mode: u32, pub shard_rank: u32,
+                            pub shard_count: u32, pub batch_paths: u32, pub integrator: u32, pub flags: u32 }
+#[repr(C)] #[derive(Copy, Clone, Debug, Default)]
+pub struct RbrtStats { pub rays: u64, pub paths: u64, pub nan_rays: u64, pub node_visits: u64, pub tri_tests: u64, pub ms_total: f64,
+                       pub ms_device: f64, pub ms_trace: f64, pub ms_h2d: f64, pub ms_d2h: f64, pub launches: u32, pub iterations: u32,
+                       pub traversed_rays: u64 }
+pub enum RbrtScene {}
+
+extern "C" {
+    pub fn rbrt_camera_new(position: RbrtVec3, look_at: RbrtVec3, up: RbrtVec3, img_height_pix: u32, img_width_pix: u32,
+                           focal_len_mm: f32, out: *mut RbrtCamera) -> c_int;
+    pub fn rbrt_transform_vertices(xyz: *mut f32, n_vertices: u64, scale: f32, rotation_rad: RbrtVec3, translation: RbrtVec3) -> c_int;
+    pub fn rbrt_gpu_init(device: c_int) -> c_int;
+    pub fn rbrt_gpu_scene_create(spheres: *const RbrtSphereDesc, num_spheres: u32, meshes: *const RbrtMeshDesc, num_meshes: u32,
+                                 opts: *const c_void, out: *mut *mut RbrtScene) -> c_int;
+    pub fn rbrt_gpu_scene_destroy(scene: *mut RbrtScene) -> c_int;
+    pub fn rbrt_gpu_render(scene: *const RbrtScene, cam: *const RbrtCamera, num_samples: u32, opts: *const RbrtRenderOpts,
+                           rgb_out: *mut u8, stats: *mut RbrtStats) -> c_int;
+    pub fn rbrt_gpu_render_hdr(scene: *const RbrtScene, cam: *const RbrtCamera, num_samples: u32, opts: *const RbrtRenderOpts,
+                               rgb_f32_out: *mut f32, stats: *mut RbrtStats) -> c_int;
+    pub fn rbrt_gpu_release_cache() -> c_int;
+    pub fn rbrt_last_error() -> *const c_char;
+    pub fn rbrt_gpu_version() -> *const c_char;
+}
+
+/// Keeps the reference's convention: errors are panics (blueprints.rs:80,87, main.rs:86-91).
+pub fn check(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(rbrt_last_error()) }.to_string_lossy().into_owned();
+        panic!("rbrt_gpu error {}: {}", rc, msg);
+    }
+}
+
+/// Owning handle of a GPU scene (flattened SoA buffers + one BVH per mesh).
+pub struct GpuScene(*mut RbrtScene);
+unsafe impl Send for GpuScene {}
+impl Drop for GpuScene { fn drop(&mut self) { unsafe { rbrt_gpu_scene_destroy(self.0); } } }
+
+impl GpuScene {
+    /// `meshes`: world-space triangle soup, 9 f32 per triangle, already scale -> rotate_point -> translate'd (mesh.rs:102-112).
+    pub fn new(spheres: &[RbrtSphereDesc], meshes: &[(&[f32], RbrtMaterial)]) -> GpuScene {
+        let descs: Vec<RbrtMeshDesc> = meshes.iter()
+            .map(|(t, m)| RbrtMeshDesc { tri_vertices: t.as_ptr(), num_triangles: (t.len() / 9) as u64, material: *m }).collect();
+        let mut h: *mut RbrtScene = std::ptr::null_mut();
+        check(unsafe { rbrt_gpu_scene_create(spheres.as_ptr(), spheres.len() as u32, descs.as_ptr(), descs.len() as u32, std::ptr::null(), &mut h) });
+        GpuScene(h)
+    }
+
+    /// Twin of `render_scene(cam, num_samples, scene)` (lib.rs:75-79): row-major RGB8, W*H*3 bytes =
+    /// the buffer of `image::ImageBuffer<Rgb<u8>, Vec<u8>>` (wrap with `ImageBuffer::from_raw(w, h, buf)`).
+    pub fn render(&self, cam: &RbrtCamera, num_samples: u32, seed: u64) -> Vec<u8> {
+        let mut buf = vec![0u8; (cam.img_width_pix as usize) * (cam.img_height_pix as usize) * 3];
+        let opts = RbrtRenderOpts { seed, ..Default::default() };
+        check(unsafe { rbrt_gpu_render(self.0, cam, num_samples, &opts, buf.as_mut_ptr(), std::ptr::null_mut()) });
+        buf
+    }
+}

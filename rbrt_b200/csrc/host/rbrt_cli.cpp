@@ -1,0 +1,380 @@
+// rbrt_cli.cpp — the `rbrt` command line (reference: src/main.rs:9-92) hosted in C++ over the C-ABI of
+// include/rbrt_gpu.h.  The reference's host language is Rust and no Rust toolchain exists in the build image, so the
+// compiled host side is C++: same flags and defaults (main.rs:14-50), same call sequence (main.rs:70-91)
+//     load_blueprints_from_yaml_file -> Camera::new(height, width) -> create_scene_from_scene_blueprint -> render_scene -> save
+// with the scene description of rbrt_lib/src/blueprints.rs:15-158 (YAML), the .obj loading and vertex transform of
+// rbrt_lib/src/mesh.rs:78-121, and the reference's messages.  The hot path is entirely inside librbrt_gpu.so.
+//
+// Third-party pieces of the reference that are re-stated here, host-side and outside the hot path (parity unpinned by the
+// reference's tests): serde_yaml 0.9 -> a parser for the block-style YAML subset the scene files use (nested mappings by
+// indentation, `- ` sequences, scalars, `#` comments, `---`); tobj 4 -> `v` / `f` records, one model per `o`/`g`, position
+// indices only, faces consumed as index triples (tobj default LoadOptions: no triangulation); image 0.25 -> an 8-bit RGB
+// PNG written with zlib (lossless, so any conforming encoder stores the same pixels) or binary PPM by extension.
+#include <zlib.h>
+
+#include <cctype>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/rbrt_gpu.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string& msg) {              // the reference panics; we exit(101) like a Rust panic does
+    fprintf(stderr, "%s\n", msg.c_str());
+    exit(101);
+}
+
+// ------------------------------------------------------------------ YAML subset
+struct Node {
+    enum Kind { Scalar, Map, Seq } kind = Scalar;
+    std::string scalar;
+    std::vector<std::pair<std::string, std::shared_ptr<Node>>> map;
+    std::vector<std::shared_ptr<Node>> seq;
+    const Node* get(const std::string& k) const {
+        for (auto& kv : map) if (kv.first == k) return kv.second.get();
+        return nullptr;
+    }
+};
+
+struct Line { int indent; std::string text; };
+
+std::string strip(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char)s[a])) ++a;
+    while (b > a && isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+std::string unquote(std::string s) {
+    s = strip(s);
+    if (s.size() >= 2 && ((s.front() == '"' && s.back() == '"') || (s.front() == '\'' && s.back() == '\''))) return s.substr(1, s.size() - 2);
+    return s;
+}
+std::string strip_comment(const std::string& s) {
+    bool q1 = false, q2 = false;
+    for (size_t i = 0; i < s.size(); ++i) {
+        if (s[i] == '"' && !q1) q2 = !q2;
+        else if (s[i] == '\'' && !q2) q1 = !q1;
+        else if (s[i] == '#' && !q1 && !q2 && (i == 0 || isspace((unsigned char)s[i - 1]))) return s.substr(0, i);
+    }
+    return s;
+}
+
+std::shared_ptr<Node> parse_block(const std::vector<Line>& L, size_t& i, int indent);
+
+// value that follows "key:" — inline scalar, or a nested block on the following lines
+std::shared_ptr<Node> parse_value(const std::vector<Line>& L, size_t& i, const std::string& rest, int parent_indent) {
+    std::string r = strip(rest);
+    if (!r.empty()) { auto n = std::make_shared<Node>(); n->scalar = unquote(r); return n; }
+    if (i < L.size() && (L[i].indent > parent_indent || (L[i].indent == parent_indent && L[i].text.rfind("- ", 0) == 0)))
+        return parse_block(L, i, L[i].indent);
+    return std::make_shared<Node>();                        // empty value
+}
+
+std::shared_ptr<Node> parse_block(const std::vector<Line>& L, size_t& i, int indent) {
+    auto n = std::make_shared<Node>();
+    if (L[i].text.rfind("- ", 0) == 0 || L[i].text == "-") {
+        n->kind = Node::Seq;
+        while (i < L.size() && L[i].indent == indent && (L[i].text.rfind("- ", 0) == 0 || L[i].text == "-")) {
+            // rewrite "- key: v" as an item block whose first line is "key: v" indented by 2
+            std::vector<Line> item;
+            std::string first = L[i].text.size() > 2 ? L[i].text.substr(2) : "";
+            int item_indent = indent + 2;
+            size_t j = i + 1;
+            if (!strip(first).empty()) item.push_back(Line{item_indent, strip(first)});
+            while (j < L.size() && L[j].indent > indent) { item.push_back(L[j]); ++j; }
+            if (item.empty()) n->seq.push_back(std::make_shared<Node>());
+            else if (item.size() == 1 && item[0].text.find(':') == std::string::npos) { auto s = std::make_shared<Node>(); s->scalar = unquote(item[0].text); n->seq.push_back(s); }
+            else { size_t k = 0; n->seq.push_back(parse_block(item, k, item[0].indent)); }
+            i = j;
+        }
+        return n;
+    }
+    n->kind = Node::Map;
+    while (i < L.size() && L[i].indent == indent) {
+        const std::string& t = L[i].text;
+        size_t c = t.find(':');
+        if (c == std::string::npos) die("Unable to parse scene blueprint: expected `key: value`, got `" + t + "`");
+        std::string key = unquote(t.substr(0, c)), rest = t.substr(c + 1);
+        ++i;
+        n->map.emplace_back(key, parse_value(L, i, rest, indent));
+    }
+    return n;
+}
+
+std::shared_ptr<Node> parse_yaml(std::istream& in) {
+    std::vector<Line> L;
+    std::string raw;
+    while (std::getline(in, raw)) {
+        std::string s = strip_comment(raw);
+        if (strip(s).empty() || strip(s) == "---" || strip(s) == "...") continue;
+        int ind = 0;
+        while (ind < (int)s.size() && s[ind] == ' ') ++ind;
+        L.push_back(Line{ind, strip(s)});
+    }
+    if (L.empty()) die("Unable to parse scene blueprint: empty document");
+    size_t i = 0;
+    return parse_block(L, i, L[0].indent);
+}
+
+float as_f32(const Node* n, const char* what) {
+    if (!n || n->kind != Node::Scalar || n->scalar.empty()) die(std::string("Unable to parse scene blueprint: missing field `") + what + "`");
+    char* end = nullptr;
+    float v = strtof(n->scalar.c_str(), &end);
+    if (end == n->scalar.c_str()) die(std::string("Unable to parse scene blueprint: `") + what + "` is not a number");
+    return v;
+}
+rbrt_vec3 as_vec3(const Node* n, const char* what) {
+    if (!n || n->kind != Node::Map) die(std::string("Unable to parse scene blueprint: missing field `") + what + "`");
+    return rbrt_vec3{as_f32(n->get("x"), what), as_f32(n->get("y"), what), as_f32(n->get("z"), what)};
+}
+std::string as_str(const Node* n, const char* what) {
+    if (!n || n->kind != Node::Scalar) die(std::string("Unable to parse scene blueprint: missing field `") + what + "`");
+    return n->scalar;
+}
+
+// ------------------------------------------------------------------ blueprints.rs:15-48
+struct MaterialBp { std::string type; bool has_albedo = false; rbrt_vec3 albedo{0, 0, 0}; bool has_param = false; float param = 0; };
+struct MeshBp { std::string obj; float scale; rbrt_vec3 translation, rotation; MaterialBp mat; };
+struct SphereBp { float radius; rbrt_vec3 center; MaterialBp mat; };
+struct SceneBp { rbrt_vec3 up, look_at, position; float focal; std::vector<MeshBp> meshes; std::vector<SphereBp> spheres; };
+
+MaterialBp material_bp(const Node* n) {
+    MaterialBp m;
+    m.type = as_str(n->get("material_type"), "material_type");
+    if (const Node* a = n->get("albedo")) if (a->kind == Node::Map) { m.has_albedo = true; m.albedo = as_vec3(a, "albedo"); }
+    if (const Node* p = n->get("material_param")) if (p->kind == Node::Scalar && !p->scalar.empty() && p->scalar != "~" && p->scalar != "null") { m.has_param = true; m.param = as_f32(p, "material_param"); }
+    return m;
+}
+
+SceneBp load_blueprints_from_yaml_file(const std::string& path) {   // blueprints.rs:76-92
+    std::ifstream f(path);
+    if (!f) die("Failed to open " + path + " to load content.");
+    auto root = parse_yaml(f);
+    if (root->kind != Node::Map) die("Unable to parse content of file " + path + " to scene blueprint");
+    SceneBp bp;
+    const Node* cam = root->get("camera_blueprint");
+    if (!cam) die("Unable to parse content of file " + path + " to scene blueprint: missing field `camera_blueprint`");
+    bp.up = as_vec3(cam->get("camera_up"), "camera_up");
+    bp.look_at = as_vec3(cam->get("camera_look_at"), "camera_look_at");
+    bp.position = as_vec3(cam->get("camera_position"), "camera_position");
+    bp.focal = as_f32(cam->get("camera_focal_length_mm"), "camera_focal_length_mm");
+    if (const Node* ms = root->get("mesh_blueprints"))
+        for (auto& it : ms->seq) {
+            MeshBp m;
+            m.obj = as_str(it->get("obj_filepath"), "obj_filepath");
+            m.scale = as_f32(it->get("scale"), "scale");
+            m.translation = as_vec3(it->get("translation"), "translation");
+            m.rotation = as_vec3(it->get("rotation_rad"), "rotation_rad");
+            m.mat = material_bp(it.get());
+            bp.meshes.push_back(m);
+        }
+    if (const Node* ss = root->get("sphere_blueprints"))
+        for (auto& it : ss->seq) {
+            SphereBp s;
+            s.radius = as_f32(it->get("radius"), "radius");
+            s.center = as_vec3(it->get("center"), "center");
+            s.mat = material_bp(it.get());
+            bp.spheres.push_back(s);
+        }
+    return bp;
+}
+
+std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
+
+// blueprints.rs:50-74: first match of "metal", "lambert", "dielectric"; a missing required field is the reference's `expect` panic
+bool create_material_from_description(const MaterialBp& m, rbrt_material* out) {
+    std::string t = lower(m.type);
+    if (t.find("metal") != std::string::npos) {
+        if (!m.has_albedo) die("you forgot to specify an albedo vector for metal");
+        if (!m.has_param) die("you forgot to specify a roughness (i.e. material_param: 0.1) for metal");
+        *out = rbrt_material{RBRT_MAT_METAL, m.albedo, m.param};
+        return true;
+    }
+    if (t.find("lambert") != std::string::npos) {
+        if (!m.has_albedo) die("you forgot to specify an albedo vector for lambertian");
+        *out = rbrt_material{RBRT_MAT_LAMBERTIAN, m.albedo, 0.0f};
+        return true;
+    }
+    if (t.find("dielectric") != std::string::npos) {
+        if (!m.has_param) die("you forgot to specify a refractory index vector (i.e. material_param: 1.8) dielectric");
+        *out = rbrt_material{RBRT_MAT_DIELECTRIC, rbrt_vec3{0, 0, 0}, m.param};
+        return true;
+    }
+    printf("Cannot figure out material_type from %s, material_type must be one of metal, lambertian or dielectric!\n", m.type.c_str());
+    return false;
+}
+
+// ------------------------------------------------------------------ mesh.rs:78-121
+std::vector<float> load_mesh_vertices_from_file(const std::string& path, rbrt_vec3 translation, rbrt_vec3 rotation, float scale) {
+    std::ifstream f(path);
+    if (!f) die("assertion failed: loaded_mesh.is_ok() (cannot open " + path + ")");   // mesh.rs:89
+    std::vector<float> pos;
+    std::vector<std::vector<long>> models(1);
+    std::string line;
+    while (std::getline(f, line)) {
+        std::istringstream ss(line);
+        std::string tag;
+        if (!(ss >> tag)) continue;
+        if (tag == "v") { float x, y, z; if (ss >> x >> y >> z) { pos.push_back(x); pos.push_back(y); pos.push_back(z); } }
+        else if (tag == "f") {
+            std::string tok;
+            while (ss >> tok) {
+                long i = strtol(tok.c_str(), nullptr, 10);       // "v", "v/vt", "v//vn", "v/vt/vn": the leading integer
+                models.back().push_back(i > 0 ? i - 1 : (long)(pos.size() / 3) + i);
+            }
+        } else if ((tag == "o" || tag == "g") && !models.back().empty()) models.emplace_back();
+    }
+    std::vector<float> tris;
+    const long nv = (long)(pos.size() / 3);
+    for (auto& m : models)
+        for (size_t t = 0; t + 2 < m.size() + 0 && t / 3 < m.size() / 3; t += 3)
+            for (int k = 0; k < 3; ++k) {
+                long i = m[t + k];
+                if (i < 0 || i >= nv) die(path + ": face index out of range");
+                tris.push_back(pos[3 * i]); tris.push_back(pos[3 * i + 1]); tris.push_back(pos[3 * i + 2]);
+            }
+    if (!tris.empty() && rbrt_transform_vertices(tris.data(), tris.size() / 3, scale, rotation, translation) != RBRT_OK) die("rbrt_transform_vertices failed");
+    printf("Successfully loaded %zu triangles from file %s!\n", tris.size() / 9, path.c_str());   // mesh.rs:115-119
+    return tris;
+}
+
+// ------------------------------------------------------------------ image save (main.rs:86)
+void put_u32(std::vector<uint8_t>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((uint8_t)(x >> s)); }
+void chunk(std::vector<uint8_t>& out, const char* tag, const std::vector<uint8_t>& data) {
+    put_u32(out, (uint32_t)data.size());
+    std::vector<uint8_t> body(tag, tag + 4);
+    body.insert(body.end(), data.begin(), data.end());
+    out.insert(out.end(), body.begin(), body.end());
+    put_u32(out, (uint32_t)crc32(0L, body.data(), (uInt)body.size()));
+}
+bool save_image(const std::string& path, const std::vector<uint8_t>& rgb, uint32_t w, uint32_t h) {
+    std::string ext = path.size() >= 4 ? lower(path.substr(path.find_last_of('.') == std::string::npos ? path.size() : path.find_last_of('.'))) : "";
+    std::vector<uint8_t> out;
+    if (ext == ".png") {
+        const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+        out.insert(out.end(), sig, sig + 8);
+        std::vector<uint8_t> ihdr; put_u32(ihdr, w); put_u32(ihdr, h);
+        const uint8_t tail[5] = {8, 2, 0, 0, 0};             // 8-bit, colour type 2 (RGB), deflate, filter 0, no interlace
+        ihdr.insert(ihdr.end(), tail, tail + 5);
+        chunk(out, "IHDR", ihdr);
+        std::vector<uint8_t> raw; raw.reserve((size_t)h * (1 + 3 * (size_t)w));
+        for (uint32_t y = 0; y < h; ++y) { raw.push_back(0); raw.insert(raw.end(), rgb.begin() + (size_t)y * w * 3, rgb.begin() + (size_t)(y + 1) * w * 3); }
+        uLongf zlen = compressBound((uLong)raw.size());
+        std::vector<uint8_t> z(zlen);
+        if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
+        z.resize(zlen);
+        chunk(out, "IDAT", z);
+        chunk(out, "IEND", {});
+    } else if (ext == ".ppm" || ext == ".pnm") {
+        char hdr[64]; int n = snprintf(hdr, sizeof(hdr), "P6\n%u %u\n255\n", w, h);
+        out.insert(out.end(), hdr, hdr + n);
+        out.insert(out.end(), rgb.begin(), rgb.end());
+    } else return false;
+    FILE* fp = fopen(path.c_str(), "wb");
+    if (!fp) return false;
+    bool ok = fwrite(out.data(), 1, out.size(), fp) == out.size();
+    return fclose(fp) == 0 && ok;
+}
+
+void usage() {
+    printf("a lighweight raytracer written in rust\n\nUsage: rbrt [OPTIONS]\n\nOptions:\n"
+           "  -t, --target_file <target_file>  file that will be created witht he rendered output [default: dbg_out.png]\n"
+           "      --height <height>            target image resolution height [default: 600]\n"
+           "  -w, --width <width>              target image resolution width [default: 800]\n"
+           "  -c, --config <config>            YAML file that specifies the scene layout and camera specification. [default: scenes/example_scene.yaml]\n"
+           "  -s, --samples <samples>          number of rays per pixel [default: 5]\n"
+           "      --seed <seed>                (extension) Philox seed; the reference is unseeded [default: 0]\n"
+           "      --device <device>            (extension) CUDA device [default: 0]\n"
+           "      --check                      (extension) parse the scene, print a summary and exit without rendering\n"
+           "  -h, --help                       Print help\n  -V, --version                    Print version\n");
+}
+
+uint32_t parse_u32(const char* s, const char* what) {
+    char* end = nullptr;
+    unsigned long v = strtoul(s, &end, 10);
+    if (end == s || *end || v > 0xFFFFFFFFul) die(std::string("error: invalid value '") + s + "' for '" + what + "'");
+    return (uint32_t)v;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string target = "dbg_out.png", config = "scenes/example_scene.yaml";      // main.rs:14-50
+    uint32_t height = 600, width = 800, samples = 5;
+    uint64_t seed = 0; int device = 0; bool check_only = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto value = [&](const char* name) -> const char* {
+            size_t eq = a.find('=');
+            if (eq != std::string::npos) return argv[i] + eq + 1;
+            if (i + 1 >= argc) die(std::string("error: a value is required for '") + name + "' but none was supplied");
+            return argv[++i];
+        };
+        std::string key = a.substr(0, a.find('='));
+        if (key == "-t" || key == "--target_file") target = value("--target_file");
+        else if (key == "--height") height = parse_u32(value("--height"), "--height");
+        else if (key == "-w" || key == "--width") width = parse_u32(value("--width"), "--width");
+        else if (key == "-c" || key == "--config") config = value("--config");
+        else if (key == "-s" || key == "--samples") samples = parse_u32(value("--samples"), "--samples");
+        else if (key == "--seed") seed = strtoull(value("--seed"), nullptr, 0);
+        else if (key == "--device") device = (int)parse_u32(value("--device"), "--device");
+        else if (key == "--check") check_only = true;
+        else if (key == "-h" || key == "--help") { usage(); return 0; }
+        else if (key == "-V" || key == "--version") { printf("rbrt 0.1 (%s)\n", rbrt_gpu_version()); return 0; }
+        else { fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str()); return 2; }
+    }
+
+    SceneBp bp = load_blueprints_from_yaml_file(config);
+    rbrt_camera cam;
+    if (rbrt_camera_new(bp.position, bp.look_at, bp.up, height, width, bp.focal, &cam) != RBRT_OK) die("rbrt_camera_new failed");   // height BEFORE width (main.rs:71-78)
+
+    // create_scene_from_scene_blueprint (blueprints.rs:132-158): meshes first, then spheres; unknown materials are skipped
+    std::vector<std::vector<float>> soups;
+    std::vector<rbrt_mesh_desc> meshes;
+    for (auto& m : bp.meshes) {
+        rbrt_material mat;
+        if (!create_material_from_description(m.mat, &mat)) { printf("Failed to parse material info provided with mesh!\n"); continue; }
+        soups.push_back(load_mesh_vertices_from_file(m.obj, m.translation, m.rotation, m.scale));
+        meshes.push_back(rbrt_mesh_desc{nullptr, soups.back().size() / 9, mat});
+    }
+    for (size_t i = 0; i < meshes.size(); ++i) meshes[i].tri_vertices = soups[i].data();
+    std::vector<rbrt_sphere_desc> spheres;
+    for (auto& s : bp.spheres) {
+        rbrt_material mat;
+        if (!create_material_from_description(s.mat, &mat)) continue;
+        spheres.push_back(rbrt_sphere_desc{s.center, s.radius, mat});
+    }
+    if (check_only) {
+        uint64_t nt = 0; for (auto& m : meshes) nt += m.num_triangles;
+        printf("scene ok: %zu spheres, %zu meshes, %llu triangles, camera %ux%u focal %g mm\n", spheres.size(), meshes.size(), (unsigned long long)nt,
+               cam.img_width_pix, cam.img_height_pix, cam.focal_len_mm);
+        return 0;
+    }
+
+    if (rbrt_gpu_init(device) != RBRT_OK) die(std::string("rbrt_gpu: ") + rbrt_last_error());
+    rbrt_scene* scene = nullptr;
+    if (rbrt_gpu_scene_create(spheres.data(), (uint32_t)spheres.size(), meshes.data(), (uint32_t)meshes.size(), nullptr, &scene) != RBRT_OK)
+        die(std::string("rbrt_gpu: ") + rbrt_last_error());
+    printf("Starting rendering...\n");                                             // lib.rs:80
+    std::vector<uint8_t> rgb((size_t)width * height * 3);
+    rbrt_render_opts opts; memset(&opts, 0, sizeof(opts)); opts.seed = seed;
+    rbrt_stats st;
+    if (rbrt_gpu_render(scene, &cam, samples, &opts, rgb.data(), &st) != RBRT_OK) die(std::string("rbrt_gpu: ") + rbrt_last_error());
+    printf("\rRendering 100%% complete!\n");                                        // lib.rs:114
+    rbrt_gpu_scene_destroy(scene);
+    printf("Saving rendered image to %s\n", target.c_str());                        // main.rs:84
+    if (!save_image(target, rgb, width, height)) die("Unable to save target img to " + target + "! Maybe the directory does not exist?");   // main.rs:86-91
+    fprintf(stderr, "[rbrt_b200] %llu rays, %llu samples in %.1f ms on the device (%.1f Mrays/s)\n", (unsigned long long)st.rays,
+            (unsigned long long)st.paths, st.ms_device, st.ms_device > 0 ? st.rays / st.ms_device / 1e3 : 0.0);
+    return 0;
+}
