@@ -123,6 +123,8 @@ class ClockSampler:
         self.index, self.proc, self.lines, self.t_begin, self.t_end, self.t_start = index, None, [], None, None, time.time()
 
     def __enter__(self):
+        if os.environ.get("RBRT_BENCH_NO_CLOCKS"):            # debugging aid: measure without the nvidia-smi side process
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -193,7 +195,7 @@ def algorithmic_bytes(st, n_spheres, n_meshes):
     72 B of queue traffic: 4 B queue index + 32 B ray + 16 B sphere pre-result read, 16 B hit record + 4 B material-queue
     index written).  The sphere and mesh-AABB tests of SURVEY.md section 8(d) (16 S + 24 M per ray) now run in the
     producing kernels (k_generate / k_shade) and are not charged to this kernel."""
-    return 64 * st["node_visits"] + 48 * st["tri_tests"] + 72 * st["traversed_rays"]
+    return 64 * st["node_visits"] + 48 * st["tri_tests"] + 72 * st["traversed_rays"]      # counts of k_trace only (tail kernel subtracted by the caller)
 
 
 def algorithmic_flops(st, n_spheres, n_meshes):
@@ -350,7 +352,8 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([sum(s["rays"] for s in stats), sum(s["paths"] for s in stats), sum(s["launches"] for s in stats) + (args.steps if rank == 0 else 0),
-                        counts["node_visits"], counts["tri_tests"], counts["rays"], counts["traversed_rays"]], dtype=torch.float64, device="cuda")
+                        counts["node_visits"] - counts["tail_node_visits"], counts["tri_tests"] - counts["tail_tri_tests"], counts["rays"],
+                        counts["traversed_rays"] - counts["tail_traversed_rays"]], dtype=torch.float64, device="cuda")
     trace_ms = torch.tensor([sum(s["ms_trace"] for s in stats)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

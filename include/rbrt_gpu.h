@@ -131,6 +131,7 @@ typedef struct rbrt_stats {
     uint32_t launches;       /* kernels launched by this call */
     uint32_t iterations;     /* wavefront bounce iterations executed */
     uint64_t traversed_rays; /* rays that entered a mesh AABB and were traversed through the LBVH (RBRT_OPT_COUNT_VISITS) */
+    uint64_t tail_node_visits, tail_tri_tests, tail_traversed_rays;   /* the part of the three counters above done by the tail kernel */
 } rbrt_stats;
 
 typedef struct rbrt_scene_info {

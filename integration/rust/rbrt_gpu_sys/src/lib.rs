@@ -26,7 +26,7 @@ pub struct RbrtRenderOpts { pub seed: u64, pub max_depth: u32, pub trace_mode: u
 #[repr(C)] #[derive(Copy, Clone, Debug, Default)]
 pub struct RbrtStats { pub rays: u64, pub paths: u64, pub nan_rays: u64, pub node_visits: u64, pub tri_tests: u64, pub ms_total: f64,
                        pub ms_device: f64, pub ms_trace: f64, pub ms_h2d: f64, pub ms_d2h: f64, pub launches: u32, pub iterations: u32,
-                       pub traversed_rays: u64 }
+                       pub traversed_rays: u64, pub tail_node_visits: u64, pub tail_tri_tests: u64, pub tail_traversed_rays: u64 }
 pub enum RbrtScene {}
 
 extern "C" {

@@ -59,7 +59,8 @@ class StatsC(C.Structure):
                 ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("ms_total", C.c_double),
                 ("ms_device", C.c_double), ("ms_trace", C.c_double), ("ms_h2d", C.c_double),
                 ("ms_d2h", C.c_double), ("launches", C.c_uint32), ("iterations", C.c_uint32),
-                ("traversed_rays", C.c_uint64)]
+                ("traversed_rays", C.c_uint64), ("tail_node_visits", C.c_uint64), ("tail_tri_tests", C.c_uint64),
+                ("tail_traversed_rays", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

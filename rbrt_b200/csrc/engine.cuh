@@ -18,7 +18,7 @@ struct IterCtr {
     uint32_t pad;
 };
 
-enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_CAND = 4, ST_COUNT = 5 };
+enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_CAND = 4, ST_TAIL_NODES = 5, ST_TAIL_TRIS = 6, ST_TAIL_CAND = 7, ST_COUNT = 8 };
 
 // Wavefront state.  Every per-path record lives at the path's own index pid (no slot compaction): a
 // path's next ray overwrites its previous one, so one ray buffer serves all bounce iterations.

@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(256) k_finish(WaveParams P, uint32_t it0, uint
         if (nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
     }
     if (COUNT) {
-        atomicAdd(&P.stats[ST_NODES], (unsigned long long)cnt.nodes); atomicAdd(&P.stats[ST_TRIS], (unsigned long long)cnt.tris);
-        atomicAdd(&P.stats[ST_CAND], (unsigned long long)n_cand);
+        atomicAdd(&P.stats[ST_TAIL_NODES], (unsigned long long)cnt.nodes); atomicAdd(&P.stats[ST_TAIL_TRIS], (unsigned long long)cnt.tris);
+        atomicAdd(&P.stats[ST_TAIL_CAND], (unsigned long long)n_cand);
     }
     // Raise the flag only when EVERY block of this launch has finished (blocks that become resident late must still
     // pass the entry check above): the last block to leave sets it; later launches see it (stream order).
@@ -476,6 +476,155 @@ __global__ void k_sum_rays(WaveParams P) {
     for (uint32_t it = threadIdx.x; it <= P.max_depth + 1; it += blockDim.x) r += P.ctr[it].ray_count;
     for (int off = 16; off; off >>= 1) r += __shfl_down_sync(FULL_MASK, r, off);
     if ((threadIdx.x & 31) == 0 && r) atomicAdd(&P.stats[ST_RAYS], r);
+}
+
+// ------------------------------------------------------------------ tail, asynchronous form (BVH mode)
+// Same hand-over as k_finish, but built like k_trace: persistent warps, every lane owns a PATH (not a ray), lanes whose
+// path has ended take the next queued item inside the loop, and traversal is the shared while-while loop with dynamic
+// fetch.  There is no barrier between bounces of different paths, so the hand-over can happen while millions of rays are
+// still alive: the sparsely populated iterations (each bounded by its slowest ray) disappear instead of being paid one
+// after another.  A lane's step: [traversal of the meshes its ray entered] -> resolve -> scatter + stage A (possibly
+// several times in a row for sphere-only bounces) -> next traversal, or end of path -> next item.
+#define TAIL_THREADS 128
+#define TAIL_FORCE_IT 12        // from this bounce iteration on, the tail kernel takes whatever is left
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t it0, uint32_t max_rays) {
+    if (P.ctr[0].pad) return;
+    const IterCtr c = P.ctr[it0];
+    if (c.ray_count > max_rays) return;
+    const uint32_t nc = c.cand_count, n0 = c.mat_count[0], n1 = c.mat_count[1], n2 = c.mat_count[2];
+    const uint32_t total = nc + n0 + n1 + n2;
+    uint32_t* head = &P.ctr[it0].shade_head;                              // unused by k_shade(it0) from now on: queue cursor of this kernel
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const int32_t SENTINEL = 0x7FFFFFFF;
+    int32_t stack[RBRT_STACK];
+    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
+    // ---- path state
+    uint32_t pid = 0, it = it0;
+    int pending = -1;                                                     // material kind of a hit waiting to be shaded, -1 none
+    // ---- ray state (as k_trace)
+    bool has_ray = false;
+    uint32_t mi = 0;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+    RaySlabs R = {0, 0, 0, 0, 0, 0, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_LO};
+    float closest = 0.0f, bt = 0.0f; int bkind = -1; uint32_t belem = 0, btri = 0;
+    int32_t cur = SENTINEL; int sp = 0;
+    float best_t = 0.0f, t_prune = 0.0f, t_limit = 0.0f; uint32_t best_idx = 0xFFFFFFFFu;
+    const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(P.S.nodes); uint32_t tri_base = 0;
+    bool exhausted = total == 0;
+    uint32_t n_nodes = 0, n_tris = 0, n_cand = 0, rays = 0, nan_count = 0;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t quota = min(32u, max(1u, (total + n_warps - 1) / n_warps));
+
+    auto start_mesh = [&](const MeshDev& M) {
+        t_limit = RBRT_T_CAP;
+        if (closest < 3.0e38f) {
+            float dl = len3(d);
+            float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+            float lim = (closest * 1.001f + 1e-5f * (omax + closest) + 1e-6f) / dl;
+            if (lim == lim) t_limit = fminf(t_limit, lim);
+        }
+        t_prune = t_limit; best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;
+        nodes = reinterpret_cast<const uint4*>(P.S.nodes) + 4 * (size_t)M.node_base; tri_base = M.tri_base;
+        R = ray_slabs(M, o, d);
+        sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
+    };
+    auto load_candidate = [&]() {                                         // the ray stage A queued for this path
+        float4 a = P.ray_o[pid], b = P.ray_d[pid];
+        uint4 h = P.hit[pid];
+        o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
+        bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
+        bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
+        has_ray = true;
+        if (COUNT) ++n_cand;
+        start_mesh(P.S.meshes[mi]);
+    };
+
+    for (;;) {
+        // ---- (1) lanes whose traversal ended: close the mesh, move to the next one or resolve the ray
+        bool idle = (cur == SENTINEL);
+        if (idle && has_ray) {
+            if (best_idx != 0xFFFFFFFFu) {
+                f3 p = o + best_t * d;
+                float dist = len3(o - p);
+                if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) { closest = dist; bkind = 1; belem = mi; btri = best_idx; bt = best_t; }
+            }
+            bool more = false;
+            while (++mi < P.S.n_meshes) {
+                const MeshDev& M = P.S.meshes[mi];
+                if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
+                start_mesh(M); more = true; break;
+            }
+            if (!more) { pending = resolve(P, it, pid, d, bkind, belem, btri, bt); has_ray = false; }   // -1: the path ended
+            else idle = false;
+        }
+        // ---- (2) lanes without a path take the next queued item (one atomic per warp)
+        bool want_fetch = idle && !has_ray && pending < 0;
+        if (!exhausted) {
+            uint32_t m = __ballot_sync(FULL_MASK, want_fetch);
+            if (quota < 32u) {
+                uint32_t busy = 32u - __popc(m);
+                uint32_t allow = busy < quota ? quota - busy : 0u;
+                if (allow == 0u) m = 0u;
+                else if (allow < (uint32_t)__popc(m)) m &= (1u << __fns(m, 0, allow + 1)) - 1u;
+                want_fetch = want_fetch && ((m >> lane) & 1u);
+            }
+            if (m) {
+                uint32_t base = warp_grab(head, __popc(m));
+                if (want_fetch) {
+                    uint32_t w = base + __popc(m & lt);
+                    if (w < total) {
+                        it = it0;
+                        if (w < nc) { pid = P.candq[w]; load_candidate(); }
+                        else if (w < nc + n0) { pid = P.matq[it0 & 1][0][w - nc]; pending = 0; }
+                        else if (w < nc + n0 + n1) { pid = P.matq[it0 & 1][1][w - nc - n0]; pending = 1; }
+                        else { pid = P.matq[it0 & 1][2][w - nc - n0 - n1]; pending = 2; }
+                    }
+                }
+                if (base + __popc(m) >= total) exhausted = true;
+            }
+        }
+        // ---- (3) pending hits: scatter + stage A, repeated while the continuation ray is resolved by a sphere alone
+        while (pending >= 0) {
+            uint32_t cls = shade_item(P, it, (uint32_t)pending, pid, key, rays, nan_count);
+            ++it;
+            if (cls == CLS_CAND) { pending = -1; load_candidate(); }
+            else if (cls == CLS_NONE) pending = -1;                       // absorbed, missed, depth exhausted: path over
+            else pending = (int)cls;
+        }
+        uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
+        if (active == 0) { if (exhausted) break; continue; }
+        const int threshold = exhausted ? 1 : min(FETCH_THRESHOLD, (int)quota);
+        // ---- (4) while-while traversal, as k_trace
+        for (;;) {
+            while ((uint32_t)cur < (uint32_t)SENTINEL) {
+                cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp);
+                if (COUNT) ++n_nodes;
+            }
+            if (cur < 0) {
+                uint32_t nt = 0;
+                leaf_step(P.S.tris, tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, nt);
+                if (COUNT) n_tris += nt;
+                cur = stack[--sp];
+            }
+            if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
+        }
+    }
+    for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
+    if (lane == 0) {
+        if (rays) atomicAdd(&P.ctr[P.max_depth + 1].ray_count, rays);
+        if (nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
+    }
+    if (COUNT) {
+        for (int off = 16; off; off >>= 1) { n_nodes += __shfl_down_sync(FULL_MASK, n_nodes, off); n_tris += __shfl_down_sync(FULL_MASK, n_tris, off); n_cand += __shfl_down_sync(FULL_MASK, n_cand, off); }
+        if (lane == 0) { atomicAdd(&P.stats[ST_TAIL_NODES], (unsigned long long)n_nodes); atomicAdd(&P.stats[ST_TAIL_TRIS], (unsigned long long)n_tris); atomicAdd(&P.stats[ST_TAIL_CAND], (unsigned long long)n_cand); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                               // last block out raises the flag (see k_finish)
+        __threadfence();
+        if (atomicAdd(&P.ctr[1].pad, 1u) == gridDim.x - 1) P.ctr[0].pad = 1u + it0;
+    }
 }
 
 // ------------------------------------------------------------------ accumulate (lib.rs:95-100)
@@ -628,7 +777,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     cudaEvent_t ev0, ev1;
     CKR(cudaEventCreate(&ev0)); CKR(cudaEventCreate(&ev1));
     CKR(cudaMemsetAsync(d_accum, 0, 16ull * W * H, st));
-    uint32_t launches = 0, iterations = 0;
+    uint32_t launches = 0, iterations = 0, batch_iters = 0;
     WaveBuffers& wb = device_wave_buffers(sc.device);
     CKR(cudaEventRecord(ev0, st));
     if (P && sh.s1 > sh.s0) {
@@ -640,7 +789,9 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         if (!target) {
             const uint64_t per_path = 92ull + 2ull * max_depth;
             const uint64_t want = std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * P, 1ull << 27);
-            if (wb.cap >= want && wb.depth_cap >= max_depth) target = (uint32_t)want;      // the pool already holds it: no driver query
+            const uint64_t want_sb = std::max<uint64_t>(want / P, 1);                       // whole samples per batch
+            if (wb.cap >= want_sb * P && wb.depth_cap >= max_depth) target = (uint32_t)want;   // the pool already holds it: no driver query
+                                                                                            // (cudaMemGetInfo takes tens of ms at times)
             else {
                 size_t free_b = 0, total_b = 0;
                 CKR(cudaMemGetInfo(&free_b, &total_b));
@@ -671,8 +822,12 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         if (!fin_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm_cached, k_finish<false, false>, 256, 0));
         const int fin_per_sm = fin_per_sm_cached;                         // k_finish: one resident wave of 256-thread blocks
         const int grid_fin = sc.sm_count * (fin_per_sm > 0 ? fin_per_sm : 2);
-        const char* tail_env = getenv("RBRT_TAIL_RAYS");                  // tuning knob; default = one ray per resident lane
-        const uint32_t tail_rays = (o.flags & RBRT_OPT_NO_TAIL_KERNEL) ? 0u : (tail_env ? (uint32_t)atoi(tail_env) : (uint32_t)grid_fin * 256u);
+        static int tail_per_sm_cached = 0;
+        if (!tail_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm_cached, k_tail<false>, TAIL_THREADS, 0));
+        const int grid_tail = sc.sm_count * (tail_per_sm_cached > 0 ? tail_per_sm_cached : 2);
+        const char* tail_env = getenv("RBRT_TAIL_RAYS");                  // tuning knob
+        // hand-over threshold: brute mode one ray per resident lane of k_finish; BVH mode (asynchronous k_tail) 2^18 rays (swept on C2, C3, C4 at 1 and 8 ranks: scripts/tail_sweep.py)
+        const uint32_t tail_rays = (o.flags & RBRT_OPT_NO_TAIL_KERNEL) ? 0u : (tail_env ? (uint32_t)atoi(tail_env) : (o.trace_mode == RBRT_TRACE_BRUTE ? (uint32_t)grid_fin * 256u : (1u << 18)));
         const bool brute = o.trace_mode == RBRT_TRACE_BRUTE;
         const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
         const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
@@ -685,17 +840,23 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
             wp.s_base = s_base; wp.s_count = (sh.s1 - s_base < S_b) ? sh.s1 - s_base : S_b;
             CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
             k_generate<<<grid, 256, 0, st>>>(wp); ++launches;
+            batch_iters = 0;
             for (uint32_t it = 0; it <= max_depth; ++it) {
-                if (it >= 1 && tail_rays) {                                // see k_finish
-                    if (brute) { if (count) k_finish<true, true><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); else k_finish<true, false><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); }
-                    else { if (count) k_finish<false, true><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); else k_finish<false, false><<<grid_fin, 256, 0, st>>>(wp, it, tail_rays); }
+                if (it >= 1 && tail_rays) {                                // see k_finish / k_tail
+                    // From iteration TAIL_FORCE_IT on the hand-over is unconditional, so the launch sequence ends there:
+                    // ~40 launches per batch instead of 155 (an empty iteration still costs three launches).
+                    const bool force = it >= TAIL_FORCE_IT;
+                    const uint32_t lim = force ? 0xFFFFFFFFu : tail_rays;
+                    if (brute) { if (count) k_finish<true, true><<<grid_fin, 256, 0, st>>>(wp, it, lim); else k_finish<true, false><<<grid_fin, 256, 0, st>>>(wp, it, lim); }
+                    else { if (count) k_tail<true><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); else k_tail<false><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); }
                     ++launches;
+                    if (force) break;
                 }
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (brute) { if (count) k_trace_brute<true><<<grid, 256, 0, st>>>(wp, it); else k_trace_brute<false><<<grid, 256, 0, st>>>(wp, it); }
                 else if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
                 else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
-                ++launches; ++iterations;
+                ++launches; ++iterations; ++batch_iters;
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (it < max_depth) { k_shade<<<grid, 256, 0, st>>>(wp, it); ++launches; }
             }
@@ -708,9 +869,11 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     if (stats) {
         CKR(cudaEventSynchronize(ev1));
         float ms = 0; CKR(cudaEventElapsedTime(&ms, ev0, ev1));
-        unsigned long long h[ST_COUNT] = {0, 0, 0, 0, 0};
+        unsigned long long h[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (wb.stats && P && sh.s1 > sh.s0) CKR(cudaMemcpy(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost));
-        stats->rays = h[ST_RAYS]; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS]; stats->traversed_rays = h[ST_CAND];
+        stats->rays = h[ST_RAYS]; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS] + h[ST_TAIL_TRIS]; stats->traversed_rays = h[ST_CAND] + h[ST_TAIL_CAND];
+        stats->node_visits += h[ST_TAIL_NODES];
+        stats->tail_node_visits = h[ST_TAIL_NODES]; stats->tail_tri_tests = h[ST_TAIL_TRIS]; stats->tail_traversed_rays = h[ST_TAIL_CAND];
         uint64_t valid_px = 0;
         for (uint32_t tj = 0; tj < sh.tiles_mine; ++tj) {
             uint32_t T = tj * sh.count + sh.rank, ty = T / sh.tiles_x, tx = T - ty * sh.tiles_x;
@@ -728,12 +891,12 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
             if (getenv("RBRT_DEBUG_ITERS")) {                              // per-iteration trace time + queue sizes of the LAST batch
                 std::vector<IterCtr> hc(max_depth + 2);
                 CKR(cudaMemcpy(hc.data(), wb.ctr, sizeof(IterCtr) * (max_depth + 2), cudaMemcpyDeviceToHost));
-                size_t per_batch = max_depth + 1, first = 2 * (iterations - per_batch);
+                size_t per_batch = batch_iters, first = 2 * (iterations - per_batch);
                 float t_first = 0; cudaEventElapsedTime(&t_first, ev0, wb.ev[first]);
                 fprintf(stderr, "setup + generate (ev0 -> first trace): %.3f ms; tail kernel ran at it %d\n", t_first, (int)hc[0].pad - 1);
-                for (uint32_t it = 0; it <= max_depth; ++it) {
+                for (uint32_t it = 0; it < per_batch; ++it) {
                     float t = 0, g = 0; cudaEventElapsedTime(&t, wb.ev[first + 2 * it], wb.ev[first + 2 * it + 1]);
-                    if (it < max_depth) cudaEventElapsedTime(&g, wb.ev[first + 2 * it + 1], wb.ev[first + 2 * it + 2]);
+                    if (it + 1 < per_batch) cudaEventElapsedTime(&g, wb.ev[first + 2 * it + 1], wb.ev[first + 2 * it + 2]);
                     else cudaEventElapsedTime(&g, wb.ev[first + 2 * it + 1], ev1);
                     fprintf(stderr, "it %2u rays %9u traversed %9u  lambert %9u metal %9u glass %9u  trace %8.3f ms  then shade+finish %8.3f ms\n", it, hc[it].ray_count,
                             hc[it].cand_count, hc[it].mat_count[0], hc[it].mat_count[1], hc[it].mat_count[2], t, g);
