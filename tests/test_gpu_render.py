@@ -203,3 +203,24 @@ def test_invalid_arguments(gpu):
     with pytest.raises(_abi.RbrtGpuError):
         R.render_scene_hdr(cam, 1, scene, shard_mode=_abi.SHARD_TILES, shard_rank=3, shard_count=2)
     assert _abi.lib().rbrt_gpu_render(scene.handle(), cam.to_c(), 1, None, None, None) == _abi.E_INVALID
+
+
+def test_many_elements_render(gpu, oracle):
+    """A scene with 20 meshes of three materials and 12 spheres: multi-mesh traversal order (scene.rs:33-41), per-element
+    attenuation history and the tail kernel's per-lane mesh loop, against the oracle."""
+    scene = R.Scene()
+    rng = np.random.default_rng(3)
+    mats = [R.Lambertian(Vec3(0.6, 0.3, 0.2)), R.Metal(Vec3(0.9, 0.9, 0.9), 0.05), R.Dielectric(1.6)]
+    k = 0
+    for x in range(-4, 6, 2):
+        for y in range(0, 8, 2):
+            scene.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(2, 0.8, (float(x), float(y) * 0.6 + 0.8, -9.0 - (x + y) % 3)), mats[k % 3]))
+            k += 1
+    scene.elements.append(R.Sphere(Vec3(0.0, -1000.0, -5.0), 1000.0, R.Lambertian(Vec3(0.02, 0.2, 0.1))))
+    for i in range(11):
+        c = rng.uniform(-5, 5, size=2)
+        scene.elements.append(R.Sphere(Vec3(c[0], 0.4, -4.0 + c[1] * 0.3), 0.4, mats[i % 3]))
+    cam = S.example_camera(160, 120)
+    ref = oracle.OracleScene.from_scene(scene).render_hdr(cam.to_c(), 4, _abi.RenderOptsC(seed=21))
+    for kw in [{}, {"no_tail_kernel": True}]:
+        assert_images_equal(R.render_scene_hdr(cam, 4, scene, seed=21, **kw), ref, f"many elements {kw}")

@@ -165,3 +165,40 @@ def test_c3_million_triangles_bvh_equals_brute(gpu):
     refl = prim[on, 3:] - 2 * (prim[on, 3:] * n).sum(1, keepdims=True) * n
     sec = np.concatenate([bvh["point"][on], refl.astype(np.float32)], 1)[:30000]
     assert_same(scene.hit(sec, _abi.TRACE_BVH), scene.hit(sec, _abi.TRACE_BRUTE), "C3 reflected subset")
+
+
+def test_builder_edge_cases(gpu, oracle):
+    """BVH builder corner cases, each compared with the oracle bit for bit: all triangles identical (equal Morton codes, a
+    binary tree kept together only by the position tie-break), a flat mesh (zero extent in one axis), zero-area and
+    needle triangles, coordinates around 1e5, twenty small meshes in one scene, 300 spheres."""
+    rng = np.random.default_rng(11)
+    cases = []
+    tri = np.float32([[-1, -1, -5], [1, -1, -5], [0, 1, -5]])
+    cases.append(("identical x 1000", [np.tile(tri, (1000, 1, 1))], (0, 0, -5), 3.0))
+    flat = rng.uniform(-3, 3, size=(4096, 3, 3)).astype(np.float32)
+    flat[:, :, 2] = -7.0
+    cases.append(("flat z = -7", [flat], (0, 0, -7), 4.0))
+    deg = synth.displaced_icosphere(3, 2.0, (0, 0, -8)).copy()
+    deg[::7, 1] = deg[::7, 0]                                    # zero-area triangles (two equal vertices)
+    deg[3::11, 2] = deg[3::11, 0] + np.float32(1e-4)             # needles
+    cases.append(("degenerate triangles", [deg], (0, 0, -8), 3.0))
+    far = synth.displaced_icosphere(3, 50.0, (1e5, -2e5, 3e5))
+    cases.append(("coordinates ~1e5", [far], (1e5, -2e5, 3e5), 80.0))
+    many = [synth.displaced_icosphere(1, 0.7, (float(x), float(y), -10.0 - (x + y) % 3)) for x in range(-4, 6, 2) for y in range(-3, 5, 2)]
+    cases.append(("20 meshes", many, (0, 0, -10), 6.0))
+    for name, meshes, center, spread in cases:
+        scene = R.Scene()
+        for i, m in enumerate(meshes):
+            scene.triangle_meshes.append(R.TriangleMesh.from_triangles(m, [R.Lambertian(Vec3(0.5, 0.5, 0.5)), R.Metal(Vec3(0.9, 0.9, 0.9), 0.1), R.Dielectric(1.5)][i % 3]))
+        rays = S.random_rays(30000, center, spread, 5)
+        ref = oracle.OracleScene.from_scene(scene).hit(rays)
+        assert (ref["kind"] == 1).sum() > 100, name
+        for mode in MODES:
+            assert_same(scene.hit(rays, mode), ref, f"{name} mode {mode}")
+        scene.close()
+    scene = R.Scene()
+    for i in range(300):
+        c = rng.uniform(-20, 20, size=3)
+        scene.elements.append(R.Sphere(Vec3(c[0], c[1], c[2] - 40), float(rng.uniform(0.3, 2.0)), R.Lambertian(Vec3(0.5, 0.5, 0.5))))
+    rays = S.random_rays(20000, (0, 0, -40), 25.0, 6)
+    assert_same(scene.hit(rays), oracle.OracleScene.from_scene(scene).hit(rays), "300 spheres")
