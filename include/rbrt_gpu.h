@@ -63,6 +63,17 @@ typedef struct rbrt_material { uint32_t kind; rbrt_vec3 albedo; float param; } r
 /* = rbrt_lib::sphere::Sphere (sphere.rs:6-10) */
 typedef struct rbrt_sphere_desc { rbrt_vec3 center; float radius; rbrt_material material; } rbrt_sphere_desc;
 
+/* = rbrt_lib::triangle::BasicTriangle::new(corners, material) (triangle.rs:9-28): a single triangle as a scene ELEMENT
+ * (an `Intersectable` pushed into Scene.elements next to the spheres; unreachable from the YAML/CLI path).  Counter-clockwise
+ * corners; tested by basic_triangle_intersect_w_ray (triangle.rs:92-130): same Moeller-Trumbore arithmetic as the mesh
+ * sweep but `u` must lie IN [0,1] (NaN rejects), there is no upper cap on t, and dist is accepted in [min_dist, max_dist]. */
+typedef struct rbrt_triangle_desc { rbrt_vec3 corners[3]; rbrt_material material; } rbrt_triangle_desc;
+
+/* One entry of Scene.elements (scene.rs:13), in iteration order: kind RBRT_ELEM_SPHERE -> spheres[index],
+ * RBRT_ELEM_TRIANGLE -> triangles[index].  Order matters: the earlier element wins exact distance ties (scene.rs:23-31). */
+enum { RBRT_ELEM_SPHERE = 0, RBRT_ELEM_TRIANGLE = 1 };
+typedef struct rbrt_element_ref { uint32_t kind; uint32_t index; } rbrt_element_ref;
+
 /* = what TriangleMesh::new (mesh.rs:41-74) holds after load_mesh_vertices_from_file
  * (mesh.rs:78-121): world-space triangle soup, 9 floats per triangle (v0 v1 v2), already
  * scale -> rotate_point -> translate'd in f32.  One material per mesh (mesh.rs:24). */
@@ -73,10 +84,10 @@ typedef struct rbrt_mesh_desc {
 } rbrt_mesh_desc;
 
 /* Result of one closest-hit query = what Scene::hit (scene.rs:19-43) returns, plus ids. */
-enum { RBRT_HIT_NONE = -1, RBRT_HIT_SPHERE = 0, RBRT_HIT_MESH = 1 };
+enum { RBRT_HIT_NONE = -1, RBRT_HIT_SPHERE = 0, RBRT_HIT_MESH = 1, RBRT_HIT_TRIANGLE = 2 /* a BasicTriangle element */ };
 typedef struct rbrt_hit {
     int32_t   kind;       /* RBRT_HIT_* */
-    uint32_t  elem_idx;   /* sphere index, or mesh index, in creation order */
+    uint32_t  elem_idx;   /* position in Scene.elements (spheres / basic triangles), or mesh index, in creation order */
     uint32_t  tri_idx;    /* original triangle index inside the mesh (0 for spheres) */
     float     t;          /* ray parameter */
     float     dist;       /* dist_from_ray_orig (lib.rs:35) */
@@ -181,6 +192,13 @@ int rbrt_gpu_init(int device);
 int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t num_spheres,
                           const rbrt_mesh_desc* meshes, uint32_t num_meshes,
                           const rbrt_scene_opts* opts, rbrt_scene** out);
+/* Same, with Scene.elements given explicitly as an ordered mix of spheres and BasicTriangles (`order`, num_elements entries);
+ *   rbrt_gpu_scene_create(...) == this with order = every sphere in array order. */
+int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t num_elements,
+                                   const rbrt_sphere_desc* spheres, uint32_t num_spheres,
+                                   const rbrt_triangle_desc* triangles, uint32_t num_triangles,
+                                   const rbrt_mesh_desc* meshes, uint32_t num_meshes,
+                                   const rbrt_scene_opts* opts, rbrt_scene** out);
 int rbrt_gpu_scene_info(const rbrt_scene* scene, rbrt_scene_info* out);
 int rbrt_gpu_scene_destroy(rbrt_scene* scene);
 

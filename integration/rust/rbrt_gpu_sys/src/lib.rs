@@ -19,6 +19,8 @@ pub const RBRT_MAT_METAL: u32 = 1;
 pub const RBRT_MAT_DIELECTRIC: u32 = 2;
 #[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtMaterial { pub kind: u32, pub albedo: RbrtVec3, pub param: f32 }
 #[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtSphereDesc { pub center: RbrtVec3, pub radius: f32, pub material: RbrtMaterial }
+#[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtTriangleDesc { pub corners: [RbrtVec3; 3], pub material: RbrtMaterial }
+#[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtElementRef { pub kind: u32, pub index: u32 }   // 0 sphere, 1 BasicTriangle
 #[repr(C)] #[derive(Copy, Clone, Debug)] pub struct RbrtMeshDesc { pub tri_vertices: *const f32, pub num_triangles: u64, pub material: RbrtMaterial }
 #[repr(C)] #[derive(Copy, Clone, Debug, Default)]
 pub struct RbrtRenderOpts { pub seed: u64, pub max_depth: u32, pub trace_mode: u32, pub shard_mode: u32, pub shard_rank: u32,
@@ -36,6 +38,9 @@ extern "C" {
     pub fn rbrt_gpu_init(device: c_int) -> c_int;
     pub fn rbrt_gpu_scene_create(spheres: *const RbrtSphereDesc, num_spheres: u32, meshes: *const RbrtMeshDesc, num_meshes: u32,
                                  opts: *const c_void, out: *mut *mut RbrtScene) -> c_int;
+    pub fn rbrt_gpu_scene_create_elements(order: *const RbrtElementRef, num_elements: u32, spheres: *const RbrtSphereDesc, num_spheres: u32,
+                                          triangles: *const RbrtTriangleDesc, num_triangles: u32, meshes: *const RbrtMeshDesc, num_meshes: u32,
+                                          opts: *const c_void, out: *mut *mut RbrtScene) -> c_int;
     pub fn rbrt_gpu_scene_destroy(scene: *mut RbrtScene) -> c_int;
     pub fn rbrt_gpu_render(scene: *const RbrtScene, cam: *const RbrtCamera, num_samples: u32, opts: *const RbrtRenderOpts,
                            rgb_out: *mut u8, stats: *mut RbrtStats) -> c_int;

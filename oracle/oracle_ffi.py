@@ -16,6 +16,8 @@ _SIG = {
     "rbrt_ref_camera_new": (C.c_int, [_abi.Vec3C, _abi.Vec3C, _abi.Vec3C, C.c_uint32, C.c_uint32, C.c_float, P(_abi.CameraC)]),
     "rbrt_ref_transform_vertices": (C.c_int, [P(C.c_float), C.c_uint64, C.c_float, _abi.Vec3C, _abi.Vec3C]),
     "rbrt_ref_scene_create": (C.c_int, [P(_abi.SphereDescC), C.c_uint32, P(_abi.MeshDescC), C.c_uint32, P(_abi.SceneOptsC), P(C.c_void_p)]),
+    "rbrt_ref_scene_create_elements": (C.c_int, [P(_abi.ElementRefC), C.c_uint32, P(_abi.SphereDescC), C.c_uint32, P(_abi.TriangleDescC), C.c_uint32,
+                                                P(_abi.MeshDescC), C.c_uint32, P(_abi.SceneOptsC), P(C.c_void_p)]),
     "rbrt_ref_scene_destroy": (C.c_int, [C.c_void_p]),
     "rbrt_ref_render": (C.c_int, [C.c_void_p, P(_abi.CameraC), C.c_uint32, P(_abi.RenderOptsC), C.c_void_p, P(_abi.StatsC)]),
     "rbrt_ref_render_hdr": (C.c_int, [C.c_void_p, P(_abi.CameraC), C.c_uint32, P(_abi.RenderOptsC), C.c_void_p, P(_abi.StatsC)]),
@@ -86,12 +88,13 @@ class OracleScene:
 
     def __init__(self, elements=(), triangle_meshes=(), simd_lanes=8):
         self.elements, self.triangle_meshes = list(elements), list(triangle_meshes)
-        ns, nm = len(self.elements), len(self.triangle_meshes)
-        spheres = (_abi.SphereDescC * max(ns, 1))(*[s.to_c() for s in self.elements])
+        from rbrt_b200.scene import element_arrays
+        order, spheres, tris, ne, ns, nt = element_arrays(self.elements)
+        nm = len(self.triangle_meshes)
         meshes = (_abi.MeshDescC * max(nm, 1))(*[m.to_c() for m in self.triangle_meshes])
         opts = _abi.SceneOptsC(simd_lanes, 0, 0.0, 0)
         self._h = C.c_void_p()
-        check(lib().rbrt_ref_scene_create(spheres, ns, meshes, nm, opts, C.byref(self._h)))
+        check(lib().rbrt_ref_scene_create_elements(order, ne, spheres, ns, tris, nt, meshes, nm, opts, C.byref(self._h)))
 
     @staticmethod
     def from_scene(scene):

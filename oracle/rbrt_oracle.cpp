@@ -328,7 +328,49 @@ bool triangle_soa_sse(const Mesh& m, const Ray& ray, float min_dist, std::vector
     return find_smallest_bigger_than_eps(params.data(), params.size(), m.is_padding.data(), eps_f, t_out, idx_out);
 }
 
+// triangle.rs:9-28 (BasicTriangle) — a single triangle as an element of Scene.elements
+struct BasicTri { V3 corners[3]; V3 normal; V3 edges[2]; Material mat; };
+
+// triangle.rs:92-130
+bool basic_triangle_intersect_w_ray(const Ray& ray, const V3 vertices[3], const V3 edges[2], float min_dist, float max_dist, float& t_out) {
+    float eps = min_dist;
+    V3 h = cross(ray.direction, edges[1]);
+    float a = dot(edges[0], h);
+    if (-eps < a && a < eps) return false;
+    float f = 1.0f / a;
+    V3 s = ray.origin - vertices[0];
+    float u = f * dot(s, h);
+    if (!(0.0f <= u && u <= 1.0f)) return false;                          // !(0.0..=1.0).contains(&u): NaN is not contained
+    V3 q = cross(s, edges[0]);
+    float v = f * dot(ray.direction, q);
+    if (v < 0.0f || u + v > 1.0f) return false;
+    float t = f * dot(edges[1], q);
+    if (t > eps) {
+        V3 p = point_at(ray, t);
+        float dist = length(ray.origin - p);
+        if (dist < min_dist || dist > max_dist) return false;
+        t_out = t;
+        return true;
+    }
+    return false;
+}
+
+// triangle.rs:412-441 (impl Intersectable for BasicTriangle)
+int basic_triangle_intersect(const BasicTri& tr, const Ray& ray, float min_dist, float max_dist, HitInfo& out) {
+    float t;
+    if (!basic_triangle_intersect_w_ray(ray, tr.corners, tr.edges, min_dist, max_dist, t)) return 0;
+    V3 p = point_at(ray, t);
+    float dist = length(ray.origin - p);
+    if (dist < min_dist || dist > max_dist) return 0;
+    out.point = p; out.normal = tr.normal; out.mat = &tr.mat; out.dist = dist; out.t = t;
+    return 1;
+}
+
+struct Element { uint32_t kind; uint32_t index; };                        // entry of Scene.elements: sphere or BasicTriangle
+
 struct Scene {
+    std::vector<Element> elements;                                        // iteration order of scene.rs:23-31
+    std::vector<BasicTri> btris;
     std::vector<Sphere> spheres;
     std::vector<Mesh*> meshes;
     unsigned lanes = 8;
@@ -358,11 +400,15 @@ bool mesh_intersect(const Scene& sc, const Mesh& m, const Ray& ray, float min_di
 int scene_hit(const Scene& sc, const Ray& ray, float min_dist, float max_dist,
               std::vector<float>& scratch, HitInfo& best) {
     bool found = false; float closest = 3.40282347e+38f;
-    for (size_t i = 0; i < sc.spheres.size(); ++i) {
+    for (size_t i = 0; i < sc.elements.size(); ++i) {
         HitInfo h; h.tri = 0;
-        int r = sphere_intersect(sc.spheres[i], ray, min_dist, max_dist, h);
+        const Element& e = sc.elements[i];
+        int r = e.kind == RBRT_ELEM_SPHERE ? sphere_intersect(sc.spheres[e.index], ray, min_dist, max_dist, h)
+                                           : basic_triangle_intersect(sc.btris[e.index], ray, min_dist, max_dist, h);
         if (r < 0) return -1;
-        if (r && h.dist < closest) { closest = h.dist; best = h; best.kind = RBRT_HIT_SPHERE; best.elem = (uint32_t)i; found = true; }
+        if (r && h.dist < closest) {
+            closest = h.dist; best = h; best.kind = e.kind == RBRT_ELEM_SPHERE ? RBRT_HIT_SPHERE : RBRT_HIT_TRIANGLE; best.elem = (uint32_t)i; found = true;
+        }
     }
     for (size_t i = 0; i < sc.meshes.size(); ++i) {
         HitInfo h;
@@ -568,9 +614,10 @@ int rbrt_ref_transform_vertices(float* xyz, uint64_t n, float scale, rbrt_vec3 r
     return RBRT_OK;
 }
 
-int rbrt_ref_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rbrt_mesh_desc* meshes,
-                          uint32_t nm, const rbrt_scene_opts* opts, rbrt_scene** out) {
-    if (!out || (ns && !spheres) || (nm && !meshes)) return fail(RBRT_E_INVALID, "null argument");
+int rbrt_ref_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, uint32_t ns,
+                                   const rbrt_triangle_desc* triangles, uint32_t nt, const rbrt_mesh_desc* meshes, uint32_t nm,
+                                   const rbrt_scene_opts* opts, rbrt_scene** out) {
+    if (!out || (ne && !order) || (ns && !spheres) || (nt && !triangles) || (nm && !meshes)) return fail(RBRT_E_INVALID, "null argument");
     Scene* sc = new Scene();
     sc->lanes = (opts && opts->simd_lanes) ? opts->simd_lanes : 8;
     if (sc->lanes != 8 && sc->lanes != 4) { delete sc; return fail(RBRT_E_INVALID, "simd_lanes must be 8 or 4"); }
@@ -578,6 +625,22 @@ int rbrt_ref_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
         const auto& s = spheres[i];
         if (s.material.kind > 2) { delete sc; return fail(RBRT_E_INVALID, "unknown material kind"); }
         sc->spheres.push_back(Sphere{from(s.center), s.radius, Material{s.material.kind, from(s.material.albedo), s.material.param}});
+    }
+    for (uint32_t i = 0; i < nt; ++i) {                                  // BasicTriangle::new (triangle.rs:19-27)
+        const auto& t = triangles[i];
+        if (t.material.kind > 2) { delete sc; return fail(RBRT_E_INVALID, "unknown material kind"); }
+        BasicTri b;
+        for (int k = 0; k < 3; ++k) b.corners[k] = from(t.corners[k]);
+        b.normal = triangle_normal(b.corners[0], b.corners[1], b.corners[2]);
+        b.edges[0] = b.corners[1] - b.corners[0]; b.edges[1] = b.corners[2] - b.corners[0];
+        b.mat = Material{t.material.kind, from(t.material.albedo), t.material.param};
+        sc->btris.push_back(b);
+    }
+    for (uint32_t i = 0; i < ne; ++i) {
+        if ((order[i].kind == RBRT_ELEM_SPHERE && order[i].index >= ns) || (order[i].kind == RBRT_ELEM_TRIANGLE && order[i].index >= nt) || order[i].kind > 1) {
+            delete sc; return fail(RBRT_E_INVALID, "bad element");
+        }
+        sc->elements.push_back(Element{order[i].kind, order[i].index});
     }
     for (uint32_t i = 0; i < nm; ++i) {
         const auto& m = meshes[i];
@@ -587,6 +650,13 @@ int rbrt_ref_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
     }
     *out = reinterpret_cast<rbrt_scene*>(sc);
     return RBRT_OK;
+}
+
+int rbrt_ref_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rbrt_mesh_desc* meshes, uint32_t nm,
+                          const rbrt_scene_opts* opts, rbrt_scene** out) {
+    std::vector<rbrt_element_ref> order(ns);
+    for (uint32_t i = 0; i < ns; ++i) order[i] = rbrt_element_ref{RBRT_ELEM_SPHERE, i};
+    return rbrt_ref_scene_create_elements(order.data(), ns, spheres, ns, nullptr, 0, meshes, nm, opts, out);
 }
 int rbrt_ref_scene_destroy(rbrt_scene* s) { delete reinterpret_cast<Scene*>(s); return RBRT_OK; }
 

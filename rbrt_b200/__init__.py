@@ -6,7 +6,7 @@ Host mirror of the reference's public surface (names and argument order as in rb
 The hot path runs in rbrt_b200/librbrt_gpu.so (hand-written CUDA, csrc/) through the C-ABI of
 include/rbrt_gpu.h.  There is no CPU fallback.
 """
-from ._abi import (HIT_DTYPE, HIT_MESH, HIT_NONE, HIT_SPHERE, SHARD_NONE, SHARD_SAMPLES, SHARD_TILES, TRACE_BRUTE,
+from ._abi import (HIT_DTYPE, HIT_MESH, HIT_NONE, HIT_SPHERE, HIT_TRIANGLE, SHARD_NONE, SHARD_SAMPLES, SHARD_TILES, TRACE_BRUTE,
                    TRACE_BVH, RbrtGpuError)
 from .blueprints import (CameraBluePrint, SceneBlueprint, SphereBlueprint, TriangleMeshBlueprint,
                          create_material_from_description, create_scene_from_scene_blueprint,
@@ -17,6 +17,7 @@ from .mesh import TriangleMesh, load_mesh_vertices_from_file
 from .render import ImageBuffer, primary_rays, render_scene, render_scene_hdr
 from .scene import Scene
 from .sphere import Sphere
+from .triangle import BasicTriangle
 from .vec3 import Ray, Vec3
 
 

@@ -34,6 +34,14 @@ class SphereDescC(C.Structure):
     _fields_ = [("center", Vec3C), ("radius", C.c_float), ("material", MaterialC)]
 
 
+class TriangleDescC(C.Structure):  # BasicTriangle::new(corners, material) (triangle.rs:9-28)
+    _fields_ = [("corners", Vec3C * 3), ("material", MaterialC)]
+
+
+class ElementRefC(C.Structure):  # one entry of Scene.elements, in order
+    _fields_ = [("kind", C.c_uint32), ("index", C.c_uint32)]
+
+
 class MeshDescC(C.Structure):
     _fields_ = [("tri_vertices", C.POINTER(C.c_float)), ("num_triangles", C.c_uint64), ("material", MaterialC)]
 
@@ -82,7 +90,8 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE = 0, 1
 OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL = 1, 2, 4
-HIT_NONE, HIT_SPHERE, HIT_MESH = -1, 0, 1
+HIT_NONE, HIT_SPHERE, HIT_MESH, HIT_TRIANGLE = -1, 0, 1, 2
+ELEM_SPHERE, ELEM_TRIANGLE = 0, 1
 E_INVALID, E_CUDA, E_NODEVICE = 1, 2, 3
 
 P = C.POINTER
@@ -92,6 +101,8 @@ GPU_SIGNATURES = {
     "rbrt_transform_vertices": (C.c_int, [P(C.c_float), C.c_uint64, C.c_float, Vec3C, Vec3C]),
     "rbrt_gpu_init": (C.c_int, [C.c_int]),
     "rbrt_gpu_scene_create": (C.c_int, [P(SphereDescC), C.c_uint32, P(MeshDescC), C.c_uint32, P(SceneOptsC), P(C.c_void_p)]),
+    "rbrt_gpu_scene_create_elements": (C.c_int, [P(ElementRefC), C.c_uint32, P(SphereDescC), C.c_uint32, P(TriangleDescC), C.c_uint32,
+                                                P(MeshDescC), C.c_uint32, P(SceneOptsC), P(C.c_void_p)]),
     "rbrt_gpu_scene_info": (C.c_int, [C.c_void_p, P(SceneInfoC)]),
     "rbrt_gpu_scene_destroy": (C.c_int, [C.c_void_p]),
     "rbrt_gpu_render": (C.c_int, [C.c_void_p, P(CameraC), C.c_uint32, P(RenderOptsC), C.c_void_p, P(StatsC)]),

@@ -115,6 +115,23 @@ int rbrt_gpu_init(int device) {
 int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rbrt_mesh_desc* meshes, uint32_t nm,
                           const rbrt_scene_opts* opts, rbrt_scene** out) {
     if (!out || (ns && !spheres) || (nm && !meshes)) { set_error("null argument"); return RBRT_E_INVALID; }
+    std::vector<rbrt_element_ref> order(ns);
+    for (uint32_t i = 0; i < ns; ++i) order[i] = rbrt_element_ref{RBRT_ELEM_SPHERE, i};
+    return rbrt_gpu_scene_create_elements(order.data(), ns, spheres, ns, nullptr, 0, meshes, nm, opts, out);
+}
+
+int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, uint32_t n_sph,
+                                   const rbrt_triangle_desc* triangles, uint32_t n_bt, const rbrt_mesh_desc* meshes, uint32_t nm,
+                                   const rbrt_scene_opts* opts, rbrt_scene** out) {
+    if (!out || (ne && !order) || (n_sph && !spheres) || (n_bt && !triangles) || (nm && !meshes)) { set_error("null argument"); return RBRT_E_INVALID; }
+    for (uint32_t i = 0; i < ne; ++i) {
+        if (order[i].kind == RBRT_ELEM_SPHERE ? order[i].index >= n_sph : (order[i].kind == RBRT_ELEM_TRIANGLE ? order[i].index >= n_bt : true)) {
+            set_error("element %u: bad kind or index", i); return RBRT_E_INVALID;
+        }
+        const rbrt_material& m = order[i].kind == RBRT_ELEM_SPHERE ? spheres[order[i].index].material : triangles[order[i].index].material;
+        if (m.kind > 2) { set_error("element %u: unknown material kind", i); return RBRT_E_INVALID; }
+    }
+    const uint32_t ns = ne;                                               // below, `ns` counts ELEMENTS (spheres + basic triangles)
     *out = nullptr;
     uint32_t lanes = (opts && opts->simd_lanes) ? opts->simd_lanes : 8;
     if (lanes != 8 && lanes != 4) { set_error("simd_lanes must be 8 (AVX) or 4 (SSE)"); return RBRT_E_INVALID; }
@@ -124,7 +141,6 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
     if (opts && opts->box_pad_rel > 0.0f) pad_rel = opts->box_pad_rel;
     else if (opts && opts->box_pad_rel < 0.0f) pad_rel = 0.0f;
     if ((uint64_t)ns + nm > 65535) { set_error("more than 65535 scene elements"); return RBRT_E_INVALID; }
-    for (uint32_t i = 0; i < ns; ++i) if (spheres[i].material.kind > 2) { set_error("sphere %u: unknown material kind", i); return RBRT_E_INVALID; }
     uint64_t total_tris = 0, total_eff = 0;
     for (uint32_t i = 0; i < nm; ++i) {
         if (meshes[i].material.kind > 2) { set_error("mesh %u: unknown material kind", i); return RBRT_E_INVALID; }
@@ -155,32 +171,56 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
 #define CKSC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { int rc_ = cuda_fail(e_, #x); destroy_scene(sc); return rc_; } } while (0)
 
     // ---- elements: spheres + per-element materials (flattened SoA, 16-byte records)
-    std::vector<float4> sph(ns), mat(ns + nm);
-    std::vector<uint32_t> kind(ns + nm);
+    std::vector<float4> sph(ns), mat(ns + nm), etris;
+    std::vector<uint32_t> kind(ns + nm), ekind(ns);
     for (uint32_t i = 0; i < ns; ++i) {
-        sph[i] = make_float4(spheres[i].center.x, spheres[i].center.y, spheres[i].center.z, spheres[i].radius);
-        mat[i] = make_float4(spheres[i].material.albedo.x, spheres[i].material.albedo.y, spheres[i].material.albedo.z, spheres[i].material.param);
-        kind[i] = spheres[i].material.kind;
+        rbrt_material m;
+        if (order[i].kind == RBRT_ELEM_SPHERE) {
+            const rbrt_sphere_desc& sp = spheres[order[i].index];
+            sph[i] = make_float4(sp.center.x, sp.center.y, sp.center.z, sp.radius);
+            m = sp.material; ekind[i] = RBRT_ELEM_SPHERE;
+        } else {                                                          // BasicTriangle::new (triangle.rs:19-27), host f32, no contraction
+            const rbrt_triangle_desc& t = triangles[order[i].index];
+            const rbrt_vec3 &a = t.corners[0], &b = t.corners[1], &c = t.corners[2];
+            float e1[3] = {b.x - a.x, b.y - a.y, b.z - a.z}, e2[3] = {c.x - a.x, c.y - a.y, c.z - a.z};
+            float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            float len = sqrtf(cx * cx + cy * cy + cz * cz);
+            uint32_t ti = (uint32_t)(etris.size() / 4);
+            float tif; memcpy(&tif, &ti, 4);
+            sph[i] = make_float4(tif, 0.0f, 0.0f, 0.0f);
+            etris.push_back(make_float4(a.x, a.y, a.z, 0.0f)); etris.push_back(make_float4(e1[0], e1[1], e1[2], 0.0f));
+            etris.push_back(make_float4(e2[0], e2[1], e2[2], 0.0f)); etris.push_back(make_float4(cx / len, cy / len, cz / len, 0.0f));
+            m = t.material; ekind[i] = RBRT_ELEM_TRIANGLE;
+        }
+        mat[i] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.param);
+        kind[i] = m.kind;
     }
     for (uint32_t i = 0; i < nm; ++i) {
         mat[ns + i] = make_float4(meshes[i].material.albedo.x, meshes[i].material.albedo.y, meshes[i].material.albedo.z, meshes[i].material.param);
         kind[ns + i] = meshes[i].material.kind;
     }
-    float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals; uint32_t* d_kind; MeshDev* d_meshes;
+    float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals, *d_etris; uint32_t *d_kind, *d_ekind; MeshDev* d_meshes;
     {
+        const size_t b_etris = a256(16ull * etris.size()), b_ekind = a256(4ull * ns);
         const size_t b_sph = a256(16ull * ns), b_mat = a256(16ull * (ns + nm)), b_kind = a256(4ull * (ns + nm)), b_tris = a256(48ull * total_eff),
                      b_nodes = a256(64ull * total_eff), b_nrm = a256(16ull * total_eff), b_mesh = a256(sizeof(MeshDev) * nm);
         char* base = nullptr;
-        CKS(arena_alloc(sc, b_nodes + b_tris + b_nrm + b_sph + b_mat + b_kind + b_mesh, &base));
+        CKS(arena_alloc(sc, b_nodes + b_tris + b_nrm + b_sph + b_mat + b_kind + b_mesh + b_etris + b_ekind, &base));
         d_nodes = (float4*)base; base += b_nodes;                          // nodes and triangles adjacent: the data every ray re-reads
         d_tris = (float4*)base; base += b_tris;
         d_normals = (float4*)base; base += b_nrm;
         d_sph = (float4*)base; base += b_sph;
         d_mat = (float4*)base; base += b_mat;
         d_kind = (uint32_t*)base; base += b_kind;
-        d_meshes = (MeshDev*)base;
+        d_meshes = (MeshDev*)base; base += b_mesh;
+        d_etris = (float4*)base; base += b_etris;
+        d_ekind = (uint32_t*)base;
     }
     if (ns) CKSC(cudaMemcpy(d_sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
+    if (!etris.empty()) {
+        CKSC(cudaMemcpy(d_etris, etris.data(), 16ull * etris.size(), cudaMemcpyHostToDevice));
+        CKSC(cudaMemcpy(d_ekind, ekind.data(), 4ull * ns, cudaMemcpyHostToDevice));
+    }
     if (ns + nm) {
         CKSC(cudaMemcpy(d_mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice));
         CKSC(cudaMemcpy(d_kind, kind.data(), 4ull * (ns + nm), cudaMemcpyHostToDevice));
@@ -220,6 +260,7 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
     }
     if (nm) CKSC(cudaMemcpy(d_meshes, sc->meshes_h.data(), sizeof(MeshDev) * nm, cudaMemcpyHostToDevice));
     CKSC(cudaDeviceSynchronize());
+    sc->dev.etris = d_etris; sc->dev.elem_kind = d_ekind; sc->dev.n_etris = (uint32_t)(etris.size() / 4);
     sc->dev.spheres = d_sph; sc->dev.tris = d_tris; sc->dev.nodes = d_nodes; sc->dev.normals = d_normals;
     sc->dev.mat = d_mat; sc->dev.mat_kind = d_kind; sc->dev.meshes = d_meshes; sc->dev.n_spheres = ns; sc->dev.n_meshes = nm;
     sc->info.num_bvh_nodes = live_total;

@@ -82,14 +82,17 @@ struct MeshDev {
 };
 
 struct SceneDev {
-    const float4* spheres;     // {cx, cy, cz, r}
+    const float4* spheres;     // per ELEMENT of Scene.elements, in order: sphere {cx, cy, cz, r}; BasicTriangle {bits(index into etris), 0, 0, 0}
+    const float4* etris;       // BasicTriangle elements: 4 x float4 {v0}, {e1}, {e2}, {unit normal} (triangle.rs:9-28)
+    const uint32_t* elem_kind; // per element: RBRT_ELEM_*; only read when n_etris > 0
     const float4* tris;        // 3 x float4 per triangle: {v0.xyz, bits(orig idx)}, {e1.xyz, 0}, {e2.xyz, 0}
     const float4* nodes;       // 4 x 16 B per 4-wide BVH node: child boxes on the mesh's 16-bit grid + 4 child refs (intersect.cuh)
     const float4* normals;     // {n.xyz, 0} per triangle, original order
     const float4* mat;         // per element: {albedo.xyz, param}
     const uint32_t* mat_kind;  // per element: RBRT_MAT_*
     const MeshDev* meshes;
-    uint32_t n_spheres, n_meshes;
+    uint32_t n_spheres, n_meshes;   // n_spheres = number of ELEMENTS (spheres + basic triangles)
+    uint32_t n_etris;
 };
 
 // leaf reference encoding: ~((first << 3) | (count - 1)), count in 1..8

@@ -48,6 +48,45 @@ __device__ __forceinline__ int sphere_intersect(float4 s, f3 o, f3 d, float& t_o
     return 1;
 }
 
+// ------------------------------------------------------------------ triangle.rs:92-130 + 412-441 (BasicTriangle element)
+// returns 1 hit, 0 miss.  Same op sequence as the mesh sweep, but: `u` must be CONTAINED in [0,1] (a NaN u rejects,
+// `!(0.0..=1.0).contains(&u)`), no upper cap on t, dist accepted in [min_dist, max_dist] inclusive (NaN dist passes).
+__device__ __forceinline__ int basic_triangle_intersect(const float4* __restrict__ rec, f3 o, f3 d, float& t_out, float& dist_out) {
+    float4 a4 = __ldg(rec), b4 = __ldg(rec + 1), c4 = __ldg(rec + 2);
+    f3 v0 = mk3(a4.x, a4.y, a4.z), e1 = mk3(b4.x, b4.y, b4.z), e2 = mk3(c4.x, c4.y, c4.z);
+    f3 h = cross3(d, e2);
+    float a = dot3(e1, h);
+    if (-RBRT_MIN_DIST < a && a < RBRT_MIN_DIST) return 0;
+    float f = XDIV(1.0f, a);
+    f3 s = o - v0;
+    float u = XMUL(f, dot3(s, h));
+    if (!(u >= 0.0f && u <= 1.0f)) return 0;
+    f3 q = cross3(s, e1);
+    float v = XMUL(f, dot3(d, q));
+    if (v < 0.0f || XADD(u, v) > 1.0f) return 0;
+    float t = XMUL(f, dot3(e2, q));
+    if (!(t > RBRT_MIN_DIST)) return 0;
+    f3 p = o + t * d;
+    float dist = len3(o - p);
+    if (dist < RBRT_MIN_DIST || dist > RBRT_MAX_DIST) return 0;
+    t_out = t; dist_out = dist;
+    return 1;
+}
+
+// One entry of Scene.elements: sphere or BasicTriangle.  returns 1 hit, 0 miss, -1 NaN discriminant (spheres only)
+__device__ __forceinline__ int element_intersect(const SceneDev& S, uint32_t i, f3 o, f3 d, float& t_out, float& dist_out) {
+    float4 e = __ldg(S.spheres + i);
+    if (S.n_etris && __ldg(S.elem_kind + i)) return basic_triangle_intersect(S.etris + 4 * (size_t)__float_as_uint(e.x), o, d, t_out, dist_out);
+    return sphere_intersect(e, o, d, t_out, dist_out);
+}
+
+// hit_normal of an element hit: sphere p - c, un-normalised (sphere.rs:56); BasicTriangle its stored unit normal (triangle.rs:433)
+__device__ __forceinline__ f3 element_normal(const SceneDev& S, uint32_t i, f3 p) {
+    float4 e = __ldg(S.spheres + i);
+    if (S.n_etris && __ldg(S.elem_kind + i)) { float4 n = __ldg(S.etris + 4 * (size_t)__float_as_uint(e.x) + 3); return mk3(n.x, n.y, n.z); }
+    return p - mk3(e.x, e.y, e.z);
+}
+
 // ------------------------------------------------------------------ aabbox.rs:28-58 (whole-mesh pre-test)
 __device__ __forceinline__ bool mesh_bbox_hit(const MeshDev& m, f3 o, f3 d) {
     float tlx = XDIV(XSUB(m.lo[0], o.x), d.x), tux = XDIV(XSUB(m.hi[0], o.x), d.x);
@@ -225,7 +264,7 @@ __device__ __forceinline__ Hit scene_hit(const SceneDev& S, f3 o, f3 d, TraceCou
     float closest = 3.40282347e+38f;                                     // f32::MAX (scene.rs:21)
     for (uint32_t i = 0; i < S.n_spheres; ++i) {                         // spheres first, in order (scene.rs:23-31)
         float t, dist;
-        int r = sphere_intersect(__ldg(S.spheres + i), o, d, t, dist);
+        int r = element_intersect(S, i, o, d, t, dist);
         if (r < 0) { best.kind = -2; return best; }
         if (r && dist < closest) { closest = dist; best.kind = 0; best.elem = i; best.t = t; best.dist = dist; }
     }

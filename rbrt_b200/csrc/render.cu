@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
     int kind = -1; uint32_t elem = 0; float t_s = 0.0f;
     for (uint32_t i = 0; i < P.S.n_spheres; ++i) {                       // spheres first, in order (scene.rs:23-31)
         float t, dist;
-        int r = sphere_intersect(__ldg(P.S.spheres + i), o, d, t, dist);
+        int r = element_intersect(P.S, i, o, d, t, dist);
         if (r < 0) { ++nan_count; end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }   // reference panics (sphere.rs:33)
         if (r && dist < closest) { closest = dist; kind = 0; elem = i; t_s = t; }
     }
@@ -363,10 +363,8 @@ __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it,
     uint32_t elem = h.y;
     f3 point = o + t * d;                                                 // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
     f3 normal;
-    if (h.w == 0u) {                                                      // sphere: p - c, un-normalised (sphere.rs:56)
-        float4 s = __ldg(P.S.spheres + elem);
-        normal = point - mk3(s.x, s.y, s.z);
-    } else {                                                              // mesh: stored unit normal (mesh.rs:253-257)
+    if (h.w == 0u) normal = element_normal(P.S, elem, point);            // sphere: p - c, un-normalised (sphere.rs:56); BasicTriangle: stored normal
+    else {                                                              // mesh: stored unit normal (mesh.rs:253-257)
         const MeshDev& M = P.S.meshes[elem - P.S.n_spheres];
         float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
         normal = mk3(nn.x, nn.y, nn.z);
@@ -675,7 +673,7 @@ __global__ void __launch_bounds__(256) k_trace_rays(SceneDev S, const rbrt_ray* 
         if (h.kind >= 0) {
             f3 p = o + h.t * d;
             f3 nrm;
-            if (h.kind == 0) { float4 s = __ldg(S.spheres + h.elem); nrm = p - mk3(s.x, s.y, s.z); }
+            if (h.kind == 0) { nrm = element_normal(S, h.elem, p); if (S.n_etris && __ldg(S.elem_kind + h.elem)) out.kind = RBRT_HIT_TRIANGLE; }
             else { float4 nn = __ldg(S.normals + S.meshes[h.elem].nrm_base + h.tri); nrm = mk3(nn.x, nn.y, nn.z); }
             out.elem_idx = h.elem; out.tri_idx = h.tri; out.t = h.t; out.dist = h.dist;
             out.point.x = p.x; out.point.y = p.y; out.point.z = p.z;

@@ -1,4 +1,4 @@
-"""Scene — host mirror of rbrt_lib::scene::Scene (scene.rs:12-16): `elements` (spheres),
+"""Scene — host mirror of rbrt_lib::scene::Scene (scene.rs:12-16): `elements` (spheres and BasicTriangles, any `Intersectable` of the reference that has a GPU twin),
 `triangle_meshes`, `lights` (dead in the reference, scene.rs:7-10).  The GPU scene (flattened SoA buffers
 + one LBVH per mesh) is created lazily on first use and owned by this object."""
 import ctypes as C
@@ -6,6 +6,21 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
+
+
+def element_arrays(elements):
+    """Scene.elements (spheres and BasicTriangles, in order) -> the arrays rbrt_gpu_scene_create_elements takes."""
+    from .triangle import BasicTriangle
+    sph = [e for e in elements if not isinstance(e, BasicTriangle)]
+    tri = [e for e in elements if isinstance(e, BasicTriangle)]
+    order, si, ti = [], 0, 0
+    for e in elements:
+        if isinstance(e, BasicTriangle):
+            order.append(_abi.ElementRefC(_abi.ELEM_TRIANGLE, ti)); ti += 1
+        else:
+            order.append(_abi.ElementRefC(_abi.ELEM_SPHERE, si)); si += 1
+    return ((_abi.ElementRefC * max(len(order), 1))(*order), (_abi.SphereDescC * max(len(sph), 1))(*[s.to_c() for s in sph]),
+            (_abi.TriangleDescC * max(len(tri), 1))(*[t.to_c() for t in tri]), len(order), len(sph), len(tri))
 
 
 class Scene:
@@ -20,12 +35,12 @@ class Scene:
     def handle(self):
         if self._handle is None:
             lib = _abi.lib()
-            ns, nm = len(self.elements), len(self.triangle_meshes)
-            spheres = (_abi.SphereDescC * max(ns, 1))(*[s.to_c() for s in self.elements])
+            order, spheres, tris, ne, ns, nt = element_arrays(self.elements)
+            nm = len(self.triangle_meshes)
             meshes = (_abi.MeshDescC * max(nm, 1))(*[m.to_c() for m in self.triangle_meshes])
             opts = _abi.SceneOptsC(self.simd_lanes, self.leaf_size, self.box_pad_rel, 0)
             h = C.c_void_p()
-            _abi.check(lib.rbrt_gpu_scene_create(spheres, ns, meshes, nm, opts, C.byref(h)))
+            _abi.check(lib.rbrt_gpu_scene_create_elements(order, ne, spheres, ns, tris, nt, meshes, nm, opts, C.byref(h)))
             self._handle = h
         return self._handle
 

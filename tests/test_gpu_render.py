@@ -224,3 +224,11 @@ def test_many_elements_render(gpu, oracle):
     ref = oracle.OracleScene.from_scene(scene).render_hdr(cam.to_c(), 4, _abi.RenderOptsC(seed=21))
     for kw in [{}, {"no_tail_kernel": True}]:
         assert_images_equal(R.render_scene_hdr(cam, 4, scene, seed=21, **kw), ref, f"many elements {kw}")
+
+
+def test_basic_triangle_elements_render(gpu, oracle):
+    from .test_gpu_trace import mixed_element_scene
+    scene, cam = mixed_element_scene(), S.example_camera(128, 96)
+    ref = oracle.OracleScene.from_scene(scene).render_hdr(cam.to_c(), 6, _abi.RenderOptsC(seed=31))
+    for kw in [{}, {"no_tail_kernel": True}, {"trace_mode": _abi.TRACE_BRUTE}]:
+        assert_images_equal(R.render_scene_hdr(cam, 6, scene, seed=31, **kw), ref, f"mixed elements {kw}")

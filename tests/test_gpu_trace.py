@@ -202,3 +202,34 @@ def test_builder_edge_cases(gpu, oracle):
         scene.elements.append(R.Sphere(Vec3(c[0], c[1], c[2] - 40), float(rng.uniform(0.3, 2.0)), R.Lambertian(Vec3(0.5, 0.5, 0.5))))
     rays = S.random_rays(20000, (0, 0, -40), 25.0, 6)
     assert_same(scene.hit(rays), oracle.OracleScene.from_scene(scene).hit(rays), "300 spheres")
+
+
+def mixed_element_scene():
+    """Spheres and BasicTriangles interleaved in Scene.elements, plus a mesh."""
+    rng = np.random.default_rng(8)
+    els = [R.Sphere(Vec3(0.0, -1000.0, -5.0), 1000.0, R.Lambertian(Vec3(0.02, 0.2, 0.1)))]
+    mats = [R.Lambertian(Vec3(0.7, 0.2, 0.2)), R.Metal(Vec3(0.9, 0.9, 0.9), 0.02), R.Dielectric(1.5)]
+    for i in range(12):
+        c = rng.uniform(-4, 4, size=3) + np.array([0, 4.5, -9])
+        if i % 2:
+            els.append(R.Sphere(Vec3(*c), float(rng.uniform(0.4, 1.0)), mats[i % 3]))
+        else:
+            p = c + rng.uniform(-1.5, 1.5, size=(3, 3))
+            els.append(R.BasicTriangle.new([tuple(v) for v in p], mats[i % 3]))
+    els.append(R.BasicTriangle.new([(-30, 0.5, -30), (30, 0.5, -30), (0, 30, -30)], R.Metal(Vec3(0.8, 0.8, 0.9), 0.0)))   # a big mirror behind
+    scene = R.Scene(elements=els)
+    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(3, 1.5, (2.5, 1.5, -7.0)), R.Dielectric(1.5)))
+    return scene
+
+
+def test_basic_triangle_elements(gpu, oracle):
+    scene = mixed_element_scene()
+    cam = S.example_camera(128, 96)
+    rays = np.concatenate([R.primary_rays(cam, 4, 0), S.random_rays(20000, (0, 4, -9), 5.0, 3)], 0)
+    ref = oracle.OracleScene.from_scene(scene).hit(rays)
+    assert (ref["kind"] == 2).sum() > 500 and (ref["kind"] == 0).sum() > 500 and (ref["kind"] == 1).sum() > 100
+    for mode in MODES:
+        assert_same(scene.hit(rays, mode), ref, f"mixed elements mode {mode}")
+    big = R.Scene(elements=[R.BasicTriangle.new(((-900, -900, -1500), (900, -900, -1500), (0, 900, -1500)), R.Lambertian(Vec3(1, 1, 1)))])
+    h = big.hit(np.float32([[0, 0, 0, 0, 0, -1]]))
+    assert h["kind"][0] == 2 and abs(h["t"][0] - 1500.0) < 1e-2                       # no upper cap on t for BasicTriangle (triangle.rs:118)

@@ -188,3 +188,28 @@ def test_q11_q15_depth_and_output(oracle):  # lib.rs:54-66,99,101,118-120
     assert np.allclose(hdr, 1.0, atol=1e-5), hdr
     rgb = osc.render(cam.to_c(), 4, _abi.RenderOptsC(seed=0))
     assert (rgb >= 254).all()
+
+
+def test_basic_triangle_element(oracle):  # triangle.rs:9-28, 92-130, 412-441
+    """BasicTriangle as an element of Scene.elements: CCW unit normal, same Moeller-Trumbore arithmetic as the mesh sweep
+    but no upper cap on t (a mesh triangle at t = 1500 is invisible, a BasicTriangle is hit), dist window inclusive, element
+    order decides exact ties, and it shares `elements` with the spheres."""
+    big = ((-900, -900, -1500), (900, -900, -1500), (0, 900, -1500))
+    sc = R.Scene()
+    sc.elements.append(R.BasicTriangle.new(big, R.Lambertian(Vec3(1, 1, 1))))
+    h = trace(oracle, sc, [[0, 0, 0, 0, 0, -1]])
+    assert h["kind"][0] == 2 and abs(h["t"][0] - 1500.0) < 1e-2 and np.array_equal(h["normal"][0], np.float32([0, 0, 1]))
+    assert trace(oracle, one_tri_scene(big), [[0, 0, 0, 0, 0, -1]])["kind"][0] == -1          # the mesh sweep caps t at 999.99994
+    far = tuple((x, y, -2001.0) for x, y, _ in big)
+    sc = R.Scene(); sc.elements.append(R.BasicTriangle.new(far, R.Lambertian(Vec3(1, 1, 1))))
+    assert trace(oracle, sc, [[0, 0, 0, 0, 0, -1]])["kind"][0] == -1                             # dist > max_dist
+    # exact tie between a sphere surface and a triangle at dist 5: whichever comes first in `elements` wins (strict <)
+    tri = R.BasicTriangle.new(TRI, R.Metal(Vec3(1, 1, 1), 0.0))
+    sph = R.Sphere(Vec3(0, 0, -6.0), 1.0, R.Lambertian(Vec3(1, 1, 1)))
+    for els, want in (([tri, sph], 2), ([sph, tri], 0)):
+        sc = R.Scene(elements=els)
+        h = trace(oracle, sc, [[0, 0, 0, 0, 0, -1]])
+        assert h["kind"][0] == want and h["elem_idx"][0] == 0 and h["dist"][0] == 5.0
+    # back face is hit too, the normal is never flipped
+    h = trace(oracle, R.Scene(elements=[tri]), [[0, 0, -10, 0, 0, 1]])
+    assert h["kind"][0] == 2 and np.array_equal(h["normal"][0], np.float32([0, 0, 1]))
