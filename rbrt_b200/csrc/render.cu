@@ -96,12 +96,14 @@ __device__ __forceinline__ void end_path(const WaveParams& P, uint32_t pid, f3 c
 
 // ------------------------------------------------------------------ stage A of Scene::hit (scene.rs:19-31 + mesh.rs:233)
 // `it` = bounce iteration of the ray (number of scatters before it).  Returns the queue class of the ray.
+template <bool ET>   // ET: Scene.elements holds BasicTriangles besides spheres (separate kernel instantiations, so the usual
+                    // sphere-only kernels carry no trace of the triangle path)
 __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, uint32_t pid, f3 o, f3 d, uint32_t& nan_count) {
     float closest = 3.40282347e+38f;                                     // f32::MAX (scene.rs:21)
     int kind = -1; uint32_t elem = 0; float t_s = 0.0f;
-    for (uint32_t i = 0; i < P.S.n_spheres; ++i) {                       // spheres first, in order (scene.rs:23-31)
+    for (uint32_t i = 0; i < P.S.n_spheres; ++i) {                       // elements first, in order (scene.rs:23-31)
         float t, dist;
-        int r = element_intersect(P.S, i, o, d, t, dist);
+        int r = ET ? element_intersect(P.S, i, o, d, t, dist) : sphere_intersect(__ldg(P.S.spheres + i), o, d, t, dist);
         if (r < 0) { ++nan_count; end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }   // reference panics (sphere.rs:33)
         if (r && dist < closest) { closest = dist; kind = 0; elem = i; t_s = t; }
     }
@@ -128,6 +130,7 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
 }
 
 // ------------------------------------------------------------------ generate (cam.rs:64-82) + stage A
+template <bool ET>
 __global__ void __launch_bounds__(256) k_generate(WaveParams P) {
     const uint32_t n_paths = P.s_count * P.paths_px;                      // multiple of 32
     const uint32_t n_groups = n_paths >> 5, lane = threadIdx.x & 31;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(256) k_generate(WaveParams P) {
                 f3 o, d;
                 camera_ray(P.cam, row, col, key, row * P.cam.width + col, P.s_base + s_local, o, d);
                 ++rays;
-                df.set(r, stage_a(P, 0, pid, o, d, nan_count), pid);
+                df.set(r, stage_a<ET>(P, 0, pid, o, d, nan_count), pid);
             }
         }
         flush(P, 0, df);
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) 
 
 // ------------------------------------------------------------------ shade (lib.rs:54-62 + the scatter impls) + stage A
 // One hit of material `kind` at iteration `it`: scatter, then stage A of the continuation ray.  Returns its queue class.
+template <bool ET>
 __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid, RngKey key,
                                                uint32_t& rays, uint32_t& nan_count) {
     float4 a = P.ray_o[pid], b = P.ray_d[pid];
@@ -363,7 +367,10 @@ __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it,
     uint32_t elem = h.y;
     f3 point = o + t * d;                                                 // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
     f3 normal;
-    if (h.w == 0u) normal = element_normal(P.S, elem, point);            // sphere: p - c, un-normalised (sphere.rs:56); BasicTriangle: stored normal
+    if (h.w == 0u) {                                                      // sphere: p - c, un-normalised (sphere.rs:56); BasicTriangle: stored normal
+        if (ET) normal = element_normal(P.S, elem, point);
+        else { float4 s4 = __ldg(P.S.spheres + elem); normal = point - mk3(s4.x, s4.y, s4.z); }
+    }
     else {                                                              // mesh: stored unit normal (mesh.rs:253-257)
         const MeshDev& M = P.S.meshes[elem - P.S.n_spheres];
         float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
@@ -378,9 +385,10 @@ __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it,
     if (!cont) { end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }       // absorbed (metal.rs:24) -> black
     P.hist[(size_t)it * P.cap + pid] = (uint16_t)elem;
     ++rays;
-    return stage_a(P, it + 1, pid, point, out_d, nan_count);
+    return stage_a<ET>(P, it + 1, pid, point, out_d, nan_count);
 }
 
+template <bool ET>
 __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n0 = c->mat_count[0], n1 = c->mat_count[1], n2 = c->mat_count[2];
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
             else { kind = 2; j = w - a1; nk = n2; }
             if (j >= nk) continue;
             uint32_t pid = P.matq[it & 1][kind][j];
-            df.set(r, shade_item(P, it, kind, pid, key, rays, nan_count), pid);
+            df.set(r, shade_item<ET>(P, it, kind, pid, key, rays, nan_count), pid);
         }
         flush(P, it + 1, df);
     }
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
 // candidates and pending hits of iteration `it`) and runs each path to its end inside one lane — colorize's own
 // loop (lib.rs:43-73) — with the same device functions as the wavefront kernels, so results are bit-identical.
 // It raises ctr[0].pad; the remaining trace / shade / finish launches of the batch return at once.
-template <bool BRUTE, bool COUNT>
+template <bool BRUTE, bool COUNT, bool ET>
 __global__ void __launch_bounds__(256) k_finish(WaveParams P, uint32_t it0, uint32_t max_rays) {
     if (P.ctr[0].pad) return;
     const IterCtr c = P.ctr[it0];
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(256) k_finish(WaveParams P, uint32_t it0, uint
         for (;;) {
             if (kind == CLS_CAND) { ++n_cand; kind = process_candidate<BRUTE>(P, it, pid, COUNT ? &cnt : nullptr); }
             if (kind < 0) break;                                          // path ended (miss / depth exhausted)
-            uint32_t cls = shade_item(P, it, (uint32_t)kind, pid, key, rays, nan_count);
+            uint32_t cls = shade_item<ET>(P, it, (uint32_t)kind, pid, key, rays, nan_count);
             if (cls == CLS_NONE) break;                                   // absorbed / resolved on the spot
             kind = (int)cls; ++it;
         }
@@ -486,7 +494,7 @@ __global__ void k_sum_rays(WaveParams P) {
 #define TAIL_THREADS 128
 #define TAIL_FORCE_IT 12        // from this bounce iteration on, the tail kernel takes whatever is left
 
-template <bool COUNT>
+template <bool COUNT, bool ET>
 __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t it0, uint32_t max_rays) {
     if (P.ctr[0].pad) return;
     const IterCtr c = P.ctr[it0];
@@ -585,7 +593,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         }
         // ---- (3) pending hits: scatter + stage A, repeated while the continuation ray is resolved by a sphere alone
         while (pending >= 0) {
-            uint32_t cls = shade_item(P, it, (uint32_t)pending, pid, key, rays, nan_count);
+            uint32_t cls = shade_item<ET>(P, it, (uint32_t)pending, pid, key, rays, nan_count);
             ++it;
             if (cls == CLS_CAND) { pending = -1; load_candidate(); }
             else if (cls == CLS_NONE) pending = -1;                       // absorbed, missed, depth exhausted: path over
@@ -817,16 +825,17 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         if (!per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_trace<false>, TRACE_THREADS, 0));
         per_sm = per_sm_cached;
         const int grid_trace = sc.sm_count * (per_sm > 0 ? per_sm : 4);
-        if (!fin_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm_cached, k_finish<false, false>, 256, 0));
+        if (!fin_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm_cached, k_finish<false, false, false>, 256, 0));
         const int fin_per_sm = fin_per_sm_cached;                         // k_finish: one resident wave of 256-thread blocks
         const int grid_fin = sc.sm_count * (fin_per_sm > 0 ? fin_per_sm : 2);
         static int tail_per_sm_cached = 0;
-        if (!tail_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm_cached, k_tail<false>, TAIL_THREADS, 0));
+        if (!tail_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm_cached, k_tail<false, true>, TAIL_THREADS, 0));
         const int grid_tail = sc.sm_count * (tail_per_sm_cached > 0 ? tail_per_sm_cached : 2);
         const char* tail_env = getenv("RBRT_TAIL_RAYS");                  // tuning knob
         // hand-over threshold: brute mode one ray per resident lane of k_finish; BVH mode (asynchronous k_tail) 2^18 rays (swept on C2, C3, C4 at 1 and 8 ranks: scripts/tail_sweep.py)
         const uint32_t tail_rays = (o.flags & RBRT_OPT_NO_TAIL_KERNEL) ? 0u : (tail_env ? (uint32_t)atoi(tail_env) : (o.trace_mode == RBRT_TRACE_BRUTE ? (uint32_t)grid_fin * 256u : (1u << 18)));
         const bool brute = o.trace_mode == RBRT_TRACE_BRUTE;
+        const bool et = sc.dev.n_etris > 0;                               // BasicTriangle elements present: the ET kernel instantiations
         const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
         const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
         size_t ev_used = 0;
@@ -837,7 +846,8 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         for (uint32_t s_base = sh.s0; s_base < sh.s1; s_base += S_b) {
             wp.s_base = s_base; wp.s_count = (sh.s1 - s_base < S_b) ? sh.s1 - s_base : S_b;
             CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
-            k_generate<<<grid, 256, 0, st>>>(wp); ++launches;
+            if (et) k_generate<true><<<grid, 256, 0, st>>>(wp); else k_generate<false><<<grid, 256, 0, st>>>(wp);
+            ++launches;
             batch_iters = 0;
             for (uint32_t it = 0; it <= max_depth; ++it) {
                 if (it >= 1 && tail_rays) {                                // see k_finish / k_tail
@@ -845,8 +855,11 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                     // ~40 launches per batch instead of 155 (an empty iteration still costs three launches).
                     const bool force = it >= TAIL_FORCE_IT;
                     const uint32_t lim = force ? 0xFFFFFFFFu : tail_rays;
-                    if (brute) { if (count) k_finish<true, true><<<grid_fin, 256, 0, st>>>(wp, it, lim); else k_finish<true, false><<<grid_fin, 256, 0, st>>>(wp, it, lim); }
-                    else { if (count) k_tail<true><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); else k_tail<false><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); }
+                    if (brute) {
+                        if (et) { if (count) k_finish<true, true, true><<<grid_fin, 256, 0, st>>>(wp, it, lim); else k_finish<true, false, true><<<grid_fin, 256, 0, st>>>(wp, it, lim); }
+                        else { if (count) k_finish<true, true, false><<<grid_fin, 256, 0, st>>>(wp, it, lim); else k_finish<true, false, false><<<grid_fin, 256, 0, st>>>(wp, it, lim); }
+                    } else if (et) { if (count) k_tail<true, true><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); else k_tail<false, true><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); }
+                    else { if (count) k_tail<true, false><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); else k_tail<false, false><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); }
                     ++launches;
                     if (force) break;
                 }
@@ -856,7 +869,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
                 ++launches; ++iterations; ++batch_iters;
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
-                if (it < max_depth) { k_shade<<<grid, 256, 0, st>>>(wp, it); ++launches; }
+                if (it < max_depth) { if (et) k_shade<true><<<grid, 256, 0, st>>>(wp, it); else k_shade<false><<<grid, 256, 0, st>>>(wp, it); ++launches; }
             }
             k_accumulate<<<(P + 255) / 256, 256, 0, st>>>(wp, d_accum); ++launches;
             k_sum_rays<<<1, 64, 0, st>>>(wp); ++launches;
