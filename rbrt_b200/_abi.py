@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librbrt_gpu.so")
+LIB_PATH = os.environ.get("RBRT_GPU_LIB") or os.path.join(_HERE, "librbrt_gpu.so")   # RBRT_GPU_LIB: an experiment build (csrc/Makefile `variant`)
 
 
 class Vec3C(C.Structure):

@@ -236,8 +236,50 @@ __device__ __forceinline__ void leaf_step(const float4* __restrict__ tris, uint3
     n_tris += count;
 }
 
-// Simple one-lane-one-ray traversal (parity hook, tail kernel); the wavefront trace kernel (render.cu) runs the same
-// two steps in while-while form with dynamic fetch.
+// ONE triangle of the current leaf (warp-voted traversal): test it, then `cur` becomes the rest of the leaf or the popped
+// stack top.  Same arithmetic and the same order of triangles within a leaf as leaf_step.
+__device__ __forceinline__ void leaf_step_one(const float4* __restrict__ tris, uint32_t tri_base, int32_t& cur, f3 o, f3 d, float t_limit,
+                                              float& best_t, uint32_t& best_idx, float& t_prune, const int32_t* stack, int& sp) {
+    const uint32_t code = (uint32_t)(~cur);
+    f3 v0, e1, e2; uint32_t orig; float t;
+    load_tri(tris, tri_base + (code >> 3), v0, e1, e2, orig);
+    if (tri_intersect(v0, e1, e2, o, d, t)) {
+        keep_min(t, orig, best_t, best_idx);
+        t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
+    }
+    cur = (code & 7u) ? (int32_t)~(code + 7u) : stack[--sp];              // {first + 1, count - 1}: +8 on first, -1 on the count field
+}
+
+// Warp-voted traversal (k_trace, k_tail).  The while-while form ("every lane descends to its next leaf, then the leaves
+// are processed together") runs the node loop until the SLOWEST lane has found a leaf: measured 11 of 32 lanes per
+// instruction there.  Here every step is ONE node visit or ONE triangle test, and the warp runs the kind that more of
+// its lanes are waiting for; lanes of the other kind sit the step out, so a step always serves at least half of the
+// lanes that have work.  A lane's own sequence of visits and tests is unchanged, hence so is every result bit.
+// Leaves the loop when fewer than `threshold` lanes still have work (the caller re-fills lanes from the queue).
+#ifndef RBRT_VOTE_N
+#define RBRT_VOTE_N 1      // node step iff  lanes at nodes * RBRT_VOTE_N >= lanes at leaves * RBRT_VOTE_L
+#define RBRT_VOTE_L 1
+#endif
+template <bool COUNT>
+__device__ __forceinline__ void traverse_voted(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t tri_base,
+                                               const RaySlabs& R, f3 o, f3 d, float t_limit, int32_t* stack, int& sp, int32_t& cur,
+                                               float& best_t, uint32_t& best_idx, float& t_prune, int threshold,
+                                               uint32_t& n_nodes, uint32_t& n_tris) {
+    for (;;) {
+        const bool at_node = (uint32_t)cur < (uint32_t)RBRT_SENTINEL, at_leaf = cur < 0;
+        const int nn = __popc(__ballot_sync(0xFFFFFFFFu, at_node)), nl = __popc(__ballot_sync(0xFFFFFFFFu, at_leaf));
+        if (nn + nl < threshold) break;
+        if (nn * RBRT_VOTE_N >= nl * RBRT_VOTE_L) {
+            if (at_node) { cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp); if (COUNT) ++n_nodes; }
+        } else if (at_leaf) {
+            leaf_step_one(tris, tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, stack, sp);
+            if (COUNT) ++n_tris;
+        }
+    }
+}
+
+// Simple one-lane-one-ray traversal (parity hook, brute/finish kernels); the wavefront trace kernel (render.cu) runs the
+// same steps warp-voted with dynamic fetch.
 __device__ __forceinline__ bool mesh_closest_bvh(const SceneDev& S, const MeshDev& M, f3 o, f3 d, float t_limit,
                                                  float& best_t, uint32_t& best_idx, TraceCounters* cnt) {
     best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;                         // min_param init (triangle.rs:398)

@@ -179,7 +179,8 @@ __device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_
 }
 
 #define TRACE_THREADS 128
-#define FETCH_THRESHOLD 20     // re-fill the warp when fewer lanes than this are still traversing
+#define FETCH_THRESHOLD 8      // re-fill the warp when fewer lanes than this are still traversing (WaveParams::fetch_thr; swept 1..24 on C3,
+                               // profiles/r1_summary.md: a re-fill stalls the whole warp on an atomic -> queue -> ray chain, so fewer is better)
 
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32_t it) {   // 8 blocks/SM = 64 registers
@@ -277,8 +278,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32
         }
         uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
         if (active == 0) { if (exhausted) break; continue; }
-        const int threshold = exhausted ? 1 : min(FETCH_THRESHOLD, (int)quota);
-        // ---- while-while traversal: every lane descends to its next leaf, then the leaves are processed together
+        const int threshold = exhausted ? 1 : min((int)P.fetch_thr, (int)quota);
+#ifndef RBRT_WHILE_WHILE
+        // ---- warp-voted traversal: one node visit or one triangle test per step, whichever more lanes wait for (intersect.cuh)
+        traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
+#else
+        // ---- while-while traversal (first form, kept for comparison): every lane descends to its next leaf, then the leaves are processed together
         for (;;) {
             while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node (intersect.cuh)
                 cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp);
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32
             }
             if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
         }
+#endif
     }
     if (COUNT) {
         for (int off = 16; off; off >>= 1) { n_nodes += __shfl_down_sync(FULL_MASK, n_nodes, off); n_tris += __shfl_down_sync(FULL_MASK, n_tris, off); }
@@ -601,8 +607,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         }
         uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
         if (active == 0) { if (exhausted) break; continue; }
-        const int threshold = exhausted ? 1 : min(FETCH_THRESHOLD, (int)quota);
-        // ---- (4) while-while traversal, as k_trace
+        const int threshold = exhausted ? 1 : min((int)P.fetch_thr, (int)quota);
+        // ---- (4) traversal, as k_trace
+#ifndef RBRT_WHILE_WHILE
+        traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
+#else
         for (;;) {
             while ((uint32_t)cur < (uint32_t)SENTINEL) {
                 cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp);
@@ -616,6 +625,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
             }
             if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
         }
+#endif
     }
     for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
     if (lane == 0) {
@@ -816,6 +826,8 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         wp.S = sc.dev; wp.cam = make_cam(cam); wp.sh = sh;
         wp.key0 = (uint32_t)o.seed; wp.key1 = (uint32_t)(o.seed >> 32);
         wp.cap = wb.cap; wp.paths_px = P; wp.max_depth = max_depth;
+        const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
+        wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
         wp.ray_o = wb.ray_o; wp.ray_d = wb.ray_d; wp.candq = wb.candq;
         wp.hit = wb.hit; for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
