@@ -135,7 +135,7 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
     *out = nullptr;
     uint32_t lanes = (opts && opts->simd_lanes) ? opts->simd_lanes : 8;
     if (lanes != 8 && lanes != 4) { set_error("simd_lanes must be 8 (AVX) or 4 (SSE)"); return RBRT_E_INVALID; }
-    uint32_t leaf_size = (opts && opts->leaf_size) ? opts->leaf_size : 4;
+    uint32_t leaf_size = (opts && opts->leaf_size) ? opts->leaf_size : 1;   // swept 1..8 on C3 (profiles/): a triangle test costs a warp step like a node visit, so fewer tests win
     if (leaf_size > 8) { set_error("leaf_size must be <= 8"); return RBRT_E_INVALID; }
     float pad_rel = 2e-5f;
     if (opts && opts->box_pad_rel > 0.0f) pad_rel = opts->box_pad_rel;

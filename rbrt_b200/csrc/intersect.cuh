@@ -122,6 +122,26 @@ __device__ __forceinline__ bool tri_intersect(f3 v0, f3 e1, f3 e2, f3 o, f3 d, f
 // equal the reference's mask algebra has_intersect = !(c1|c2|c3) & c4 (triangle.rs:243-247) for every
 // input, NaN included.
 
+// The same test without early-outs — literally the reference's lane: every quantity is computed, then the four masks
+// are combined (triangle.rs:189-247).  Used by the warp-voted traversal, where the lanes of a step run in lock-step
+// anyway: no divergence, and the three record loads are issued together instead of v0 waiting behind the first cull.
+__device__ __forceinline__ bool tri_intersect_masks(f3 v0, f3 e1, f3 e2, f3 o, f3 d, float& t_out) {
+    f3 h = cross3(d, e2);
+    float a = dot3(e1, h);
+    f3 s = o - v0;
+    float f = XDIV(1.0f, a);                                             // a == 0 -> inf, masked by c1 like the AVX lane
+    float u = XMUL(f, dot3(s, h));
+    f3 q = cross3(s, e1);
+    float v = XMUL(f, dot3(d, q));
+    float t = XMUL(f, dot3(e2, q));
+    const bool c1 = (-RBRT_MIN_DIST < a) & (a < RBRT_MIN_DIST);
+    const bool c2 = (u < 0.0f) | (u > 1.0f);
+    const bool c3 = (v < 0.0f) | (XADD(u, v) > 1.0f);
+    const bool c4 = (t > RBRT_MIN_DIST) & (t < RBRT_T_CAP);
+    t_out = t;
+    return !(c1 | c2 | c3) & c4;
+}
+
 __device__ __forceinline__ void load_tri(const float4* __restrict__ tris, uint32_t i, f3& v0, f3& e1, f3& e2, uint32_t& orig) {
     float4 a = __ldg(tris + 3 * (size_t)i), b = __ldg(tris + 3 * (size_t)i + 1), c = __ldg(tris + 3 * (size_t)i + 2);
     v0 = mk3(a.x, a.y, a.z); e1 = mk3(b.x, b.y, b.z); e2 = mk3(c.x, c.y, c.z);
@@ -243,7 +263,7 @@ __device__ __forceinline__ void leaf_step_one(const float4* __restrict__ tris, u
     const uint32_t code = (uint32_t)(~cur);
     f3 v0, e1, e2; uint32_t orig; float t;
     load_tri(tris, tri_base + (code >> 3), v0, e1, e2, orig);
-    if (tri_intersect(v0, e1, e2, o, d, t)) {
+    if (tri_intersect_masks(v0, e1, e2, o, d, t)) {
         keep_min(t, orig, best_t, best_idx);
         t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
     }
