@@ -10,7 +10,10 @@ path) — the reference's `render_scene(cam, spp, scene)` (lib.rs:75-124).  Rays
 (`Scene::hit` calls, primary + bounces), counted on the device.
 
   value      whole-job Mrays/s with the scene (SoA buffers + LBVH) already resident in HBM; the timed region is
-             render -> [NCCL reduce to rank 0] -> finalize (1/spp, sqrt, x256, saturating u8) on the device.
+             K x (render -> [NCCL reduce to rank 0] -> finalize (1/spp, sqrt, x256, saturating u8) on the device), with
+             --frames-in-flight frames (default 2) in flight on their own streams (rbrt_b200.FramePipeline): the sparse,
+             latency-bound last bounces of one frame overlap the dense first bounces of the next.  `single_frame` is the
+             same measurement one frame at a time.  The last pipelined image is checked against the single-frame one.
   e2e        the same metric through the reference-facing call with HOST buffers: every step uploads the
              triangle soup from pinned host memory (rbrt_gpu_scene_create: H2D + LBVH build), renders
              (rbrt_gpu_render / the multi-rank building blocks) and copies the RGB8 image back to the host.
@@ -332,77 +335,106 @@ def run_gpu(args):
     barrier()
     counts = cst.as_dict()
 
-    # ---- resident arm
+    # ---- single-frame pass: one frame at a time (host waits for each), every trace launch bracketed by CUDA events.
+    #      Gives the per-frame counters (identical every frame: fixed seed), the un-overlapped kernel times the roofline
+    #      is computed from, and the reference image the pipelined frames are checked against.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
+    for _ in range(max(args.warmup, 3)):
+        step_resident(scene.handle(), dict(time_kernels=True), _abi.StatsC())
+    barrier()
+    n_single = 3
+    e0.record(stream)
+    for _ in range(n_single):
+        st = _abi.StatsC()
+        step_resident(scene.handle(), dict(time_kernels=True), st)
+        stats.append(st.as_dict())
+    e1.record(stream)
+    barrier()
+    ms_single = e0.elapsed_time(e1) / n_single
+    rgb_ref = rgb.clone() if rank == 0 else None
+    frame = stats[-1]
+    assert all(s_["rays"] == frame["rays"] and s_["paths"] == frame["paths"] for s_ in stats), "frames of one seed differ"
+
+    # ---- resident arm (timed region): `steps` frames through the FramePipeline, `frames_in_flight` of them in flight on
+    #      their own streams and wavefront pools, so the sparse last bounces of one frame overlap the next frame's first
+    pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode)
     with ClockSampler(local) as clk:
         time.sleep(0.3)                                       # let nvidia-smi deliver its first samples
         for _ in range(max(args.warmup, 3)):
-            step_resident(scene.handle(), dict(time_kernels=True), _abi.StatsC())
+            pipe.submit(cam_c, spp, scene.handle(), seed=SEED)
+        pipe.drain()
         barrier()
         clk.mark_begin()
         e0.record(stream)
         for _ in range(args.steps):
-            st = _abi.StatsC()
-            step_resident(scene.handle(), dict(time_kernels=True), st)
-            stats.append(st.as_dict())
+            pipe.submit(cam_c, spp, scene.handle(), seed=SEED)
+        pipe.wait_on(stream)
         e1.record(stream)
         barrier()
         clk.mark_end()
+    last = pipe.drain()[-1][0]
+    if rank == 0:
+        assert torch.equal(last, rgb_ref), "pipelined frame differs from the single-frame render"
     ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([sum(s["rays"] for s in stats), sum(s["paths"] for s in stats), sum(s["launches"] for s in stats) + (args.steps if rank == 0 else 0),
+    t = torch.tensor([ms, ms_single], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([frame["rays"] * args.steps, frame["paths"] * args.steps, (frame["launches"] + (1 if rank == 0 else 0)) * args.steps,
                         counts["node_visits"] - counts["tail_node_visits"], counts["tri_tests"] - counts["tail_tri_tests"], counts["rays"],
                         counts["traversed_rays"] - counts["tail_traversed_rays"]], dtype=torch.float64, device="cuda")
-    trace_ms = torch.tensor([sum(s["ms_trace"] for s in stats)], dtype=torch.float64, device="cuda")
+    trace_ms = torch.tensor([sum(s_["ms_trace"] for s_ in stats) / n_single * args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         dist.all_reduce(trace_ms, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, ms_single = (float(x) for x in t.tolist())
     rays, paths, launches, V, T, Rc, Cc = (float(x) for x in agg.tolist())
     trace_ms = float(trace_ms.item())
     clocks = clk.summary()
 
     # ---- e2e arm: host buffers in, host image out, every step (scene upload + LBVH build inside the timed region)
     pinned, keep = pin_meshes(meshes)
-    host_rgb = torch.empty(H * W * 3, dtype=torch.uint8, pin_memory=True)
     h2d = sum(t.nbytes for t in pinned) + 36 * len(spheres) + 20 * (len(spheres) + len(meshes)) + 64
     d2h = H * W * 3
+
+    pipe_e = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=True, shard_mode=shard_mode)
+    e2e_last = [None]
+
+    def retire(fin):
+        if fin is not None:
+            img, old_scene = fin
+            old_scene.close()
+            e2e_last[0] = img
 
     def step_e2e():
         t_a = time.perf_counter()
         sc = make_scene(spheres, meshes, pinned)
-        try:
-            h = sc.handle()                                   # rbrt_gpu_scene_create: H2D of the triangle soup + LBVH build
-            t_b = time.perf_counter()
-            st = _abi.StatsC()
-            if world == 1:
-                out = np.frombuffer(host_rgb.numpy(), np.uint8)
-                _abi.check(lib.rbrt_gpu_render(h, cam_c, spp, make_opts(seed=SEED), out.ctypes.data, st))
-            else:
-                step_resident(h, {}, st)
-                if rank == 0:
-                    host_rgb.copy_(rgb, non_blocking=False)
-            t_c = time.perf_counter()
-            return st.rays, (t_b - t_a) * 1e3, (t_c - t_b) * 1e3
-        finally:
-            sc.close()
+        sc.handle()                                           # rbrt_gpu_scene_create: H2D of the triangle soup + LBVH build
+        t_b = time.perf_counter()
+        # render -> [reduce] -> finalize -> RGB8 image to pinned host memory, enqueued on the frame's stream; the image of
+        # the frame submitted `frames_in_flight` steps ago is collected (host buffer ready) and its scene destroyed
+        retire(pipe_e.submit(cam_c, spp, sc, tag=sc, seed=SEED))
+        t_c = time.perf_counter()
+        return (t_b - t_a) * 1e3, (t_c - t_b) * 1e3
 
-    for _ in range(2):
+    for _ in range(max(2, args.frames_in_flight + 1)):
         step_e2e()
+    for fin in pipe_e.drain():
+        retire(fin)
     barrier()
     e_steps = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     e0.record(stream)
-    e_rays = 0
     for _ in range(e_steps):
-        r_, ms_create, ms_render = step_e2e()
-        e_rays += r_
-        print(f"[e2e rank {rank}] scene_create {ms_create:.1f} ms, render+readback {ms_render:.1f} ms", file=sys.stderr)
+        ms_create, ms_render = step_e2e()
+        print(f"[e2e rank {rank}] scene_create {ms_create:.1f} ms, submit (+ wait for the frame {args.frames_in_flight} steps back) {ms_render:.1f} ms", file=sys.stderr)
+    for fin in pipe_e.drain():                                # every image of the timed steps is on the host when the clock stops
+        retire(fin)
     e1.record(stream)
     barrier()
     e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # host-side work (malloc, sync copies) counts too
+    if rank == 0:
+        assert np.array_equal(e2e_last[0].pixels.reshape(-1), rgb_ref.cpu().numpy()), "e2e image differs from the single-frame render"
+    e_rays = frame["rays"] * e_steps
     te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
     re = torch.tensor([float(e_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -430,21 +462,26 @@ def run_gpu(args):
         "metric": "Mrays/s", "value": rays / (ms / 1e3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, spheres, meshes, world),
+        "config": dict(workload_config(args.workload, spheres, meshes, world), frames_in_flight=args.frames_in_flight),
+        "single_frame": {"ms_per_step": ms_single, "value": rays / args.steps / (ms_single / 1e3) / 1e6, "unit": "Mrays/s",
+                         "note": "one frame at a time, host waits for each (latency of a lone render_scene call); `value` keeps "
+                                 "`frames_in_flight` frames in flight on separate streams"},
         "samples_per_s": paths / (ms / 1e3), "rays_per_step": rays / args.steps, "rays_per_sample": rays / max(paths, 1),
         "clocks": clocks,
         "e2e": {"value": e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-                "ms_per_step": float(te.item()) / e_steps, "includes": "scene upload from pinned host memory + LBVH build + render + RGB8 image to host, per step"},
+                "ms_per_step": float(te.item()) / e_steps, "includes": "scene upload from pinned host memory + LBVH build + render + RGB8 image to pinned host memory, per step; "
+                            "frames_in_flight frames overlap (FramePipeline), all images on the host when the clock stops"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_trace (stage B: persistent LBVH traversal with dynamic fetch + Moeller-Trumbore tests)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_traversed_ray": bytes_step / max(Cc, 1),
                      "traversed_rays_per_step": Cc, "traversed_share_of_rays": Cc / max(Rc, 1),
                      "node_visits_per_traversed_ray": V / max(Cc, 1), "tri_tests_per_traversed_ray": T / max(Cc, 1),
-                     "trace_ms_per_step": trace_ms_step, "trace_share_of_step": trace_ms_step / (ms / args.steps),
+                     "trace_ms_per_step": trace_ms_step, "trace_share_of_step": trace_ms_step / ms_single,
                      "fp32_achieved_tflops": flops_step / max(world, 1) / (trace_ms_step / 1e3) / 1e12 if trace_ms_step > 0 else None,
                      "note": "achieved = per-GPU algorithmic bytes of all trace launches of a step / their summed CUDA-event time (per-launch "
-                             "average x launches); nodes+triangles mostly hit in L2, so this is requested bandwidth against the HBM copy peak"},
+                             "average x launches), events taken in this run's single-frame pass (frames of the timed region overlap, which "
+                             "would smear per-kernel times); nodes+triangles mostly hit in L2, so this is requested bandwidth against the HBM copy peak"},
         "scene": {"bvh_nodes": info["num_bvh_nodes"], "device_bytes": info["device_bytes"], "ms_upload": info["ms_upload"], "ms_build": info["ms_build"]},
     }
     if world == 1 and not args.no_cpu:
@@ -469,6 +506,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="frames kept in flight on separate streams in the timed region (1 = one frame at a time)")
     args = ap.parse_args()
     # exactly ONE line goes to stdout (the JSON); the host mirror's progress prints (lib.rs:80,114, mesh.rs:115) go to stderr
     # (NCCL and the host mirror also write to fd 1 from C: redirect the descriptor itself, keep a private duplicate for the JSON)

@@ -106,7 +106,12 @@ enum { RBRT_TRACE_BVH = 0, RBRT_TRACE_BRUTE = 1 };
 enum {
     RBRT_OPT_COUNT_VISITS = 1,   /* fill rbrt_stats.node_visits / tri_tests (instrumented kernels, slower) */
     RBRT_OPT_TIME_KERNELS = 2,   /* bracket every trace launch with CUDA events -> rbrt_stats.ms_trace */
-    RBRT_OPT_NO_TAIL_KERNEL = 4  /* run all 51 bounce iterations as wavefront launches (no single-launch tail) */
+    RBRT_OPT_NO_TAIL_KERNEL = 4, /* run all 51 bounce iterations as wavefront launches (no single-launch tail) */
+    RBRT_OPT_POOL_SHIFT = 3,     /* bits 3-4: which of the device's FOUR pools of wavefront state the call uses (0 = default), so that
+                                    up to four renders can be in flight on four streams (rbrt_gpu_render_accum_device with
+                                    stats = NULL returns without synchronising): the sparse last bounces of one frame then
+                                    overlap the dense first bounces of the next */
+    RBRT_OPT_POOL_MASK = 24
 };
 
 typedef struct rbrt_scene_opts {

@@ -14,6 +14,7 @@ from .blueprints import (CameraBluePrint, SceneBlueprint, SphereBlueprint, Trian
 from .cam import Camera
 from .materials import Dielectric, Lambertian, Metal
 from .mesh import TriangleMesh, load_mesh_vertices_from_file
+from .pipeline import FramePipeline
 from .render import ImageBuffer, primary_rays, render_scene, render_scene_hdr
 from .scene import Scene
 from .sphere import Sphere

@@ -89,7 +89,7 @@ HIT_DTYPE = [("kind", "<i4"), ("elem_idx", "<u4"), ("tri_idx", "<u4"), ("t", "<f
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE = 0, 1
-OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL = 1, 2, 4
+OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL, OPT_POOL_SHIFT = 1, 2, 4, 3
 HIT_NONE, HIT_SPHERE, HIT_MESH, HIT_TRIANGLE = -1, 0, 1, 2
 ELEM_SPHERE, ELEM_TRIANGLE = 0, 1
 E_INVALID, E_CUDA, E_NODEVICE = 1, 2, 3

@@ -259,7 +259,7 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
         tri_off += n_eff;
     }
     if (nm) CKSC(cudaMemcpy(d_meshes, sc->meshes_h.data(), sizeof(MeshDev) * nm, cudaMemcpyHostToDevice));
-    CKSC(cudaDeviceSynchronize());
+    CKSC(cudaStreamSynchronize(0));                                       // upload + build ran on the default stream; renders in flight on other (non-blocking) streams are not waited for
     sc->dev.etris = d_etris; sc->dev.elem_kind = d_ekind; sc->dev.n_etris = (uint32_t)(etris.size() / 4);
     sc->dev.spheres = d_sph; sc->dev.tris = d_tris; sc->dev.nodes = d_nodes; sc->dev.normals = d_normals;
     sc->dev.mat = d_mat; sc->dev.mat_kind = d_kind; sc->dev.meshes = d_meshes; sc->dev.n_spheres = ns; sc->dev.n_meshes = nm;

@@ -82,7 +82,7 @@ int primary_rays_device(const rbrt_camera& cam, uint64_t seed, uint32_t sample, 
 void free_wave_buffers(WaveBuffers& wb);
 // Per-device pool of wavefront state, shared by every scene of the process and kept between renders (allocating and
 // freeing tens of GB per render would cost more than the render).  The library is single-threaded per device.
-WaveBuffers& device_wave_buffers(int device);
+WaveBuffers& device_wave_buffers(int device, int pool = 0);
 void release_device_wave_buffers();
 
 }  // namespace rbrt

@@ -739,11 +739,12 @@ static CamDev make_cam(const rbrt_camera& c) {
     return d;
 }
 
-static WaveBuffers g_wave[64];
-WaveBuffers& device_wave_buffers(int device) { return g_wave[(device >= 0 && device < 64) ? device : 0]; }
+static WaveBuffers g_wave[4][64];                                       // [pool][device]; pools 1..3 = RBRT_OPT_POOL_* (more frames in flight)
+WaveBuffers& device_wave_buffers(int device, int pool) { return g_wave[pool & 3][(device >= 0 && device < 64) ? device : 0]; }
 void release_device_wave_buffers() {
     int cur = 0; cudaGetDevice(&cur);
-    for (int d = 0; d < 64; ++d) if (g_wave[d].cap || g_wave[d].accum || g_wave[d].rgb) { cudaSetDevice(d); free_wave_buffers(g_wave[d]); }
+    for (int p = 0; p < 4; ++p)
+        for (int d = 0; d < 64; ++d) if (g_wave[p][d].cap || g_wave[p][d].accum || g_wave[p][d].rgb) { cudaSetDevice(d); free_wave_buffers(g_wave[p][d]); }
     cudaSetDevice(cur);
 }
 
@@ -805,7 +806,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     CKR(cudaEventCreate(&ev0)); CKR(cudaEventCreate(&ev1));
     CKR(cudaMemsetAsync(d_accum, 0, 16ull * W * H, st));
     uint32_t launches = 0, iterations = 0, batch_iters = 0;
-    WaveBuffers& wb = device_wave_buffers(sc.device);
+    WaveBuffers& wb = device_wave_buffers(sc.device, (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT));
     CKR(cudaEventRecord(ev0, st));
     if (P && sh.s1 > sh.s0) {
         // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is

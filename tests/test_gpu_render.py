@@ -71,6 +71,39 @@ def test_mesh_scene_and_batching(gpu, oracle):
         assert_images_equal(R.render_scene_hdr(cam, 6, scene, seed=9, **kw), ref, f"opts {kw}")
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+def test_frame_pipeline_is_bit_identical(gpu, depth):
+    """FramePipeline: frames in flight on separate streams and wavefront pools (RBRT_OPT_POOL_*) give the same images
+    as lone render_scene calls — different seeds, two scenes, host (pinned) and device outputs, tile-shard options."""
+    import torch
+    cam = S.example_camera(96, 64)
+    scenes = [S.small_mesh_scene(3), S.spheres_scene()]
+    jobs = [(scenes[k % 2], 5, 100 + k) for k in range(7)]
+    want = [R.render_scene(cam, spp, sc, seed=seed).pixels for sc, spp, seed in jobs]
+    pipe = R.FramePipeline(96, 64, depth=depth)
+    got = []
+    for k, (sc, spp, seed) in enumerate(jobs):
+        fin = pipe.submit(cam, spp, sc, tag=k, seed=seed)
+        assert (fin is None) == (k < depth)
+        if fin is not None:
+            got.append(fin)
+    got += pipe.drain()
+    assert [t for _, t in got] == list(range(7))
+    for (img, t), w in zip(got, want):
+        assert np.array_equal(img.pixels, w), f"frame {t} differs"
+    # device output + HDR + an explicit tile shard
+    hdr = R.render_scene_hdr(cam, 4, scenes[0], seed=3, shard_mode=_abi.SHARD_TILES, shard_rank=1, shard_count=3)
+    pipe = R.FramePipeline(96, 64, depth=depth, host_output=False, hdr=True)
+    for _ in range(depth + 1):
+        pipe.submit(cam, 4, scenes[0], seed=3, shard_mode=_abi.SHARD_TILES, shard_rank=1, shard_count=3)
+    for img, _ in pipe.drain():
+        assert np.array_equal(img.cpu().numpy().reshape(64, 96, 3), hdr)
+    with pytest.raises(ValueError):
+        R.FramePipeline(8, 8, depth=5)
+    with pytest.raises(ValueError):
+        pipe.submit(S.example_camera(8, 8), 1, scenes[1])
+
+
 def test_depth_budget(gpu, oracle):  # lib.rs:54-66,99
     sc = R.Scene()
     tris = np.array([((-50, -50, -5), (50, -50, -5), (0, 50, -5))] * 8 + [((-50, -50, 5), (0, 50, 5), (50, -50, 5))] * 8, np.float32)
