@@ -182,8 +182,11 @@ __device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_
 #define FETCH_THRESHOLD 8      // re-fill the warp when fewer lanes than this are still traversing (WaveParams::fetch_thr; swept 1..24 on C3,
                                // profiles/r1_summary.md: a re-fill stalls the whole warp on an atomic -> queue -> ray chain, so fewer is better)
 
+#ifndef TRACE_BLOCKS
+#define TRACE_BLOCKS 8         // resident blocks per SM: 8 x 128 threads = 64 registers per thread
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(TRACE_THREADS, 8) k_trace(WaveParams P, uint32_t it) {   // 8 blocks/SM = 64 registers
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n = c->cand_count;
     if (n == 0 || P.ctr[0].pad) return;
