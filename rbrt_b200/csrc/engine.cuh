@@ -25,14 +25,14 @@ enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_CAND = 4, ST_TAIL_
 struct WaveBuffers {
     uint32_t cap = 0;            // paths per batch the buffers hold
     uint32_t depth_cap = 0;      // bounce iterations the history/counter arrays hold
-    float4* ray_o = nullptr;     // [pid] {origin.xyz, -}
-    float4* ray_d = nullptr;     // [pid] {direction.xyz, -}
-    uint4* hit = nullptr;        // [pid] sphere pre-result for queued candidates, final hit for queued shading work
+    uint4* rec = nullptr;        // [pid] ONE 64-byte record per path = two 32-byte DRAM sectors (render.cu, "path record"):
+                                 //   hit (16 B: sphere pre-result for queued candidates, final hit for queued shading work),
+                                 //   ray origin + direction (24 B), the first 12 entries of the scatter history (24 B)
     uint32_t* candq = nullptr;   // pids queued for BVH traversal
     uint32_t* matq[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // pids queued for shading, by iteration parity and material kind
                                  // (k_shade(it) reads parity it&1 while it fills parity (it+1)&1)
     float4* out = nullptr;       // [pid] final radiance of the path (written exactly once, when the path ends)
-    uint16_t* hist = nullptr;    // [iteration][pid]: element scattered at, for the attenuation product
+    uint16_t* hist = nullptr;    // [iteration - 12][pid]: element scattered at (attenuation product), iterations >= 12 (the first 12 live in rec)
     IterCtr* ctr = nullptr;      // [depth_cap + 2]
     unsigned long long* stats = nullptr;   // ST_COUNT counters
     float4* accum = nullptr;     // internal W*H accumulation buffer for the host-pointer entry points
@@ -64,8 +64,8 @@ struct WaveParams {
     uint32_t s_count;        // samples in this batch
     uint32_t max_depth;      // 50 (lib.rs:99)
     uint32_t fetch_thr;      // k_trace / k_tail re-fill a warp from the queue when fewer lanes than this still traverse
-    float4* ray_o; float4* ray_d;
-    uint4* hit; uint32_t* candq; uint32_t* matq[2][3];
+    uint4* rec;
+    uint32_t* candq; uint32_t* matq[2][3];
     float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;
 };
 

@@ -81,10 +81,39 @@ __device__ __forceinline__ void flush(const WaveParams& P, uint32_t it, const De
     }
 }
 
+// ------------------------------------------------------------------ path record
+// Everything a path's queued ray needs sits in ONE 64-byte, 64-byte-aligned record = two 32-byte DRAM sectors:
+//   bytes  0..15  hit      uint4  (stage A's sphere pre-result for traversal candidates; the final hit for shading work)
+//   bytes 16..39  ray      origin.xyz, direction.xyz
+//   bytes 40..63  history  u16[12]: element scattered at in bounce iterations 0..11 (later ones: WaveParams::hist)
+// The bounce iterations' shade launches are bound by random 32-byte sector traffic to DRAM (3.3 TB/s of sectors at it 1,
+// more resident warps or prefetching only made them slower): with separate ray_o / ray_d / hit / history arrays an item
+// touched five sectors and used half of each, now it touches these two and uses all of them.
+#define REC_HIST 12
+__device__ __forceinline__ uint4* rec_ptr(const WaveParams& P, uint32_t pid) { return P.rec + 4 * (size_t)pid; }
+__device__ __forceinline__ uint4 load_hit(const WaveParams& P, uint32_t pid) { return rec_ptr(P, pid)[0]; }
+__device__ __forceinline__ void store_hit(const WaveParams& P, uint32_t pid, uint4 h) { rec_ptr(P, pid)[0] = h; }
+__device__ __forceinline__ void load_ray(const WaveParams& P, uint32_t pid, f3& o, f3& d) {
+    const float4 a = reinterpret_cast<const float4*>(rec_ptr(P, pid))[1];
+    const float2 b = reinterpret_cast<const float2*>(rec_ptr(P, pid))[4];
+    o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
+}
+__device__ __forceinline__ void store_ray(const WaveParams& P, uint32_t pid, f3 o, f3 d) {
+    reinterpret_cast<float4*>(rec_ptr(P, pid))[1] = make_float4(o.x, o.y, o.z, d.x);
+    reinterpret_cast<float2*>(rec_ptr(P, pid))[4] = make_float2(d.y, d.z);
+}
+__device__ __forceinline__ uint32_t load_hist(const WaveParams& P, uint32_t pid, uint32_t k) {
+    return k < REC_HIST ? reinterpret_cast<const uint16_t*>(rec_ptr(P, pid))[20 + k] : P.hist[(size_t)(k - REC_HIST) * P.cap + pid];
+}
+__device__ __forceinline__ void store_hist(const WaveParams& P, uint32_t pid, uint32_t k, uint32_t elem) {
+    if (k < REC_HIST) reinterpret_cast<uint16_t*>(rec_ptr(P, pid))[20 + k] = (uint16_t)elem;
+    else P.hist[(size_t)(k - REC_HIST) * P.cap + pid] = (uint16_t)elem;
+}
+
 // att_1 * (att_2 * (... * leaf)): the recursion of lib.rs:62 unwinds innermost first
 __device__ __forceinline__ f3 unwind(const WaveParams& P, f3 col, uint32_t n_scatters, uint32_t pid) {
     for (int k = (int)n_scatters - 1; k >= 0; --k) {
-        uint32_t e = P.hist[(size_t)k * P.cap + pid];
+        uint32_t e = load_hist(P, pid, (uint32_t)k);
         float4 m = __ldg(P.S.mat + e);
         f3 att = __ldg(P.S.mat_kind + e) == 2u ? mk3(1.0f, 1.0f, 1.0f) : mk3(m.x, m.y, m.z);
         col = att * col;
@@ -110,16 +139,14 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
     for (uint32_t mi = 0; mi < P.S.n_meshes; ++mi) {                     // whole-mesh AABB pre-test (mesh.rs:233)
         const MeshDev& M = P.S.meshes[mi];
         if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
-        P.ray_o[pid] = make_float4(o.x, o.y, o.z, 0.0f);
-        P.ray_d[pid] = make_float4(d.x, d.y, d.z, 0.0f);
-        P.hit[pid] = make_uint4(__float_as_uint(t_s), elem, __float_as_uint(closest), (mi << 8) | (uint32_t)(kind & 0xFF));
+        store_ray(P, pid, o, d);
+        store_hit(P, pid, make_uint4(__float_as_uint(t_s), elem, __float_as_uint(closest), (mi << 8) | (uint32_t)(kind & 0xFF)));
         return CLS_CAND;
     }
     if (kind == 0) {
         if (it < P.max_depth) {                                           // depth > 0: scatter() will run (lib.rs:54)
-            P.ray_o[pid] = make_float4(o.x, o.y, o.z, 0.0f);
-            P.ray_d[pid] = make_float4(d.x, d.y, d.z, 0.0f);
-            P.hit[pid] = make_uint4(__float_as_uint(t_s), elem, 0u, 0u);
+            store_ray(P, pid, o, d);
+            store_hit(P, pid, make_uint4(__float_as_uint(t_s), elem, 0u, 0u));
             return __ldg(P.S.mat_kind + elem);
         }
         end_path(P, pid, mk3(0, 0, 0));                                   // depth exhausted -> black (lib.rs:63-66)
@@ -168,7 +195,7 @@ __device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_
     if (kind >= 0) {
         if (it < P.max_depth) {
             uint32_t e = kind == 0 ? elem : P.S.n_spheres + elem;
-            P.hit[pid] = make_uint4(__float_as_uint(t), e, tri, (uint32_t)kind);
+            store_hit(P, pid, make_uint4(__float_as_uint(t), e, tri, (uint32_t)kind));
             return (int)__ldg(P.S.mat_kind + e);
         }
         end_path(P, pid, mk3(0, 0, 0));
@@ -267,9 +294,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
                     uint32_t qi = base + __popc(m & lt);
                     if (qi < n) {
                         pid = P.candq[qi];
-                        float4 a = P.ray_o[pid], b = P.ray_d[pid];
-                        uint4 h = P.hit[pid];
-                        o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
+                        uint4 h = load_hit(P, pid);
+                        load_ray(P, pid, o, d);
                         bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
                         bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
                         has_ray = true;
@@ -313,9 +339,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
 // material kind to shade, or -1 when the path ended.
 template <bool BRUTE>
 __device__ __forceinline__ int process_candidate(const WaveParams& P, uint32_t it, uint32_t pid, TraceCounters* cnt) {
-    float4 a = P.ray_o[pid], b = P.ray_d[pid];
-    uint4 h = P.hit[pid];
-    f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+    uint4 h = load_hit(P, pid);
+    f3 o, d; load_ray(P, pid, o, d);
     float bt = __uint_as_float(h.x), closest = __uint_as_float(h.z);
     uint32_t belem = h.y, btri = 0; int bkind = (h.w & 0xFFu) == 0u ? 0 : -1;
     for (uint32_t mi = h.w >> 8; mi < P.S.n_meshes; ++mi) {
@@ -369,9 +394,8 @@ __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) 
 template <bool ET>
 __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid, RngKey key,
                                                uint32_t& rays, uint32_t& nan_count) {
-    float4 a = P.ray_o[pid], b = P.ray_d[pid];
-    uint4 h = P.hit[pid];
-    f3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+    uint4 h = load_hit(P, pid);
+    f3 o, d; load_ray(P, pid, o, d);
     float t = __uint_as_float(h.x);
     uint32_t elem = h.y;
     f3 point = o + t * d;                                                 // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
@@ -392,13 +416,16 @@ __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it,
     bool cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam.width + col,
                         P.s_base + s_local, it + 1, out_d);
     if (!cont) { end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }       // absorbed (metal.rs:24) -> black
-    P.hist[(size_t)it * P.cap + pid] = (uint16_t)elem;
+    store_hist(P, pid, it, elem);
     ++rays;
     return stage_a<ET>(P, it + 1, pid, point, out_d, nan_count);
 }
 
+#ifndef SHADE_BLOCKS
+#define SHADE_BLOCKS 4
+#endif
 template <bool ET>
-__global__ void __launch_bounds__(256) k_shade(WaveParams P, uint32_t it) {
+__global__ void __launch_bounds__(256, SHADE_BLOCKS) k_shade(WaveParams P, uint32_t it) {
     IterCtr* c = P.ctr + it;
     const uint32_t n0 = c->mat_count[0], n1 = c->mat_count[1], n2 = c->mat_count[2];
     // virtual index space: each material's run is padded to a multiple of 32 so a warp round never mixes kinds
@@ -557,9 +584,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
     };
     auto load_candidate = [&]() {                                         // the ray stage A queued for this path
-        float4 a = P.ray_o[pid], b = P.ray_d[pid];
-        uint4 h = P.hit[pid];
-        o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
+        uint4 h = load_hit(P, pid);
+        load_ray(P, pid, o, d);
         bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
         bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
         has_ray = true;
@@ -752,8 +778,8 @@ void release_device_wave_buffers() {
 }
 
 void free_wave_buffers(WaveBuffers& wb) {
-    cudaFree(wb.ray_o); cudaFree(wb.ray_d); cudaFree(wb.candq);
-    cudaFree(wb.hit); for (int i = 0; i < 6; ++i) cudaFree(wb.matq[i / 3][i % 3]);
+    cudaFree(wb.rec); cudaFree(wb.candq);
+    for (int i = 0; i < 6; ++i) cudaFree(wb.matq[i / 3][i % 3]);
     cudaFree(wb.out); cudaFree(wb.hist); cudaFree(wb.ctr); cudaFree(wb.stats); cudaFree(wb.accum);
     cudaFree(wb.rgb); cudaFree(wb.hdr);
     for (cudaEvent_t e : wb.ev) cudaEventDestroy(e);
@@ -770,12 +796,11 @@ static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
     free_wave_buffers(wb);
     wb.accum = accum; wb.accum_px = accum_px; wb.rgb = rgb; wb.hdr = hdr; wb.out_px = out_px; wb.ev.swap(ev);
     size_t b = 0;
-    CKR(cudaMalloc(&wb.ray_o, 16ull * cap)); CKR(cudaMalloc(&wb.ray_d, 16ull * cap)); b += 32ull * cap;
+    CKR(cudaMalloc(&wb.rec, 64ull * cap)); b += 64ull * cap;
     CKR(cudaMalloc(&wb.candq, 4ull * cap)); b += 4ull * cap;
-    CKR(cudaMalloc(&wb.hit, 16ull * cap)); b += 16ull * cap;
     for (int i = 0; i < 6; ++i) { CKR(cudaMalloc(&wb.matq[i / 3][i % 3], 4ull * cap)); b += 4ull * cap; }
     CKR(cudaMalloc(&wb.out, 16ull * cap)); b += 16ull * cap;
-    CKR(cudaMalloc(&wb.hist, 2ull * cap * depth)); b += 2ull * cap * depth;
+    { const uint64_t rows = depth > REC_HIST ? depth - REC_HIST : 1; CKR(cudaMalloc(&wb.hist, 2ull * cap * rows)); b += 2ull * cap * rows; }
     CKR(cudaMalloc(&wb.ctr, sizeof(IterCtr) * (depth + 2)));
     CKR(cudaMalloc(&wb.stats, 8 * ST_COUNT));
     wb.cap = cap; wb.depth_cap = depth; wb.bytes = b;
@@ -818,7 +843,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         // (92 + 2*max_depth bytes of wavefront state each: 25.8 GB at depth 50) and at most half of the free HBM.
         uint32_t target = o.batch_paths;
         if (!target) {
-            const uint64_t per_path = 92ull + 2ull * max_depth;
+            const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
             const uint64_t want = std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * P, 1ull << 27);
             const uint64_t want_sb = std::max<uint64_t>(want / P, 1);                       // whole samples per batch
             if (wb.cap >= want_sb * P && wb.depth_cap >= max_depth) target = (uint32_t)want;   // the pool already holds it: no driver query
@@ -843,8 +868,8 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         wp.cap = wb.cap; wp.paths_px = P; wp.max_depth = max_depth;
         const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
         wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
-        wp.ray_o = wb.ray_o; wp.ray_d = wb.ray_d; wp.candq = wb.candq;
-        wp.hit = wb.hit; for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
+        wp.rec = wb.rec; wp.candq = wb.candq;
+        for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
         const int grid = sc.sm_count * 8;                                  // producers / brute: 256-thread blocks
         int per_sm = 0;                                                   // k_trace: persistent blocks, exactly one resident wave
