@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
     bool has_ray = false;
     uint32_t pid = 0, mi = 0;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
-    RaySlabs R = {0, 0, 0, 0, 0, 0, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_LO};
+    RaySlabs R = {0, 0, 0, 0, 0, 0, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_HI, RBRT_SEL_HI, RBRT_SEL_HI};
     float closest = 0.0f, bt = 0.0f; int bkind = -1; uint32_t belem = 0, btri = 0;   // best over spheres + finished meshes
     // ---- traversal state of the current mesh
     int32_t cur = SENTINEL; int sp = 0;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
     bool has_ray = false;
     uint32_t mi = 0;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
-    RaySlabs R = {0, 0, 0, 0, 0, 0, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_LO};
+    RaySlabs R = {0, 0, 0, 0, 0, 0, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_LO, RBRT_SEL_HI, RBRT_SEL_HI, RBRT_SEL_HI};
     float closest = 0.0f, bt = 0.0f; int bkind = -1; uint32_t belem = 0, btri = 0;
     int32_t cur = SENTINEL; int sp = 0;
     float best_t = 0.0f, t_prune = 0.0f, t_limit = 0.0f; uint32_t best_idx = 0xFFFFFFFFu;
