@@ -223,8 +223,8 @@ __device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const
     RBRT_CHILD(0, w0.x, w0.y, w0.z) RBRT_CHILD(1, w0.w, w1.x, w1.y) RBRT_CHILD(2, w1.z, w1.w, w2.x) RBRT_CHILD(3, w2.y, w2.z, w2.w)
 #undef RBRT_CHILD
     r[0] = (int32_t)w3.x; r[1] = (int32_t)w3.y; r[2] = (int32_t)w3.z; r[3] = (int32_t)w3.w;
-#ifndef RBRT_NEAREST_ONLY
-    // sort the four (entry distance, ref) pairs ascending; misses end up last
+#ifdef RBRT_FULL_SORT
+    // sort the four (entry distance, ref) pairs ascending; misses end up last (measured 1-3 % slower than nearest-only on C2/C3/C4)
 #define RBRT_CSWAP(a, b) { const bool sw = t[b] < t[a]; const float tl = fminf(t[a], t[b]), th = fmaxf(t[a], t[b]); \
         const int32_t ra = sw ? r[b] : r[a], rb = sw ? r[a] : r[b]; t[a] = tl; t[b] = th; r[a] = ra; r[b] = rb; }
     RBRT_CSWAP(0, 1) RBRT_CSWAP(2, 3) RBRT_CSWAP(0, 2) RBRT_CSWAP(1, 3) RBRT_CSWAP(1, 2)
