@@ -487,7 +487,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         O, osc = oracle_scene(spheres, meshes)
         cores = int(O.lib().rbrt_ref_hardware_threads())
-        stride, s_spp = choose_stride(O, osc, cam_c, spp, 15.0)
+        stride, s_spp = choose_stride(O, osc, cam_c, spp, 22.0)
         st = cpu_leg(O, osc, cam_c, stride, s_spp)
         line["cpu_baseline"] = {"value": st["rays"] / (st["ms_total"] / 1e3) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                 "sample": f"pixel lattice stride {stride}x{stride} of the {W}x{H} frame, {s_spp} of {spp} spp: {st['paths']} paths, "

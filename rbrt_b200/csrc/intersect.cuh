@@ -212,8 +212,38 @@ __device__ __forceinline__ float q16(uint32_t w, uint32_t sel) { return __uint_a
 
 // One node visit: returns the next reference to process (nearest hit child, or the popped stack top); the other
 // hit children are pushed far-to-near.
-__device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const RaySlabs& R, float t_prune, int32_t* stack, int& sp) {
+// Traversal stacks.  StackL: plain per-lane array (local memory: entry e of all lanes shares a 128-byte line, so lanes at
+// different depths touch different lines — up to 32 L1 requests per push).  StackS: the first K entries live in shared
+// memory, laid out [entry][thread] (bank = lane, conflict-free at any mix of depths: one request per push), deeper
+// entries spill to the local array.
+struct StackL {
+    int32_t* l;
+    __device__ __forceinline__ void put(int i, int32_t v) const { l[i] = v; }
+    __device__ __forceinline__ int32_t get(int i) const { return l[i]; }
+};
+template <int K, int STRIDE>
+struct StackS {
+    int32_t* s;      // &smem[0][threadIdx.x]
+    int32_t* l;
+    __device__ __forceinline__ void put(int i, int32_t v) const { if (i < K) s[i * STRIDE] = v; else l[i - K] = v; }
+    __device__ __forceinline__ int32_t get(int i) const { return i < K ? s[i * STRIDE] : l[i - K]; }
+};
+
+// 256-bit read-only load (sm_100: LDG.E.256): a 64-byte node is two requests to L1 instead of four (the trace kernel runs
+// L1TEX at 75-80 % of its peak, mostly on these gathers).  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
+template <class STK>
+__device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const RaySlabs& R, float t_prune, const STK& stack, int& sp) {
+#ifndef RBRT_LDG128
+    uint4 w0, w1, w2, w3;
+    ldg256(nd, w0, w1); ldg256(nd + 2, w2, w3);
+#else
     const uint4 w0 = __ldg(nd), w1 = __ldg(nd + 1), w2 = __ldg(nd + 2), w3 = __ldg(nd + 3);
+#endif
     const uint32_t fx = R.fx, fy = R.fy, fz = R.fz;
     float t[4]; int32_t r[4];
 #define RBRT_CHILD(k, X, Y, Z) { \
@@ -236,10 +266,10 @@ __device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const
     RBRT_CSWAP(0, 1) RBRT_CSWAP(2, 3) RBRT_CSWAP(0, 2)
 #undef RBRT_CSWAP
 #endif
-    if (t[3] < RBRT_MISS_T) stack[sp++] = r[3];
-    if (t[2] < RBRT_MISS_T) stack[sp++] = r[2];
-    if (t[1] < RBRT_MISS_T) stack[sp++] = r[1];
-    return t[0] < RBRT_MISS_T ? r[0] : stack[--sp];
+    if (t[3] < RBRT_MISS_T) stack.put(sp++, r[3]);
+    if (t[2] < RBRT_MISS_T) stack.put(sp++, r[2]);
+    if (t[1] < RBRT_MISS_T) stack.put(sp++, r[1]);
+    return t[0] < RBRT_MISS_T ? r[0] : stack.get(--sp);
 }
 
 // Leaf: <= 8 contiguous triangle records, exact test, running lexicographic minimum.
@@ -262,8 +292,9 @@ __device__ __forceinline__ void leaf_step(const float4* __restrict__ tris, uint3
 
 // ONE triangle of the current leaf (warp-voted traversal): test it, then `cur` becomes the rest of the leaf or the popped
 // stack top.  Same arithmetic and the same order of triangles within a leaf as leaf_step.
+template <class STK>
 __device__ __forceinline__ void leaf_step_one(const float4* __restrict__ tris, uint32_t tri_base, int32_t& cur, f3 o, f3 d, float t_limit,
-                                              float& best_t, uint32_t& best_idx, float& t_prune, const int32_t* stack, int& sp) {
+                                              float& best_t, uint32_t& best_idx, float& t_prune, const STK& stack, int& sp) {
     const uint32_t code = (uint32_t)(~cur);
     f3 v0, e1, e2; uint32_t orig; float t;
     load_tri(tris, tri_base + (code >> 3), v0, e1, e2, orig);
@@ -271,7 +302,7 @@ __device__ __forceinline__ void leaf_step_one(const float4* __restrict__ tris, u
         keep_min(t, orig, best_t, best_idx);
         t_prune = fminf(t_limit, __fmaf_rn(best_t, 1.0001f, 1e-4f));
     }
-    cur = (code & 7u) ? (int32_t)~(code + 7u) : stack[--sp];              // {first + 1, count - 1}: +8 on first, -1 on the count field
+    cur = (code & 7u) ? (int32_t)~(code + 7u) : stack.get(--sp);              // {first + 1, count - 1}: +8 on first, -1 on the count field
 }
 
 // Warp-voted traversal (k_trace, k_tail).  The while-while form ("every lane descends to its next leaf, then the leaves
@@ -284,9 +315,9 @@ __device__ __forceinline__ void leaf_step_one(const float4* __restrict__ tris, u
 #define RBRT_VOTE_N 1      // node step iff  lanes at nodes * RBRT_VOTE_N >= lanes at leaves * RBRT_VOTE_L
 #define RBRT_VOTE_L 1
 #endif
-template <bool COUNT>
+template <bool COUNT, class STK>
 __device__ __forceinline__ void traverse_voted(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t tri_base,
-                                               const RaySlabs& R, f3 o, f3 d, float t_limit, int32_t* stack, int& sp, int32_t& cur,
+                                               const RaySlabs& R, f3 o, f3 d, float t_limit, const STK& stack, int& sp, int32_t& cur,
                                                float& best_t, uint32_t& best_idx, float& t_prune, int threshold,
                                                uint32_t& n_nodes, uint32_t& n_tris) {
     asm volatile("" : "+r"(threshold));                                   // keep it in a register (otherwise re-derived from three values every step)
@@ -311,14 +342,15 @@ __device__ __forceinline__ bool mesh_closest_bvh(const SceneDev& S, const MeshDe
     float t_prune = t_limit;
     const RaySlabs R = ray_slabs(M, o, d);
     const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(S.nodes) + 4 * (size_t)M.node_base;
-    int32_t stack[RBRT_STACK];
+    int32_t lstack[RBRT_STACK];
+    const StackL stack = {lstack};
     int sp = 0;
     int32_t cur = M.root_ref;
-    stack[sp++] = RBRT_SENTINEL;
+    stack.put(sp++, RBRT_SENTINEL);
     uint32_t n_nodes = 0, n_tris = 0;
     while (cur != RBRT_SENTINEL) {
         if (cur >= 0) { cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp); ++n_nodes; }
-        else { leaf_step(S.tris, M.tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, n_tris); cur = stack[--sp]; }
+        else { leaf_step(S.tris, M.tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, n_tris); cur = stack.get(--sp); }
     }
     if (cnt) { cnt->nodes += n_nodes; cnt->tris += n_tris; }
     return best_idx != 0xFFFFFFFFu;

@@ -209,6 +209,9 @@ __device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_
 #define FETCH_THRESHOLD 8      // re-fill the warp when fewer lanes than this are still traversing (WaveParams::fetch_thr; swept 1..24 on C3,
                                // profiles/r1_summary.md: a re-fill stalls the whole warp on an atomic -> queue -> ray chain, so fewer is better)
 
+#ifndef TRACE_SMEM_STACK
+#define TRACE_SMEM_STACK 0     // traversal-stack entries per lane kept in shared memory (intersect.cuh StackS); 0 = all in local memory
+#endif
 #ifndef TRACE_BLOCKS
 #define TRACE_BLOCKS 8         // resident blocks per SM: 8 x 128 threads = 64 registers per thread
 #endif
@@ -220,7 +223,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
     if (COUNT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_CAND], (unsigned long long)n);
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const int32_t SENTINEL = 0x7FFFFFFF;
-    int32_t stack[RBRT_STACK];
+    int32_t lstack[RBRT_STACK];
+#if TRACE_SMEM_STACK > 0
+    __shared__ int32_t s_stack[TRACE_SMEM_STACK][TRACE_THREADS];
+    const StackS<TRACE_SMEM_STACK, TRACE_THREADS> stack = {&s_stack[0][threadIdx.x], lstack};
+#else
+    const StackL stack = {lstack};
+#endif
     // ---- ray state
     bool has_ray = false;
     uint32_t pid = 0, mi = 0;
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
         t_prune = t_limit; best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;     // min_param init (triangle.rs:398)
         nodes = reinterpret_cast<const uint4*>(P.S.nodes) + 4 * (size_t)M.node_base; tri_base = M.tri_base;
         R = ray_slabs(M, o, d);
-        sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
+        sp = 0; stack.put(sp++, SENTINEL); cur = M.root_ref;
     };
 
     for (;;) {
@@ -308,25 +317,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
         uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
         if (active == 0) { if (exhausted) break; continue; }
         const int threshold = exhausted ? 1 : min((int)P.fetch_thr, (int)quota);
-#ifndef RBRT_WHILE_WHILE
         // ---- warp-voted traversal: one node visit or one triangle test per step, whichever more lanes wait for (intersect.cuh)
         traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
-#else
-        // ---- while-while traversal (first form, kept for comparison): every lane descends to its next leaf, then the leaves are processed together
-        for (;;) {
-            while ((uint32_t)cur < (uint32_t)SENTINEL) {                  // internal node (intersect.cuh)
-                cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp);
-                if (COUNT) ++n_nodes;
-            }
-            if (cur < 0) {                                                // leaf: <= 8 contiguous triangles
-                uint32_t nt = 0;
-                leaf_step(P.S.tris, tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, nt);
-                if (COUNT) n_tris += nt;
-                cur = stack[--sp];
-            }
-            if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
-        }
-#endif
     }
     if (COUNT) {
         for (int off = 16; off; off >>= 1) { n_nodes += __shfl_down_sync(FULL_MASK, n_nodes, off); n_tris += __shfl_down_sync(FULL_MASK, n_tris, off); }
@@ -551,7 +543,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
     uint32_t* head = &P.ctr[it0].shade_head;                              // unused by k_shade(it0) from now on: queue cursor of this kernel
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
     const int32_t SENTINEL = 0x7FFFFFFF;
-    int32_t stack[RBRT_STACK];
+    int32_t lstack[RBRT_STACK];
+    const StackL stack = {lstack};
     RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     // ---- path state
     uint32_t pid = 0, it = it0;
@@ -581,7 +574,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         t_prune = t_limit; best_t = 1000000.0f; best_idx = 0xFFFFFFFFu;
         nodes = reinterpret_cast<const uint4*>(P.S.nodes) + 4 * (size_t)M.node_base; tri_base = M.tri_base;
         R = ray_slabs(M, o, d);
-        sp = 0; stack[sp++] = SENTINEL; cur = M.root_ref;
+        sp = 0; stack.put(sp++, SENTINEL); cur = M.root_ref;
     };
     auto load_candidate = [&]() {                                         // the ray stage A queued for this path
         uint4 h = load_hit(P, pid);
@@ -649,23 +642,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         if (active == 0) { if (exhausted) break; continue; }
         const int threshold = exhausted ? 1 : min((int)P.fetch_thr, (int)quota);
         // ---- (4) traversal, as k_trace
-#ifndef RBRT_WHILE_WHILE
         traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
-#else
-        for (;;) {
-            while ((uint32_t)cur < (uint32_t)SENTINEL) {
-                cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp);
-                if (COUNT) ++n_nodes;
-            }
-            if (cur < 0) {
-                uint32_t nt = 0;
-                leaf_step(P.S.tris, tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, nt);
-                if (COUNT) n_tris += nt;
-                cur = stack[--sp];
-            }
-            if (__popc(__ballot_sync(FULL_MASK, cur != SENTINEL)) < threshold) break;
-        }
-#endif
     }
     for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
     if (lane == 0) {
