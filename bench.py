@@ -18,7 +18,7 @@ path) — the reference's `render_scene(cam, spp, scene)` (lib.rs:75-124).  Rays
              triangle soup from pinned host memory (rbrt_gpu_scene_create: H2D + LBVH build), renders
              (rbrt_gpu_render / the multi-rank building blocks) and copies the RGB8 image back to the host.
   roofline   the trace kernel (BVH traversal + intersection tests): algorithmic bytes per step from an
-             instrumented counting pass (64 B per node visit, 48 B per triangle test, 72 B of queue traffic per
+             instrumented counting pass (64 B per node visit, 48 B per triangle test, 64 B of queue / path-record traffic per
              traversed ray) / the summed CUDA-event durations of that kernel's
              launches inside the timed region, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline / --impl reference
@@ -194,11 +194,11 @@ def peaks():
 
 def algorithmic_bytes(st, n_spheres, n_meshes):
     """Trace kernel (stage B: LBVH traversal of the rays that entered a mesh AABB), DESIGN.md section 4:
-    bytes/step = 64 V + 48 T + 72 C   (V node visits x 64-B node, T triangle tests x 48-B record, C traversed rays x
-    72 B of queue traffic: 4 B queue index + 32 B ray + 16 B sphere pre-result read, 16 B hit record + 4 B material-queue
-    index written).  The sphere and mesh-AABB tests of SURVEY.md section 8(d) (16 S + 24 M per ray) now run in the
-    producing kernels (k_generate / k_shade) and are not charged to this kernel."""
-    return 64 * st["node_visits"] + 48 * st["tri_tests"] + 72 * st["traversed_rays"]      # counts of k_trace only (tail kernel subtracted by the caller)
+    bytes/step = 64 V + 48 T + 64 C   (V node visits x 64-B node, T triangle tests x 48-B record, C traversed rays x
+    64 B of queue / path-record traffic: 4 B queue index + 40 B of the path record (16 B sphere pre-result + 24 B ray) read,
+    16 B hit record + 4 B material-queue index written).  The sphere and mesh-AABB tests of SURVEY.md section 8(d)
+    (16 S + 24 M per ray) run in the producing kernels (k_generate / k_shade) and are not charged to this kernel."""
+    return 64 * st["node_visits"] + 48 * st["tri_tests"] + 64 * st["traversed_rays"]      # counts of k_trace only (tail kernel subtracted by the caller)
 
 
 def algorithmic_flops(st, n_spheres, n_meshes):

@@ -220,7 +220,10 @@ int rbrt_gpu_render_hdr(const rbrt_scene* scene, const rbrt_camera* cam, uint32_
 /* Multi-GPU building block: renders this rank's shard and leaves the per-pixel SUM over its
  * samples (lib.rs:95-100, before the 1/spp scale) in a DEVICE buffer of W*H*4 f32 (rgb + pad),
  * zero outside the shard, on the given CUDA stream (0 = default stream).  Ranks then sum these
- * buffers (NCCL reduce) and rank 0 calls rbrt_gpu_finalize_device. */
+ * buffers (NCCL reduce) and rank 0 calls rbrt_gpu_finalize_device.
+ * With stats == NULL the call only ENQUEUES the frame on cuda_stream and returns (with stats it waits for the frame
+ * and fills the counters).  Frames in flight at the same time must use different streams, different accumulation
+ * buffers and different wavefront pools (opts->flags, RBRT_OPT_POOL_*); the scene must outlive them. */
 int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam,
                                  uint32_t num_samples, const rbrt_render_opts* opts,
                                  void* d_accum_rgba_f32, void* cuda_stream, rbrt_stats* stats);

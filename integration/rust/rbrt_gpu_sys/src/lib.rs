@@ -30,6 +30,11 @@ pub struct RbrtStats { pub rays: u64, pub paths: u64, pub nan_rays: u64, pub nod
                        pub ms_device: f64, pub ms_trace: f64, pub ms_h2d: f64, pub ms_d2h: f64, pub launches: u32, pub iterations: u32,
                        pub traversed_rays: u64, pub tail_node_visits: u64, pub tail_tri_tests: u64, pub tail_traversed_rays: u64 }
 pub enum RbrtScene {}
+pub const RBRT_OPT_COUNT_VISITS: u32 = 1;
+pub const RBRT_OPT_TIME_KERNELS: u32 = 2;
+pub const RBRT_OPT_NO_TAIL_KERNEL: u32 = 4;
+pub const RBRT_OPT_POOL_SHIFT: u32 = 3;    // flags |= slot << RBRT_OPT_POOL_SHIFT, slot in 0..4: the wavefront pool of a frame in flight
+pub const RBRT_OPT_POOL_MASK: u32 = 24;
 
 extern "C" {
     pub fn rbrt_camera_new(position: RbrtVec3, look_at: RbrtVec3, up: RbrtVec3, img_height_pix: u32, img_width_pix: u32,
@@ -46,6 +51,12 @@ extern "C" {
                            rgb_out: *mut u8, stats: *mut RbrtStats) -> c_int;
     pub fn rbrt_gpu_render_hdr(scene: *const RbrtScene, cam: *const RbrtCamera, num_samples: u32, opts: *const RbrtRenderOpts,
                                rgb_f32_out: *mut f32, stats: *mut RbrtStats) -> c_int;
+    /// Multi-GPU / pipelining building blocks: render into a device accumulation buffer on `stream` (stats = null: enqueue only),
+    /// then 1/spp, sqrt, x256, saturating u8 on the device.  `opts.flags` bits 3-4 (RBRT_OPT_POOL_*) pick one of four wavefront pools.
+    pub fn rbrt_gpu_render_accum_device(scene: *const RbrtScene, cam: *const RbrtCamera, num_samples: u32, opts: *const RbrtRenderOpts,
+                                        d_accum: *mut c_void, stream: *mut c_void, stats: *mut RbrtStats) -> c_int;
+    pub fn rbrt_gpu_finalize_device(d_accum: *const c_void, width: u32, height: u32, num_samples: u32, d_rgb: *mut c_void,
+                                    d_hdr: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rbrt_gpu_release_cache() -> c_int;
     pub fn rbrt_last_error() -> *const c_char;
     pub fn rbrt_gpu_version() -> *const c_char;
