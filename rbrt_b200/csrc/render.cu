@@ -525,7 +525,7 @@ __global__ void k_sum_rays(WaveParams P) {
 
 // ------------------------------------------------------------------ tail, asynchronous form (BVH mode)
 // Same hand-over as k_finish, but built like k_trace: persistent warps, every lane owns a PATH (not a ray), lanes whose
-// path has ended take the next queued item inside the loop, and traversal is the shared while-while loop with dynamic
+// path has ended take the next queued item inside the loop, and traversal is the shared warp-voted loop with dynamic
 // fetch.  There is no barrier between bounces of different paths, so the hand-over can happen while millions of rays are
 // still alive: the sparsely populated iterations (each bounded by its slowest ray) disappear instead of being paid one
 // after another.  A lane's step: [traversal of the meshes its ray entered] -> resolve -> scatter + stage A (possibly
@@ -817,7 +817,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is
         // bounded below by its slowest ray, so the ~45 sparsely populated tail iterations cost the same for a
         // small batch as for a large one: the default is therefore "as many paths as fit" — up to 2^27 paths
-        // (92 + 2*max_depth bytes of wavefront state each: 25.8 GB at depth 50) and at most half of the free HBM.
+        // (108 + 2*(max_depth - 12) bytes of wavefront state each: 24.7 GB at depth 50) and at most half of the free HBM.
         uint32_t target = o.batch_paths;
         if (!target) {
             const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
