@@ -63,7 +63,8 @@ struct WaveParams {
     uint32_t s_base;         // first sample index of this batch
     uint32_t s_count;        // samples in this batch
     uint32_t max_depth;      // 50 (lib.rs:99)
-    uint32_t fetch_thr;      // k_trace / k_tail re-fill a warp from the queue when fewer lanes than this still traverse
+    uint32_t fetch_thr;      // k_trace re-fills a warp from the queue when fewer lanes than this still traverse
+    uint32_t tail_thr;       // the same for k_tail, whose "re-fill" also shades the lanes' pending hits
     uint4* rec;
     uint32_t* candq; uint32_t* matq[2][3];
     float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;

@@ -531,6 +531,7 @@ __global__ void k_sum_rays(WaveParams P) {
 // after another.  A lane's step: [traversal of the meshes its ray entered] -> resolve -> scatter + stage A (possibly
 // several times in a row for sphere-only bounces) -> next traversal, or end of path -> next item.
 #define TAIL_THREADS 128
+#define TAIL_FETCH_THRESHOLD 8  // WaveParams::tail_thr
 #define TAIL_FORCE_IT 12        // from this bounce iteration on, the tail kernel takes whatever is left
 
 template <bool COUNT, bool ET>
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         }
         uint32_t active = __ballot_sync(FULL_MASK, cur != SENTINEL);
         if (active == 0) { if (exhausted) break; continue; }
-        const int threshold = exhausted ? 1 : min((int)P.fetch_thr, (int)quota);
+        const int threshold = exhausted ? 1 : min((int)P.tail_thr, (int)quota);
         // ---- (4) traversal, as k_trace
         traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
     }
@@ -845,6 +846,8 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         wp.cap = wb.cap; wp.paths_px = P; wp.max_depth = max_depth;
         const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
         wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
+        const char* tthr_env = getenv("RBRT_TAIL_FETCH_THRESHOLD");
+        wp.tail_thr = tthr_env ? (uint32_t)std::min(32, std::max(1, atoi(tthr_env))) : TAIL_FETCH_THRESHOLD;
         wp.rec = wb.rec; wp.candq = wb.candq;
         for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
