@@ -105,11 +105,27 @@ struct CamDev {
     uint32_t width, height;
 };
 
+// Division by a launch-invariant 32-bit divisor (Granlund-Montgomery round-up form, exact for every 32-bit dividend):
+// the pixel mapping divides twice per path and bounce, and a run-time `/` is ~20 instructions.
+struct FastDiv { uint32_t m, s1, s2; };
+inline FastDiv make_fastdiv(uint32_t d) {
+    uint32_t l = 0; while ((1ull << l) < d) ++l;                            // ceil(log2 d)
+    FastDiv f;
+    f.m = (uint32_t)((((1ull << 32) * ((1ull << l) - d)) / d) + 1);
+    f.s1 = l < 1 ? l : 1; f.s2 = l - f.s1;
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, FastDiv f) {
+    const uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 // Pixel enumeration of one rank's shard: 8x4-pixel tiles (one warp = one tile), linear tile id
 // T = tj * shard_count + shard_rank, row-major over ceil(W/8) x ceil(H/4) tiles.
 struct ShardDev {
     uint32_t rank, count;      // tile striping (1 rank: 0,1)
     uint32_t tiles_x, tiles_total, tiles_mine;
+    FastDiv fd_tiles_x;        // division by tiles_x
     uint32_t s0, s1;           // sample range rendered by this rank
 };
 
@@ -117,7 +133,7 @@ __device__ __forceinline__ bool shard_pixel(const ShardDev& sh, const CamDev& ca
     uint32_t tj = j >> 5, lane = j & 31;
     uint32_t T = tj * sh.count + sh.rank;
     if (T >= sh.tiles_total) return false;
-    uint32_t ty = T / sh.tiles_x, tx = T - ty * sh.tiles_x;
+    uint32_t ty = fast_div(T, sh.fd_tiles_x), tx = T - ty * sh.tiles_x;
     col = tx * 8 + (lane & 7);
     row = ty * 4 + (lane >> 3);
     return col < cam.width && row < cam.height;

@@ -60,6 +60,7 @@ struct WaveParams {
     uint32_t key0, key1;
     uint32_t cap;            // capacity of the per-path buffers = paths of a full batch
     uint32_t paths_px;       // P_r = tiles_mine * 32: path id = s_local * paths_px + j
+    FastDiv fd_paths_px;     // division by paths_px
     uint32_t s_base;         // first sample index of this batch
     uint32_t s_count;        // samples in this batch
     uint32_t max_depth;      // 50 (lib.rs:99)

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_generate(WaveParams P) {
             uint32_t g = g0 + r;
             if (g >= n_groups) break;
             uint32_t pid = (g << 5) + lane;
-            uint32_t s_local = pid / P.paths_px, j = pid - s_local * P.paths_px;
+            uint32_t s_local = fast_div(pid, P.fd_paths_px), j = pid - s_local * P.paths_px;
             uint32_t row, col;
             if (shard_pixel(P.sh, P.cam, j, row, col)) {
                 f3 o, d;
@@ -401,7 +401,7 @@ __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it,
         float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
         normal = mk3(nn.x, nn.y, nn.z);
     }
-    uint32_t s_local = pid / P.paths_px, jp = pid - s_local * P.paths_px;
+    uint32_t s_local = fast_div(pid, P.fd_paths_px), jp = pid - s_local * P.paths_px;
     uint32_t row, col;
     shard_pixel(P.sh, P.cam, jp, row, col);
     f3 out_d;
@@ -797,6 +797,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     ShardDev sh;
     sh.rank = 0; sh.count = 1; sh.s0 = 0; sh.s1 = spp;
     sh.tiles_x = (W + 7) / 8;
+    sh.fd_tiles_x = make_fastdiv(sh.tiles_x);
     sh.tiles_total = sh.tiles_x * ((H + 3) / 4);
     if (o.shard_count > 1) {
         if (o.shard_rank >= o.shard_count) { set_error("shard_rank >= shard_count"); return RBRT_E_INVALID; }
@@ -843,7 +844,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         WaveParams wp;
         wp.S = sc.dev; wp.cam = make_cam(cam); wp.sh = sh;
         wp.key0 = (uint32_t)o.seed; wp.key1 = (uint32_t)(o.seed >> 32);
-        wp.cap = wb.cap; wp.paths_px = P; wp.max_depth = max_depth;
+        wp.cap = wb.cap; wp.paths_px = P; wp.fd_paths_px = make_fastdiv(P); wp.max_depth = max_depth;
         const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
         wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
         const char* tthr_env = getenv("RBRT_TAIL_FETCH_THRESHOLD");
