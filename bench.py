@@ -360,17 +360,21 @@ def run_gpu(args):
 
     # ---- resident arm (timed region): `steps` frames through the FramePipeline, `frames_in_flight` of them in flight on
     #      their own streams and wavefront pools, so the sparse last bounces of one frame overlap the next frame's first
-    pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode)
+    fpb = args.frames_per_batch or (1 if world == 1 else min(4, world // 2) if world >= 4 else 1)   # a rank's batch ~ a frame's worth of paths
+    if args.workload in SAMPLE_SHARDED:
+        fpb = args.frames_per_batch or 1
+    pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode, frames_per_batch=fpb)
     with ClockSampler(local) as clk:
         time.sleep(0.3)                                       # let nvidia-smi deliver its first samples
-        for _ in range(max(args.warmup, 3)):
-            pipe.submit(cam_c, spp, scene.handle(), seed=SEED)
+        for _ in range(max(args.warmup, 3) * fpb):
+            pipe.submit(cam_c, spp, scene, seed=SEED)
         pipe.drain()
         barrier()
         clk.mark_begin()
         e0.record(stream)
         for _ in range(args.steps):
-            pipe.submit(cam_c, spp, scene.handle(), seed=SEED)
+            pipe.submit(cam_c, spp, scene, seed=SEED)
+        pipe.flush()                                          # a last, partially filled group of frames
         pipe.wait_on(stream)
         e1.record(stream)
         barrier()
@@ -414,7 +418,8 @@ def run_gpu(args):
         t_b = time.perf_counter()
         # render -> [reduce] -> finalize -> RGB8 image to pinned host memory, enqueued on the frame's stream; the image of
         # the frame submitted `frames_in_flight` steps ago is collected (host buffer ready) and its scene destroyed
-        retire(pipe_e.submit(cam_c, spp, sc, tag=sc, seed=SEED))
+        for fin in pipe_e.submit(cam_c, spp, sc, tag=sc, seed=SEED):
+            retire(fin)
         t_c = time.perf_counter()
         return (t_b - t_a) * 1e3, (t_c - t_b) * 1e3
 
@@ -464,10 +469,10 @@ def run_gpu(args):
         "metric": "Mrays/s", "value": rays / (ms / 1e3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.workload, spheres, meshes, world), frames_in_flight=args.frames_in_flight),
+        "config": dict(workload_config(args.workload, spheres, meshes, world), frames_in_flight=args.frames_in_flight, frames_per_batch=fpb),
         "single_frame": {"ms_per_step": ms_single, "value": rays / args.steps / (ms_single / 1e3) / 1e6, "unit": "Mrays/s",
                          "note": "one frame at a time, host waits for each (latency of a lone render_scene call); `value` keeps "
-                                 "`frames_in_flight` frames in flight on separate streams"},
+                                 "`frames_in_flight` groups of `frames_per_batch` frames in flight on separate streams"},
         "samples_per_s": paths / (ms / 1e3), "rays_per_step": rays / args.steps, "rays_per_sample": rays / max(paths, 1),
         "clocks": clocks,
         "e2e": {"value": e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
@@ -529,6 +534,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--frames-per-batch", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="frames rendered together in the same wavefront batches in the timed region (0 = 1 on 1-2 GPUs, 2 on 4, 4 on 8: "
+                         "a rank's batch then holds about one frame's worth of paths)")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2, 3, 4],
                     help="frames kept in flight on separate streams in the timed region (1 = one frame at a time)")
     args = ap.parse_args()

@@ -228,6 +228,15 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
                                  uint32_t num_samples, const rbrt_render_opts* opts,
                                  void* d_accum_rgba_f32, void* cuda_stream, rbrt_stats* stats);
 
+/* The same for n_frames (1..4) frames of ONE scene rendered TOGETHER in the same wavefront batches: one camera, one
+ * seed (Philox key) and one accumulation buffer per frame, all cameras with the same image size, the same sample count
+ * and options for all (opts->seed is ignored).  Each image is bit-identical to what rbrt_gpu_render_accum_device gives
+ * for that camera and seed alone; the point is kernel size: a rank's share of a frame on 8 GPUs is small, and two or
+ * four frames per batch restore the efficiency the kernels have on larger shards. */
+int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_camera* cams, const uint64_t* seeds,
+                                        uint32_t n_frames, uint32_t num_samples, const rbrt_render_opts* opts,
+                                        void* const* d_accum_rgba_f32, void* cuda_stream, rbrt_stats* stats);
+
 /* = lib.rs:101 + lib.rs:116-122: colour *= 1/spp; (sqrt(c)*256) as u8 (saturating).
  *   d_rgb_u8 (W*H*3) and d_hdr_f32 (W*H*3) are DEVICE pointers; either may be NULL. */
 int rbrt_gpu_finalize_device(const void* d_accum_rgba_f32, uint32_t width, uint32_t height,

@@ -90,6 +90,7 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE = 0, 1
 OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL, OPT_POOL_SHIFT = 1, 2, 4, 3
+MAX_FRAMES = 4          # frames one wavefront batch can hold (rbrt_gpu_render_accum_device_frames)
 HIT_NONE, HIT_SPHERE, HIT_MESH, HIT_TRIANGLE = -1, 0, 1, 2
 ELEM_SPHERE, ELEM_TRIANGLE = 0, 1
 E_INVALID, E_CUDA, E_NODEVICE = 1, 2, 3
@@ -108,6 +109,8 @@ GPU_SIGNATURES = {
     "rbrt_gpu_render": (C.c_int, [C.c_void_p, P(CameraC), C.c_uint32, P(RenderOptsC), C.c_void_p, P(StatsC)]),
     "rbrt_gpu_render_hdr": (C.c_int, [C.c_void_p, P(CameraC), C.c_uint32, P(RenderOptsC), C.c_void_p, P(StatsC)]),
     "rbrt_gpu_render_accum_device": (C.c_int, [C.c_void_p, P(CameraC), C.c_uint32, P(RenderOptsC), C.c_void_p, C.c_void_p, P(StatsC)]),
+    "rbrt_gpu_render_accum_device_frames": (C.c_int, [C.c_void_p, P(CameraC), P(C.c_uint64), C.c_uint32, C.c_uint32, P(RenderOptsC),
+                                                      P(C.c_void_p), C.c_void_p, P(StatsC)]),
     "rbrt_gpu_finalize_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rbrt_gpu_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, P(StatsC)]),
     "rbrt_gpu_primary_rays": (C.c_int, [P(CameraC), C.c_uint64, C.c_uint32, C.c_void_p]),

@@ -293,7 +293,24 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
     CKA(cudaSetDevice(sc.device));
     double t0 = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
-    int rc = render_accum(sc, *cam, spp, opts, (float4*)d_accum, (cudaStream_t)stream, stats);
+    float4* acc1[1] = {(float4*)d_accum};
+    int rc = render_accum(sc, cam, nullptr, 1, spp, opts, acc1, (cudaStream_t)stream, stats);
+    if (rc) return rc;
+    if (stats) stats->ms_total = now_ms() - t0;
+    return RBRT_OK;
+}
+
+int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames,
+                                        uint32_t spp, const rbrt_render_opts* opts, void* const* d_accum, void* stream, rbrt_stats* stats) {
+    if (!scene || !cams || !seeds || !d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
+    if (!n_frames || n_frames > RBRT_MAX_FRAMES) { set_error("n_frames must be 1..%d", RBRT_MAX_FRAMES); return RBRT_E_INVALID; }
+    float4* acc[RBRT_MAX_FRAMES];
+    for (uint32_t f = 0; f < n_frames; ++f) { if (!d_accum[f]) { set_error("null accumulation buffer"); return RBRT_E_INVALID; } acc[f] = (float4*)d_accum[f]; }
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    CKA(cudaSetDevice(sc.device));
+    double t0 = now_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    int rc = render_accum(sc, cams, seeds, n_frames, spp, opts, acc, (cudaStream_t)stream, stats);
     if (rc) return rc;
     if (stats) stats->ms_total = now_ms() - t0;
     return RBRT_OK;
@@ -329,7 +346,8 @@ static int render_host(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     rbrt_stats local; memset(&local, 0, sizeof(local));
-    int rc = render_accum(sc, *cam, spp, opts, wb.accum, 0, &local);
+    float4* acc1[1] = {wb.accum};
+    int rc = render_accum(sc, cam, nullptr, 1, spp, opts, acc1, 0, &local);
     if (rc) return rc;
     rc = finalize(wb.accum, cam->img_width_pix, cam->img_height_pix, spp, rgb_out ? wb.rgb : nullptr, hdr_out ? wb.hdr : nullptr, 0);
     if (rc) return rc;

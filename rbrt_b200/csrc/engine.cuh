@@ -7,6 +7,8 @@
 
 namespace rbrt {
 
+#define RBRT_MAX_FRAMES 4    // frames one wavefront batch can hold (rbrt_gpu_render_accum_device_frames)
+
 // Per-iteration queue counters.  All iterations of a batch get their own slot, so one memset per
 // batch resets everything and no kernel ever has to reset a counter another kernel still reads.
 struct IterCtr {
@@ -55,9 +57,11 @@ struct Scene {
 // Everything a wavefront kernel needs, passed by value (kernel parameter space).
 struct WaveParams {
     SceneDev S;
-    CamDev cam;
+    CamDev cam[RBRT_MAX_FRAMES];                 // one camera and one Philox key per FRAME of the batch (same image size)
     ShardDev sh;
-    uint32_t key0, key1;
+    uint32_t key0[RBRT_MAX_FRAMES], key1[RBRT_MAX_FRAMES];
+    uint32_t n_frames;       // frames rendered together: path id = ((f * s_count + s_local) * paths_px + j
+    FastDiv fd_s_count;      // division by s_count (frame index of a path)
     uint32_t cap;            // capacity of the per-path buffers = paths of a full batch
     uint32_t paths_px;       // P_r = tiles_mine * 32: path id = s_local * paths_px + j
     FastDiv fd_paths_px;     // division by paths_px
@@ -75,8 +79,8 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
 // render.cu
-int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rbrt_render_opts* opts,
-                 float4* d_accum, cudaStream_t st, rbrt_stats* stats);
+int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
+                 const rbrt_render_opts* opts, float4* const* d_accum, cudaStream_t st, rbrt_stats* stats);
 int finalize(const float4* d_accum, uint32_t W, uint32_t H, uint32_t spp, uint8_t* d_rgb, float* d_hdr, cudaStream_t st);
 int trace_rays_device(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, uint32_t mode, rbrt_hit* d_hits,
                       unsigned long long* d_stats, cudaStream_t st);

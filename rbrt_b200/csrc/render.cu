@@ -110,6 +110,14 @@ __device__ __forceinline__ void store_hist(const WaveParams& P, uint32_t pid, ui
     else P.hist[(size_t)(k - REC_HIST) * P.cap + pid] = (uint16_t)elem;
 }
 
+// Path id -> (frame of the batch, sample of the batch, pixel enumeration index): pid = ((f * s_count) + s_local) * paths_px + j
+__device__ __forceinline__ void path_coords(const WaveParams& P, uint32_t pid, uint32_t& f, uint32_t& s_local, uint32_t& j) {
+    const uint32_t v = fast_div(pid, P.fd_paths_px);
+    j = pid - v * P.paths_px;
+    f = P.n_frames > 1u ? fast_div(v, P.fd_s_count) : 0u;
+    s_local = v - f * P.s_count;
+}
+
 // att_1 * (att_2 * (... * leaf)): the recursion of lib.rs:62 unwinds innermost first
 __device__ __forceinline__ f3 unwind(const WaveParams& P, f3 col, uint32_t n_scatters, uint32_t pid) {
     for (int k = (int)n_scatters - 1; k >= 0; --k) {
@@ -159,10 +167,9 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
 // ------------------------------------------------------------------ generate (cam.rs:64-82) + stage A
 template <bool ET>
 __global__ void __launch_bounds__(256) k_generate(WaveParams P) {
-    const uint32_t n_paths = P.s_count * P.paths_px;                      // multiple of 32
+    const uint32_t n_paths = P.n_frames * P.s_count * P.paths_px;         // multiple of 32
     const uint32_t n_groups = n_paths >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     uint32_t nan_count = 0, rays = 0;
     for (uint32_t g0 = warp * ROUNDS; g0 < n_groups; g0 += n_warps * ROUNDS) {
         Deferred df; df.clear();
@@ -171,11 +178,13 @@ __global__ void __launch_bounds__(256) k_generate(WaveParams P) {
             uint32_t g = g0 + r;
             if (g >= n_groups) break;
             uint32_t pid = (g << 5) + lane;
-            uint32_t s_local = fast_div(pid, P.fd_paths_px), j = pid - s_local * P.paths_px;
+            uint32_t f, s_local, j;
+            path_coords(P, pid, f, s_local, j);
             uint32_t row, col;
-            if (shard_pixel(P.sh, P.cam, j, row, col)) {
+            if (shard_pixel(P.sh, P.cam[0], j, row, col)) {
                 f3 o, d;
-                camera_ray(P.cam, row, col, key, row * P.cam.width + col, P.s_base + s_local, o, d);
+                RngKey key; key.k0 = P.key0[f]; key.k1 = P.key1[f];
+                camera_ray(P.cam[f], row, col, key, row * P.cam[0].width + col, P.s_base + s_local, o, d);
                 ++rays;
                 df.set(r, stage_a<ET>(P, 0, pid, o, d, nan_count), pid);
             }
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) 
 // ------------------------------------------------------------------ shade (lib.rs:54-62 + the scatter impls) + stage A
 // One hit of material `kind` at iteration `it`: scatter, then stage A of the continuation ray.  Returns its queue class.
 template <bool ET>
-__device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid, RngKey key,
+__device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid,
                                                uint32_t& rays, uint32_t& nan_count) {
     uint4 h = load_hit(P, pid);
     f3 o, d; load_ray(P, pid, o, d);
@@ -401,11 +410,13 @@ __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it,
         float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
         normal = mk3(nn.x, nn.y, nn.z);
     }
-    uint32_t s_local = fast_div(pid, P.fd_paths_px), jp = pid - s_local * P.paths_px;
+    uint32_t f, s_local, jp;
+    path_coords(P, pid, f, s_local, jp);
     uint32_t row, col;
-    shard_pixel(P.sh, P.cam, jp, row, col);
+    shard_pixel(P.sh, P.cam[0], jp, row, col);
+    RngKey key; key.k0 = P.key0[f]; key.k1 = P.key1[f];
     f3 out_d;
-    bool cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam.width + col,
+    bool cont = scatter(kind, __ldg(P.S.mat + elem), d, point, normal, key, row * P.cam[0].width + col,
                         P.s_base + s_local, it + 1, out_d);
     if (!cont) { end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }       // absorbed (metal.rs:24) -> black
     store_hist(P, pid, it, elem);
@@ -424,7 +435,6 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS) k_shade(WaveParams P, uint3
     const uint32_t a0 = (n0 + 31u) & ~31u, a1 = a0 + ((n1 + 31u) & ~31u), total = a1 + ((n2 + 31u) & ~31u);
     if (total == 0 || P.ctr[0].pad) return;
     const uint32_t lane = threadIdx.x & 31;
-    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     uint32_t nan_count = 0, rays = 0;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t rounds = min((uint32_t)ROUNDS, max(1u, (total / 32u + n_warps - 1) / n_warps));   // tail iterations: spread the work
@@ -453,7 +463,7 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS) k_shade(WaveParams P, uint3
             const uint32_t kind = (kinds >> (2 * r)) & 3u;
             if (kind == 3u) continue;
             const uint32_t pid = df.pid[r];
-            df.set(r, shade_item<ET>(P, it, kind, pid, key, rays, nan_count), pid);
+            df.set(r, shade_item<ET>(P, it, kind, pid, rays, nan_count), pid);
         }
         flush(P, it + 1, df);
     }
@@ -479,7 +489,6 @@ __global__ void __launch_bounds__(256) k_finish(WaveParams P, uint32_t it0, uint
     const uint32_t nc = c.cand_count, n0 = c.mat_count[0], n1 = c.mat_count[1], n2 = c.mat_count[2];
     const uint32_t total = nc + n0 + n1 + n2;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     uint32_t nan_count = 0, rays = 0;
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     uint32_t n_cand = 0;
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(256) k_finish(WaveParams P, uint32_t it0, uint
         for (;;) {
             if (kind == CLS_CAND) { ++n_cand; kind = process_candidate<BRUTE>(P, it, pid, COUNT ? &cnt : nullptr); }
             if (kind < 0) break;                                          // path ended (miss / depth exhausted)
-            uint32_t cls = shade_item<ET>(P, it, (uint32_t)kind, pid, key, rays, nan_count);
+            uint32_t cls = shade_item<ET>(P, it, (uint32_t)kind, pid, rays, nan_count);
             if (cls == CLS_NONE) break;                                   // absorbed / resolved on the spot
             kind = (int)cls; ++it;
         }
@@ -546,7 +555,6 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
     const int32_t SENTINEL = 0x7FFFFFFF;
     int32_t lstack[RBRT_STACK];
     const StackL stack = {lstack};
-    RngKey key; key.k0 = P.key0; key.k1 = P.key1;
     // ---- path state
     uint32_t pid = 0, it = it0;
     int pending = -1;                                                     // material kind of a hit waiting to be shaded, -1 none
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         }
         // ---- (3) pending hits: scatter + stage A, repeated while the continuation ray is resolved by a sphere alone
         while (pending >= 0) {
-            uint32_t cls = shade_item<ET>(P, it, (uint32_t)pending, pid, key, rays, nan_count);
+            uint32_t cls = shade_item<ET>(P, it, (uint32_t)pending, pid, rays, nan_count);
             ++it;
             if (cls == CLS_CAND) { pending = -1; load_candidate(); }
             else if (cls == CLS_NONE) pending = -1;                       // absorbed, missed, depth exhausted: path over
@@ -662,15 +670,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
 }
 
 // ------------------------------------------------------------------ accumulate (lib.rs:95-100)
-__global__ void __launch_bounds__(256) k_accumulate(WaveParams P, float4* __restrict__ accum) {
+struct AccumPtrs { float4* p[RBRT_MAX_FRAMES]; };
+__global__ void __launch_bounds__(256) k_accumulate(WaveParams P, AccumPtrs A) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t f = blockIdx.y;                                        // frame of the batch
     if (j >= P.paths_px) return;
     uint32_t row, col;
-    if (!shard_pixel(P.sh, P.cam, j, row, col)) return;
-    size_t px = (size_t)row * P.cam.width + col;
+    if (!shard_pixel(P.sh, P.cam[0], j, row, col)) return;
+    size_t px = (size_t)row * P.cam[0].width + col;
+    float4* __restrict__ accum = A.p[f];
     float4 acc = accum[px];
     for (uint32_t s = 0; s < P.s_count; ++s) {
-        float4 c = P.out[(size_t)s * P.paths_px + j];
+        float4 c = P.out[((size_t)f * P.s_count + s) * P.paths_px + j];
         acc.x = XADD(acc.x, c.x); acc.y = XADD(acc.y, c.y); acc.z = XADD(acc.z, c.z);
     }
     accum[px] = acc;
@@ -785,9 +796,18 @@ static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
     return RBRT_OK;
 }
 
-int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rbrt_render_opts* opts,
-                 float4* d_accum, cudaStream_t st, rbrt_stats* stats) {
+// Renders n_frames (1..RBRT_MAX_FRAMES) frames of ONE scene — a camera and a Philox key each, same image size and
+// sample count — in the same wavefront batches: a rank's share of a frame can be small (1/8 of C3: launches of
+// 0.3-1 M rays that run at a third of the dense rate and each end in a drain as long as their slowest ray), and two
+// or four frames per batch give the kernels the size they have on fewer GPUs.  Every path keeps its own (pixel,
+// sample, frame) identity, so each image is bit-identical to a lone render of that frame.
+int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
+                 const rbrt_render_opts* opts, float4* const* d_accum, cudaStream_t st, rbrt_stats* stats) {
+    if (!n_frames || n_frames > RBRT_MAX_FRAMES) { set_error("n_frames must be 1..%d", RBRT_MAX_FRAMES); return RBRT_E_INVALID; }
+    const rbrt_camera& cam = cams[0];
     const uint32_t W = cam.img_width_pix, H = cam.img_height_pix;
+    for (uint32_t f = 1; f < n_frames; ++f)
+        if (cams[f].img_width_pix != W || cams[f].img_height_pix != H) { set_error("frames of one batch must have the same image size"); return RBRT_E_INVALID; }
     if (!W || !H || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
     if ((uint64_t)W * H > 0x7FFFFFFFull) { set_error("image too large"); return RBRT_E_INVALID; }
     rbrt_render_opts o{}; if (opts) o = *opts;
@@ -811,7 +831,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
     const uint32_t P = sh.tiles_mine * 32;
     cudaEvent_t ev0, ev1;
     CKR(cudaEventCreate(&ev0)); CKR(cudaEventCreate(&ev1));
-    CKR(cudaMemsetAsync(d_accum, 0, 16ull * W * H, st));
+    for (uint32_t f = 0; f < n_frames; ++f) CKR(cudaMemsetAsync(d_accum[f], 0, 16ull * W * H, st));
     uint32_t launches = 0, iterations = 0, batch_iters = 0;
     WaveBuffers& wb = device_wave_buffers(sc.device, (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT));
     CKR(cudaEventRecord(ev0, st));
@@ -823,9 +843,10 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         uint32_t target = o.batch_paths;
         if (!target) {
             const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
-            const uint64_t want = std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * P, 1ull << 27);
-            const uint64_t want_sb = std::max<uint64_t>(want / P, 1);                       // whole samples per batch
-            if (wb.cap >= want_sb * P && wb.depth_cap >= max_depth) target = (uint32_t)want;   // the pool already holds it: no driver query
+            const uint64_t PF = (uint64_t)P * n_frames;                                       // paths of one sample of every frame of the batch
+            const uint64_t want = std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * PF, 1ull << 27);
+            const uint64_t want_sb = std::max<uint64_t>(want / PF, 1);                      // whole samples per batch
+            if (wb.cap >= want_sb * PF && wb.depth_cap >= max_depth) target = (uint32_t)want;  // the pool already holds it: no driver query
                                                                                             // (cudaMemGetInfo takes tens of ms at times)
             else {
                 size_t free_b = 0, total_b = 0;
@@ -835,15 +856,20 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
             }
         }
-        uint32_t S_b = target / P; if (S_b < 1) S_b = 1; if (S_b > sh.s1 - sh.s0) S_b = sh.s1 - sh.s0;
-        if ((uint64_t)S_b * P > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
-        const uint32_t cap = S_b * P;
+        uint32_t S_b = target / (P * n_frames); if (S_b < 1) S_b = 1; if (S_b > sh.s1 - sh.s0) S_b = sh.s1 - sh.s0;
+        if ((uint64_t)S_b * P * n_frames > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
+        const uint32_t cap = S_b * P * n_frames;
         int rc = ensure_wave_buffers(wb, cap, max_depth);
         if (rc) return rc;
         CKR(cudaMemsetAsync(wb.stats, 0, 8 * ST_COUNT, st));
         WaveParams wp;
-        wp.S = sc.dev; wp.cam = make_cam(cam); wp.sh = sh;
-        wp.key0 = (uint32_t)o.seed; wp.key1 = (uint32_t)(o.seed >> 32);
+        wp.S = sc.dev; wp.sh = sh; wp.n_frames = n_frames;
+        for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) {
+            const uint32_t g = f < n_frames ? f : 0;
+            const uint64_t seed = seeds ? seeds[g] : o.seed;
+            wp.cam[f] = make_cam(cams[g]); wp.key0[f] = (uint32_t)seed; wp.key1[f] = (uint32_t)(seed >> 32);
+        }
+        AccumPtrs ap; for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) ap.p[f] = d_accum[f < n_frames ? f : 0];
         wp.cap = wb.cap; wp.paths_px = P; wp.fd_paths_px = make_fastdiv(P); wp.max_depth = max_depth;
         const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
         wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
@@ -878,6 +904,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
         };
         for (uint32_t s_base = sh.s0; s_base < sh.s1; s_base += S_b) {
             wp.s_base = s_base; wp.s_count = (sh.s1 - s_base < S_b) ? sh.s1 - s_base : S_b;
+            wp.fd_s_count = make_fastdiv(wp.s_count);
             CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
             if (et) k_generate<true><<<grid, 256, 0, st>>>(wp); else k_generate<false><<<grid, 256, 0, st>>>(wp);
             ++launches;
@@ -904,7 +931,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
                 if (time_kernels) CKR(cudaEventRecord(next_event(), st));
                 if (it < max_depth) { if (et) k_shade<true><<<grid, 256, 0, st>>>(wp, it); else k_shade<false><<<grid, 256, 0, st>>>(wp, it); ++launches; }
             }
-            k_accumulate<<<(P + 255) / 256, 256, 0, st>>>(wp, d_accum); ++launches;
+            k_accumulate<<<dim3((P + 255) / 256, n_frames), 256, 0, st>>>(wp, ap); ++launches;
             k_sum_rays<<<1, 64, 0, st>>>(wp); ++launches;
             CKR(cudaGetLastError());
         }
@@ -924,7 +951,7 @@ int render_accum(const Scene& sc, const rbrt_camera& cam, uint32_t spp, const rb
             uint32_t w = W - tx * 8 < 8 ? W - tx * 8 : 8, hh = H - ty * 4 < 4 ? H - ty * 4 : 4;
             valid_px += (uint64_t)w * hh;
         }
-        stats->paths = valid_px * (sh.s1 - sh.s0);
+        stats->paths = valid_px * (sh.s1 - sh.s0) * n_frames;
         stats->ms_device = ms; stats->launches = launches; stats->iterations = iterations;
         if (P && sh.s1 > sh.s0 && (o.flags & RBRT_OPT_TIME_KERNELS)) {
             double tr = 0;

@@ -1,120 +1,163 @@
-"""FramePipeline — several render_scene calls in flight on one GPU (one per CUDA stream).
+"""FramePipeline — a SEQUENCE of render_scene calls kept in flight on one GPU.
 
-A frame of the wavefront tracer ends with a sparse phase: the last bounce iterations and the tail kernel
-are bounded by the latency of their longest path (C3: ~2 ms of a 38 ms frame on one GPU, ~1.7 ms of the
-6.4 ms a rank spends on its eighth of the frame), during which most of the GPU idles.  The reference
-renders one image per process, so nothing can hide that there; a host that renders a SEQUENCE of images
-(an animation, a camera sweep, progressive refinement) can: frame k+1 is enqueued on a second stream with
-its own pool of wavefront state (RBRT_OPT_POOL_*) while frame k is still finishing, and its dense first
-bounces fill the SMs frame k's sparse phase leaves empty.  Every frame is computed by exactly the same
-kernels on the same inputs as a lone render_scene call, so images stay bit-identical (tests).
+A frame of the wavefront tracer ends with a sparse phase: the last bounce iterations and the tail kernel are bounded
+by the latency of their longest path (C3: ~2.7 ms of a 36 ms frame on one GPU, ~1.7 ms of the 6.4 ms a rank spends on
+its eighth of the frame), during which most of the GPU idles; and a rank's share of a frame on 8 GPUs is small enough
+that its launches run well below the dense rate.  The reference renders one image per process, so nothing can hide
+that there; a host that renders a sequence of images (an animation, a camera sweep, progressive refinement) can:
 
-    pipe = FramePipeline(width, height, depth=2)
+* `depth` frames (groups) in flight: each is enqueued on its own stream with its own pool of wavefront state
+  (RBRT_OPT_POOL_*), so the dense first bounces of the next one fill the SMs the previous one's tail leaves empty;
+* `frames_per_batch` frames of the same scene rendered TOGETHER in the same wavefront batches
+  (rbrt_gpu_render_accum_device_frames), which gives the kernels of a small shard the size they have on fewer GPUs.
+
+Every frame is computed by the same kernels on the same inputs as a lone render_scene call — each path keeps its own
+(pixel, sample, frame) identity — so images stay bit-identical (tests).
+
+    pipe = FramePipeline(width, height, depth=2, frames_per_batch=1)
     for cam, scene in frames:
-        done = pipe.submit(cam, spp, scene)      # returns the frame submitted `depth` calls ago (or None)
+        for image, tag in pipe.submit(cam, spp, scene, tag=...):     # frames that finished meanwhile, in order
+            ...
     rest = pipe.drain()
 
-With torch.distributed initialised every rank calls submit() in the same order; the per-frame reduce of the
-f32 accumulation buffers (dist.py) is enqueued on the frame's stream and rank 0 gets the images.
+With torch.distributed initialised every rank calls submit() in the same order; the reduce of the f32 accumulation
+buffers to rank 0 (dist.py; one per group) is enqueued on the group's stream and rank 0 gets the images.
 """
-import numpy as np
+import ctypes as C
 
 from . import _abi
 from .render import ImageBuffer, make_opts
 
 
 class _Slot:
-    def __init__(self, torch, n_px, host_output, hdr):
+    def __init__(self, torch, n_px, fpb, host_output, hdr):
         self.stream = torch.cuda.Stream()
-        self.accum = torch.empty(n_px * 4, dtype=torch.float32, device="cuda")
-        self.out = torch.empty(n_px * 3, dtype=torch.float32 if hdr else torch.uint8, device="cuda")
-        self.host = torch.empty(n_px * 3, dtype=self.out.dtype, pin_memory=True) if host_output else None
+        self.accum = torch.empty((fpb, n_px * 4), dtype=torch.float32, device="cuda")
+        self.out = torch.empty((fpb, n_px * 3), dtype=torch.float32 if hdr else torch.uint8, device="cuda")
+        self.host = torch.empty((fpb, n_px * 3), dtype=self.out.dtype, pin_memory=True) if host_output else None
         self.done = torch.cuda.Event()
         self.busy = False
-        self.keep = None       # the scene (and anything else) that must outlive the frame in flight
-        self.tag = None
+        self.keep = None       # the scene (and anything else) that must outlive the group in flight
+        self.tags = []
 
 
 class FramePipeline:
-    def __init__(self, width, height, depth=2, host_output=True, hdr=False, shard_mode=_abi.SHARD_TILES):
+    def __init__(self, width, height, depth=2, host_output=True, hdr=False, shard_mode=_abi.SHARD_TILES, frames_per_batch=1):
         import torch
         import torch.distributed as dist
         if depth not in (1, 2, 3, 4):
             raise ValueError("depth must be 1..4 (the library keeps four pools of wavefront state per device)")
+        if not 1 <= frames_per_batch <= _abi.MAX_FRAMES:
+            raise ValueError(f"frames_per_batch must be 1..{_abi.MAX_FRAMES}")
         self._torch, self._dist = torch, dist
-        self.width, self.height, self.depth, self.hdr = int(width), int(height), depth, hdr
+        self.width, self.height, self.depth, self.hdr, self.fpb = int(width), int(height), depth, hdr, int(frames_per_batch)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.shard_mode = shard_mode
-        self._slots = [_Slot(torch, self.width * self.height, host_output and self.rank == 0, hdr) for _ in range(depth)]
-        self._n = 0
+        self._slots = [_Slot(torch, self.width * self.height, self.fpb, host_output and self.rank == 0, hdr) for _ in range(depth)]
+        self._n = 0                  # groups launched
+        self._pending = []           # frames of the group being collected: (cam_c, seed, tag)
+        self._pending_key = None     # (scene, spp, opts) the pending frames share
+        self._pending_hv = None
         self._lib = _abi.lib()
 
     # ------------------------------------------------------------------ internals
     def _collect(self, slot):
-        """Wait for the frame in `slot` and hand out its result (rank 0: image; other ranks: None)."""
+        """Wait for the group in `slot`; returns its frames as [(image, tag)] (rank 0: images; other ranks: None)."""
         slot.done.synchronize()
         slot.busy = False
-        keep, tag = slot.keep, slot.tag
-        slot.keep = slot.tag = None
-        res = None
-        if self.rank == 0:
-            src = slot.host if slot.host is not None else slot.out
-            if slot.host is not None:
-                arr = slot.host.numpy().reshape(self.height, self.width, 3).copy()
-                res = arr if self.hdr else ImageBuffer(arr)
-            else:
-                res = src          # device tensor, valid until the slot is reused
-        return res, tag, keep
+        tags, slot.tags, slot.keep = slot.tags, [], None
+        res = []
+        for k, tag in enumerate(tags):
+            img = None
+            if self.rank == 0:
+                if slot.host is not None:
+                    arr = slot.host[k].numpy().reshape(self.height, self.width, 3).copy()
+                    img = arr if self.hdr else ImageBuffer(arr)
+                else:
+                    with self._torch.cuda.stream(slot.stream):   # a copy ordered before the slot's next group overwrites it
+                        img = slot.out[k].clone()
+            res.append((img, tag))
+        if self.rank == 0 and slot.host is None and tags:
+            slot.stream.synchronize()                          # the copies above (the group itself finished long ago)
+        return res
 
-    # ------------------------------------------------------------------ API
-    def submit(self, cam, num_samples, scene, tag=None, keep=None, **opts):
-        """Enqueue render_scene(cam, num_samples, scene) and return at once.  Returns (image, tag) of the frame whose
-        slot is being reused — the one submitted `depth` calls earlier — or None while the pipeline fills.  `scene`
-        must stay alive (not closed) until its frame has been returned; it is held here until then."""
+    def _launch(self):
+        """Enqueue the pending group on the next slot; returns the frames of the group that slot held before."""
         torch, dist = self._torch, self._dist
+        frames, (scene, spp, opt_items) = self._pending, self._pending_key
+        self._pending, self._pending_key = [], None
         slot = self._slots[self._n % self.depth]
-        finished = None
-        if slot.busy:
-            img, t, _ = self._collect(slot)
-            finished = (img, t)
-        cam_c = cam.to_c() if hasattr(cam, "to_c") else cam
-        handle = scene.handle() if hasattr(scene, "handle") else scene
-        W, H = int(cam_c.img_width_pix), int(cam_c.img_height_pix)
-        if (W, H) != (self.width, self.height):
-            raise ValueError("camera size differs from the pipeline's")
+        finished = self._collect(slot) if slot.busy else []
+        opts = dict(opt_items)
         sm, sr, sc = opts.pop("shard_mode", _abi.SHARD_NONE), opts.pop("shard_rank", 0), opts.pop("shard_count", 1)
         if self.world > 1:                                    # one process per GPU: the process group decides the shard
             sm, sr, sc = self.shard_mode, self.rank, self.world
         o = make_opts(shard_mode=sm, shard_rank=sr, shard_count=sc, pool=self._n % self.depth, **opts)
+        handle = scene.handle() if hasattr(scene, "handle") else scene
+        nf, W, H = len(frames), self.width, self.height
         s = slot.stream
         with torch.cuda.stream(s):
-            # stats = NULL: the call only enqueues (no event synchronisation inside the library)
-            _abi.check(self._lib.rbrt_gpu_render_accum_device(handle, cam_c, int(num_samples), o, slot.accum.data_ptr(), s.cuda_stream, None))
+            # stats = NULL: the calls only enqueue (no event synchronisation inside the library)
+            if nf == 1:
+                cam_c, seed, _ = frames[0]
+                o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+                _abi.check(self._lib.rbrt_gpu_render_accum_device(handle, cam_c, int(spp), o, slot.accum[0].data_ptr(), s.cuda_stream, None))
+            else:
+                cams = (_abi.CameraC * nf)(*[f[0] for f in frames])
+                seeds = (C.c_uint64 * nf)(*[int(f[1]) & 0xFFFFFFFFFFFFFFFF for f in frames])
+                accs = (C.c_void_p * nf)(*[slot.accum[k].data_ptr() for k in range(nf)])
+                _abi.check(self._lib.rbrt_gpu_render_accum_device_frames(handle, cams, seeds, nf, int(spp), o, accs, s.cuda_stream, None))
             if self.world > 1:
-                dist.reduce(slot.accum, dst=0, op=dist.ReduceOp.SUM)
+                dist.reduce(slot.accum[:nf], dst=0, op=dist.ReduceOp.SUM)
             if self.rank == 0:
-                rgb, hdr = (None, slot.out.data_ptr()) if self.hdr else (slot.out.data_ptr(), None)
-                _abi.check(self._lib.rbrt_gpu_finalize_device(slot.accum.data_ptr(), W, H, int(num_samples), rgb, hdr, s.cuda_stream))
+                for k in range(nf):
+                    rgb, hdr = (None, slot.out[k].data_ptr()) if self.hdr else (slot.out[k].data_ptr(), None)
+                    _abi.check(self._lib.rbrt_gpu_finalize_device(slot.accum[k].data_ptr(), W, H, int(spp), rgb, hdr, s.cuda_stream))
                 if slot.host is not None:
-                    slot.host.copy_(slot.out, non_blocking=True)
+                    slot.host[:nf].copy_(slot.out[:nf], non_blocking=True)
             slot.done.record(s)
-        slot.busy, slot.keep, slot.tag = True, (scene, keep), tag
+        slot.busy, slot.keep, slot.tags = True, (scene, [f[0] for f in frames]), [f[2] for f in frames]
         self._n += 1
         return finished
 
+    # ------------------------------------------------------------------ API
+    def submit(self, cam, num_samples, scene, tag=None, seed=0, **opts):
+        """Queue render_scene(cam, num_samples, scene) and return at once.  Returns the list of (image, tag) of the frames
+        that left the pipeline meanwhile (possibly empty), in submission order.  `scene` must stay alive (not closed) until
+        its frame has been returned; it is held here until then.  Frames are launched in groups of `frames_per_batch`
+        that share scene, sample count and options; a frame that differs in one of them starts a new group."""
+        cam_c = cam.to_c() if hasattr(cam, "to_c") else cam
+        if (int(cam_c.img_width_pix), int(cam_c.img_height_pix)) != (self.width, self.height):
+            raise ValueError("camera size differs from the pipeline's")
+        h = scene.handle() if hasattr(scene, "handle") else scene
+        hv = h.value if hasattr(h, "value") else int(h)       # the same scene = the same library handle
+        key = (scene, int(num_samples), tuple(sorted(opts.items())))
+        finished = []
+        if self._pending and (self._pending_hv != hv or self._pending_key[1:] != key[1:]):
+            finished += self._launch()
+        self._pending_hv = hv
+        self._pending.append((cam_c, seed, tag))
+        self._pending_key = key
+        if len(self._pending) == self.fpb:
+            finished += self._launch()
+        return finished
+
+    def flush(self):
+        """Launch a partially filled group now; returns the frames that left the pipeline meanwhile."""
+        return self._launch() if self._pending else []
+
     def drain(self):
-        """Wait for every frame still in flight; returns their (image, tag) in submission order."""
-        out = []
+        """Launch what is pending and wait for everything in flight; returns the (image, tag) in submission order."""
+        out = self.flush()
         for k in range(self.depth):
             slot = self._slots[(self._n + k) % self.depth]
             if slot.busy:
-                img, t, _ = self._collect(slot)
-                out.append((img, t))
+                out += self._collect(slot)
         return out
 
     def wait_on(self, stream=None):
-        """Make `stream` (default: the current stream) wait for everything enqueued so far — for device-side timing."""
+        """Make `stream` (default: the current stream) wait for everything launched so far — for device-side timing."""
         torch = self._torch
         stream = stream or torch.cuda.current_stream()
         for slot in self._slots:

@@ -26,7 +26,8 @@ def step():
     sc = bench.make_scene(spheres, meshes, pinned)
     sc.handle()
     t1 = time.perf_counter()
-    retire(pipe.submit(cam, spp, sc, tag=sc, seed=1, **kw))
+    for fin in pipe.submit(cam, spp, sc, tag=sc, seed=1, **kw):
+        retire(fin)
     return (t1 - t0) * 1e3
 
 for _ in range(4):

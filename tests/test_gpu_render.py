@@ -71,35 +71,45 @@ def test_mesh_scene_and_batching(gpu, oracle):
         assert_images_equal(R.render_scene_hdr(cam, 6, scene, seed=9, **kw), ref, f"opts {kw}")
 
 
-@pytest.mark.parametrize("depth", [1, 2, 3, 4])
-def test_frame_pipeline_is_bit_identical(gpu, depth):
-    """FramePipeline: frames in flight on separate streams and wavefront pools (RBRT_OPT_POOL_*) give the same images
-    as lone render_scene calls — different seeds, two scenes, host (pinned) and device outputs, tile-shard options."""
+@pytest.mark.parametrize("depth,fpb", [(1, 1), (2, 1), (3, 1), (4, 1), (2, 2), (1, 3), (2, 4)])
+def test_frame_pipeline_is_bit_identical(gpu, depth, fpb):
+    """FramePipeline: groups of frames in flight on separate streams and wavefront pools (RBRT_OPT_POOL_*), `fpb` frames
+    of a scene rendered together in the same batches (rbrt_gpu_render_accum_device_frames), give the same images as lone
+    render_scene calls — different cameras, seeds and sample counts, two scenes, host (pinned) and device outputs, tile shards."""
     import torch
-    cam = S.example_camera(96, 64)
+    from rbrt_b200 import synth
+    cb = synth.example_camera_blueprint()
+    cams = [R.Camera.new(Vec3(cb.camera_position.x + 0.3 * k, cb.camera_position.y, cb.camera_position.z + 0.2 * k), cb.camera_look_at,
+                         cb.camera_up, 64, 96, cb.camera_focal_length_mm) for k in range(3)]
     scenes = [S.small_mesh_scene(3), S.spheres_scene()]
-    jobs = [(scenes[k % 2], 5, 100 + k) for k in range(7)]
-    want = [R.render_scene(cam, spp, sc, seed=seed).pixels for sc, spp, seed in jobs]
-    pipe = R.FramePipeline(96, 64, depth=depth)
+    # runs of frames of the same scene and spp (they can share a batch), then changes of scene / spp that force a new group
+    jobs = [(0, 5), (0, 5), (0, 5), (0, 5), (0, 5), (1, 5), (1, 5), (1, 3), (0, 3), (0, 3), (0, 3)]
+    jobs = [(scenes[si], spp, 100 + k, cams[k % 3]) for k, (si, spp) in enumerate(jobs)]
+    want = [R.render_scene(cam, spp, sc, seed=seed).pixels for sc, spp, seed, cam in jobs]
+    pipe = R.FramePipeline(96, 64, depth=depth, frames_per_batch=fpb)
     got = []
-    for k, (sc, spp, seed) in enumerate(jobs):
-        fin = pipe.submit(cam, spp, sc, tag=k, seed=seed)
-        assert (fin is None) == (k < depth)
-        if fin is not None:
-            got.append(fin)
+    for k, (sc, spp, seed, cam) in enumerate(jobs):
+        got += pipe.submit(cam, spp, sc, tag=k, seed=seed)
     got += pipe.drain()
-    assert [t for _, t in got] == list(range(7))
+    assert [t for _, t in got] == list(range(len(jobs)))
     for (img, t), w in zip(got, want):
         assert np.array_equal(img.pixels, w), f"frame {t} differs"
-    # device output + HDR + an explicit tile shard
-    hdr = R.render_scene_hdr(cam, 4, scenes[0], seed=3, shard_mode=_abi.SHARD_TILES, shard_rank=1, shard_count=3)
-    pipe = R.FramePipeline(96, 64, depth=depth, host_output=False, hdr=True)
-    for _ in range(depth + 1):
-        pipe.submit(cam, 4, scenes[0], seed=3, shard_mode=_abi.SHARD_TILES, shard_rank=1, shard_count=3)
-    for img, _ in pipe.drain():
-        assert np.array_equal(img.cpu().numpy().reshape(64, 96, 3), hdr)
+    # device output + HDR + an explicit tile shard + a batch limit that splits the group's samples over several batches
+    for extra in [{}, {"batch_paths": 96 * 64 * 2}]:
+        kw = dict(shard_mode=_abi.SHARD_TILES, shard_rank=1, shard_count=3, **extra)
+        hdrs = [R.render_scene_hdr(cams[k % 3], 4, scenes[0], seed=3 + k, **kw) for k in range(fpb + 1)]
+        pipe = R.FramePipeline(96, 64, depth=depth, host_output=False, hdr=True, frames_per_batch=fpb)
+        out = []
+        for k in range(fpb + 1):
+            out += [(i.cpu().numpy().copy(), t) for i, t in pipe.submit(cams[k % 3], 4, scenes[0], tag=k, seed=3 + k, **kw)]
+        out += [(i.cpu().numpy().copy(), t) for i, t in pipe.drain()]
+        assert [t for _, t in out] == list(range(fpb + 1))
+        for (img, t) in out:
+            assert np.array_equal(img.reshape(64, 96, 3), hdrs[t]), f"hdr frame {t} differs ({extra})"
     with pytest.raises(ValueError):
         R.FramePipeline(8, 8, depth=5)
+    with pytest.raises(ValueError):
+        R.FramePipeline(8, 8, frames_per_batch=5)
     with pytest.raises(ValueError):
         pipe.submit(S.example_camera(8, 8), 1, scenes[1])
 
