@@ -55,6 +55,11 @@ extern "C" {
     /// then 1/spp, sqrt, x256, saturating u8 on the device.  `opts.flags` bits 3-4 (RBRT_OPT_POOL_*) pick one of four wavefront pools.
     pub fn rbrt_gpu_render_accum_device(scene: *const RbrtScene, cam: *const RbrtCamera, num_samples: u32, opts: *const RbrtRenderOpts,
                                         d_accum: *mut c_void, stream: *mut c_void, stats: *mut RbrtStats) -> c_int;
+    /// The same for up to four frames of one scene rendered together in the same wavefront batches (one camera, seed and
+    /// accumulation buffer per frame; opts.seed is ignored).
+    pub fn rbrt_gpu_render_accum_device_frames(scene: *const RbrtScene, cams: *const RbrtCamera, seeds: *const u64, n_frames: u32,
+                                               num_samples: u32, opts: *const RbrtRenderOpts, d_accum: *const *mut c_void,
+                                               stream: *mut c_void, stats: *mut RbrtStats) -> c_int;
     pub fn rbrt_gpu_finalize_device(d_accum: *const c_void, width: u32, height: u32, num_samples: u32, d_rgb: *mut c_void,
                                     d_hdr: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rbrt_gpu_release_cache() -> c_int;
