@@ -12,8 +12,10 @@ path) — the reference's `render_scene(cam, spp, scene)` (lib.rs:75-124).  Rays
   value      whole-job Mrays/s with the scene (SoA buffers + LBVH) already resident in HBM; the timed region is
              K x (render -> [NCCL reduce to rank 0] -> finalize (1/spp, sqrt, x256, saturating u8) on the device), with
              --frames-in-flight frames (default 2) in flight on their own streams (rbrt_b200.FramePipeline): the sparse,
-             latency-bound last bounces of one frame overlap the dense first bounces of the next.  `single_frame` is the
-             same measurement one frame at a time.  The last pipelined image is checked against the single-frame one.
+             latency-bound last bounces of one frame overlap the dense first bounces of the next; on 4 / 8 GPUs 2 / 4
+             consecutive frames are also rendered in the same wavefront batches (--frames-per-batch), which gives a rank's
+             launches the size they have on fewer GPUs.  `single_frame` is the same measurement one frame at a time.  The
+             last pipelined image is checked against the single-frame one.
   e2e        the same metric through the reference-facing call with HOST buffers: every step uploads the
              triangle soup from pinned host memory (rbrt_gpu_scene_create: H2D + LBVH build), renders
              (rbrt_gpu_render / the multi-rank building blocks) and copies the RGB8 image back to the host.

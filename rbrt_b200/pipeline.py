@@ -54,7 +54,7 @@ class FramePipeline:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.shard_mode = shard_mode
-        self._slots = [_Slot(torch, self.width * self.height, self.fpb, host_output and self.rank == 0, hdr) for _ in range(depth)]
+        self._slots = [self._make_slot(host_output and self.rank == 0) for _ in range(depth)]
         self._n = 0                  # groups launched
         self._pending = []           # frames of the group being collected: (cam_c, seed, tag)
         self._pending_key = None     # (scene, spp, opts) the pending frames share
@@ -62,6 +62,9 @@ class FramePipeline:
         self._lib = _abi.lib()
 
     # ------------------------------------------------------------------ internals
+    def _make_slot(self, host_output):
+        return _Slot(self._torch, self.width * self.height, self.fpb, host_output, self.hdr)
+
     def _collect(self, slot):
         """Wait for the group in `slot`; returns its frames as [(image, tag)] (rank 0: images; other ranks: None)."""
         slot.done.synchronize()
@@ -84,12 +87,18 @@ class FramePipeline:
 
     def _launch(self):
         """Enqueue the pending group on the next slot; returns the frames of the group that slot held before."""
-        torch, dist = self._torch, self._dist
         frames, (scene, spp, opt_items) = self._pending, self._pending_key
         self._pending, self._pending_key = [], None
         slot = self._slots[self._n % self.depth]
         finished = self._collect(slot) if slot.busy else []
-        opts = dict(opt_items)
+        self._enqueue(slot, frames, scene, spp, dict(opt_items))
+        slot.busy, slot.keep, slot.tags = True, (scene, [f[0] for f in frames]), [f[2] for f in frames]
+        self._n += 1
+        return finished
+
+    def _enqueue(self, slot, frames, scene, spp, opts):
+        """Enqueue one group of frames (render -> [reduce] -> finalize -> [copy to pinned host memory]) on the slot's stream."""
+        torch, dist = self._torch, self._dist
         sm, sr, sc = opts.pop("shard_mode", _abi.SHARD_NONE), opts.pop("shard_rank", 0), opts.pop("shard_count", 1)
         if self.world > 1:                                    # one process per GPU: the process group decides the shard
             sm, sr, sc = self.shard_mode, self.rank, self.world
@@ -117,9 +126,6 @@ class FramePipeline:
                 if slot.host is not None:
                     slot.host[:nf].copy_(slot.out[:nf], non_blocking=True)
             slot.done.record(s)
-        slot.busy, slot.keep, slot.tags = True, (scene, [f[0] for f in frames]), [f[2] for f in frames]
-        self._n += 1
-        return finished
 
     # ------------------------------------------------------------------ API
     def submit(self, cam, num_samples, scene, tag=None, seed=0, **opts):
