@@ -362,7 +362,8 @@ def run_gpu(args):
 
     # ---- resident arm (timed region): `steps` frames through the FramePipeline, `frames_in_flight` of them in flight on
     #      their own streams and wavefront pools, so the sparse last bounces of one frame overlap the next frame's first
-    fpb = args.frames_per_batch or (1 if world == 1 else min(4, world // 2) if world >= 4 else 1)   # a rank's batch ~ a frame's worth of paths
+    fpb = args.frames_per_batch or (1 if world == 1 else 2 if world < 8 else 4)     # measured: 2 GPUs 17.10 -> 16.55 ms/frame, 4 GPUs 9.22 -> 8.60 with 2;
+                                                                                    # 1/8 shard on one GPU 5.15 -> 4.29 with 4 (profiles/r1_summary.md)
     if args.workload in SAMPLE_SHARDED:
         fpb = args.frames_per_batch or 1
     pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode, frames_per_batch=fpb)
@@ -537,8 +538,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--frames-per-batch", type=int, default=0, choices=[0, 1, 2, 3, 4],
-                    help="frames rendered together in the same wavefront batches in the timed region (0 = 1 on 1-2 GPUs, 2 on 4, 4 on 8: "
-                         "a rank's batch then holds about one frame's worth of paths)")
+                    help="frames rendered together in the same wavefront batches in the timed region (0 = 1 on one GPU, 2 on 2-7, 4 on 8: "
+                         "a rank's launches then have about the size they have on fewer GPUs)")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2, 3, 4],
                     help="frames kept in flight on separate streams in the timed region (1 = one frame at a time)")
     args = ap.parse_args()
