@@ -14,9 +14,16 @@
  * 0 on success and a non-zero RBRT_E_* code on failure (message via rbrt_last_error()).
  * The CPU checker used by the tests mirrors these shapes; it is never linked here.
  *
- * One process drives one GPU (rbrt_gpu_init(device)); multi-GPU renders run one process per
- * GPU, each rendering a shard selected by rbrt_render_opts.shard_*, and sum their
- * accumulation buffers with one NCCL reduce (see rbrt_gpu_render_accum_device).
+ * Multi-GPU is INSIDE this boundary, like the reference's one parallelism strategy is inside render_scene
+ * (rayon over columns, rbrt_lib/src/lib.rs:84-86).  Two set-ups, same entry points afterwards:
+ *   - one process, N GPUs:     rbrt_gpu_init_multi(devices, N, transport)
+ *   - one process per GPU:     rbrt_gpu_init(device); rank 0: rbrt_gpu_comm_unique_id(id); every rank:
+ *                              rbrt_gpu_comm_init_rank(id, rank, world)   (id travels over any side channel)
+ * Under a communicator rbrt_gpu_scene_create uploads and builds the LBVH ONCE (rank 0) and replicates the scene's
+ * device block to the other GPUs over NVLink (NCCL broadcast / peer copies); rbrt_gpu_render shards the image by
+ * interleaved 8x4-pixel tiles (or by sample range), every GPU finalises its own pixels and rank 0 gathers them.
+ * The explicit building blocks (rbrt_render_opts.shard_*, rbrt_gpu_render_accum_device) remain for hosts that
+ * place shards themselves.
  */
 #ifndef RBRT_GPU_H
 #define RBRT_GPU_H
@@ -102,7 +109,13 @@ typedef struct rbrt_hit {
 enum { RBRT_LANES_AVX = 8, RBRT_LANES_SSE = 4 };
 
 enum { RBRT_SHARD_NONE = 0, RBRT_SHARD_TILES = 1, RBRT_SHARD_SAMPLES = 2 };
-enum { RBRT_TRACE_BVH = 0, RBRT_TRACE_BRUTE = 1 };
+enum {
+    RBRT_TRACE_BVH = 0,        /* per-mesh LBVH (render: the wavefront kernels; rbrt_gpu_trace_rays: a plain one-lane-one-ray traversal) */
+    RBRT_TRACE_BRUTE = 1,      /* every triangle, the reference's own loop (triangle.rs:163-262) */
+    RBRT_TRACE_WAVEFRONT = 2   /* rbrt_gpu_trace_rays only: the caller's rays go through the RENDERER's own kernels — stage A
+                                  (spheres + mesh-AABB pre-test) and k_trace (persistent warps, warp-voted traversal, dynamic fetch) */
+};
+#define RBRT_MAX_FRAMES 4      /* frames one wavefront batch can hold (rbrt_gpu_render_accum_device_frames) */
 enum {
     RBRT_OPT_COUNT_VISITS = 1,   /* fill rbrt_stats.node_visits / tri_tests (instrumented kernels, slower) */
     RBRT_OPT_TIME_KERNELS = 2,   /* bracket every trace launch with CUDA events -> rbrt_stats.ms_trace */
@@ -114,11 +127,15 @@ enum {
     RBRT_OPT_POOL_MASK = 24
 };
 
+enum {
+    RBRT_SCENE_LOCAL = 1,     /* under a communicator: build on THIS rank only, no replication (renders of it are not auto-sharded) */
+    RBRT_SCENE_NO_SAH = 2     /* skip the SAH pass over the LBVH (tree rotations during the refit): the plain Morton-order tree */
+};
 typedef struct rbrt_scene_opts {
     uint32_t simd_lanes;     /* RBRT_LANES_*; 0 = 8 */
     uint32_t leaf_size;      /* max triangles per BVH leaf; 0 = default */
     float    box_pad_rel;    /* conservative padding of BVH boxes relative to the mesh extent; 0 = default (2e-5), <0 = none */
-    uint32_t reserved;
+    uint32_t flags;          /* RBRT_SCENE_* */
 } rbrt_scene_opts;
 
 typedef struct rbrt_render_opts {
@@ -189,6 +206,28 @@ int rbrt_transform_vertices(float* xyz, uint64_t n_vertices, float scale,
 /* Select the CUDA device this process renders on (one process per GPU). */
 int rbrt_gpu_init(int device);
 
+/* ---- multi-GPU set-up (see the head of this file) ---------------------------------------- */
+#define RBRT_COMM_ID_BYTES 128           /* = sizeof(ncclUniqueId) */
+enum {
+    RBRT_TRANSPORT_AUTO = 0,             /* one process: PEER when every GPU can map GPU 0's memory, else NCCL; process per GPU: NCCL */
+    RBRT_TRANSPORT_NCCL = 1,             /* NCCL broadcast / send-recv gather / reduce over NVLink */
+    RBRT_TRANSPORT_PEER = 2              /* one process only: the finalise kernel of every GPU stores its pixels straight into rank 0's
+                                            image through peer-mapped memory (compute + gather in ONE kernel), scene replicas by peer copies */
+};
+typedef struct rbrt_comm_info {
+    int32_t  active, world, rank, local_devices;   /* rank = global rank of this process's first device */
+    int32_t  transport;                            /* RBRT_TRANSPORT_* in use */
+    int32_t  nccl_version;                         /* of the library loaded at run time, 0 if none */
+    int32_t  devices[16];
+} rbrt_comm_info;
+/* One process, n_devices GPUs (devices == NULL: 0..n_devices-1).  The same device may be listed several times with
+ * RBRT_TRANSPORT_PEER (a one-GPU emulation of N ranks, used by the tests). */
+int rbrt_gpu_init_multi(const int* devices, int n_devices, int transport);
+int rbrt_gpu_comm_unique_id(uint8_t id_out[RBRT_COMM_ID_BYTES]);
+int rbrt_gpu_comm_init_rank(const uint8_t id[RBRT_COMM_ID_BYTES], int rank, int world);
+int rbrt_gpu_comm_info(rbrt_comm_info* out);
+int rbrt_gpu_comm_destroy(void);
+
 /* = create_scene_from_scene_blueprint (blueprints.rs:132-158) after material parsing: copies
  *   the inputs to 16-byte-aligned SoA device buffers, applies the reference's SIMD tail rule
  *   (mesh.rs:136-144 + triangle.rs:167), computes edges / unit normals / exact mesh AABB
@@ -208,7 +247,10 @@ int rbrt_gpu_scene_info(const rbrt_scene* scene, rbrt_scene_info* out);
 int rbrt_gpu_scene_destroy(rbrt_scene* scene);
 
 /* = render_scene (lib.rs:75-124).  rgb_out: caller-allocated W*H*3 bytes, row-major RGB8 =
- *   the layout of image::ImageBuffer<Rgb<u8>>.  opts / stats may be NULL.  HOST pointers. */
+ *   the layout of image::ImageBuffer<Rgb<u8>>.  opts / stats may be NULL.  HOST pointers.
+ *   Under a communicator (scene created collectively, opts->shard_count == 0) the call is collective: every rank makes
+ *   it, the image is sharded over all GPUs (opts->shard_mode: tiles by default, RBRT_SHARD_SAMPLES for sample ranges),
+ *   rank 0 receives the image (rgb_out may be NULL on the other ranks); stats are this process's own GPUs'. */
 int rbrt_gpu_render(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t num_samples,
                     const rbrt_render_opts* opts, uint8_t* rgb_out, rbrt_stats* stats);
 
@@ -237,6 +279,16 @@ int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_came
                                         uint32_t n_frames, uint32_t num_samples, const rbrt_render_opts* opts,
                                         void* const* d_accum_rgba_f32, void* cuda_stream, rbrt_stats* stats);
 
+/* The collective render with DEVICE outputs, enqueue-only when stats == NULL: n_frames (1..RBRT_MAX_FRAMES) frames of one scene
+ * (a camera and a seed each) -> per GPU: render its shard, finalise its own pixels -> gather on rank 0 into
+ * d_rgb_u8[f] (W*H*3 u8) and / or d_hdr_f32[f] (W*H*3 f32), device pointers on rank 0's GPU (ignored elsewhere; either
+ * array may be NULL).  Everything is ordered on cuda_stream (a stream of this process's first device).  Without a
+ * communicator this is render + finalise on one GPU.  Frames in flight at the same time use different streams and
+ * different pools (opts->flags, RBRT_OPT_POOL_*); every rank must issue its calls in the same order. */
+int rbrt_gpu_render_frames_device(const rbrt_scene* scene, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames,
+                                  uint32_t num_samples, const rbrt_render_opts* opts, void* const* d_rgb_u8,
+                                  void* const* d_hdr_f32, void* cuda_stream, rbrt_stats* stats);
+
 /* = lib.rs:101 + lib.rs:116-122: colour *= 1/spp; (sqrt(c)*256) as u8 (saturating).
  *   d_rgb_u8 (W*H*3) and d_hdr_f32 (W*H*3) are DEVICE pointers; either may be NULL. */
 int rbrt_gpu_finalize_device(const void* d_accum_rgba_f32, uint32_t width, uint32_t height,
@@ -249,14 +301,35 @@ int rbrt_gpu_finalize_device(const void* d_accum_rgba_f32, uint32_t width, uint3
 int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t n,
                         uint32_t trace_mode, rbrt_hit* hits_out, rbrt_stats* stats);
 
+/* Parity hook = RayScattering::scatter (materials.rs:4-12; lambertian.rs:11-24, metal.rs:12-25, dielectric.rs:11-60) for
+ * caller-supplied hits: item i scatters in_ray at (hit_point, hit_normal) off `material`, drawing from the Philox stream the
+ * renderer would use at (seed, pixel, sample, bounce).  out[i].scattered = scatter()'s return value; attenuation and out_ray as
+ * the reference leaves them (out_ray.origin = hit_point).  HOST pointers. */
+typedef struct rbrt_scatter_in {
+    rbrt_material material;
+    rbrt_ray      in_ray;
+    rbrt_vec3     hit_point, hit_normal;
+    uint32_t      pixel, sample, bounce;
+} rbrt_scatter_in;
+typedef struct rbrt_scatter_out { int32_t scattered; rbrt_vec3 attenuation; rbrt_ray out_ray; } rbrt_scatter_out;
+int rbrt_gpu_scatter(const rbrt_scatter_in* items, uint64_t n, uint64_t seed, rbrt_scatter_out* out);
+
 /* Primary rays exactly as the renderer generates them (cam.rs:64-82 with the Philox stream of
  * sample `sample_idx`), one per pixel, row-major.  HOST pointer, W*H rays. */
 int rbrt_gpu_primary_rays(const rbrt_camera* cam, uint64_t seed, uint32_t sample_idx,
                           rbrt_ray* rays_out);
 
 /* The wavefront state (ray / hit / queue buffers, tens of GB at full batch size) is pooled per device and kept
- * between renders and across scenes; this releases it.  Renders on one device must not run concurrently. */
+ * between renders and across scenes; this releases it (and the pooled scene blocks and the build scratch). */
 int rbrt_gpu_release_cache(void);
+
+/* Upper bound, in bytes, of ONE pool of wavefront state (there are up to four per device, one per frame in flight).
+ * 0 = default: as many paths as fit, <= 2^27 paths (24.7 GB at depth 50) and <= half of the free HBM.  A host that
+ * embeds the library next to other users of the GPU sets this; smaller pools mean more, smaller wavefront batches. */
+int rbrt_gpu_set_pool_limit(uint64_t max_bytes_per_pool);
+
+/* Threading: every entry point may be called from any thread; calls are serialised by one process-wide lock (the
+ * library keeps per-device pools).  Calls that only ENQUEUE work (stats == NULL) hold it for microseconds. */
 
 /* Thread-local message of the last failing call on this thread. */
 const char* rbrt_last_error(void);

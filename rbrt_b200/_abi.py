@@ -53,7 +53,26 @@ class HitC(C.Structure):
 
 class SceneOptsC(C.Structure):
     _fields_ = [("simd_lanes", C.c_uint32), ("leaf_size", C.c_uint32), ("box_pad_rel", C.c_float),
-                ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32)]
+
+
+class ScatterInC(C.Structure):  # rbrt_scatter_in
+    _fields_ = [("material", MaterialC), ("in_ray", RayC), ("hit_point", Vec3C), ("hit_normal", Vec3C),
+                ("pixel", C.c_uint32), ("sample", C.c_uint32), ("bounce", C.c_uint32)]
+
+
+class ScatterOutC(C.Structure):  # rbrt_scatter_out
+    _fields_ = [("scattered", C.c_int32), ("attenuation", Vec3C), ("out_ray", RayC)]
+
+
+class CommInfoC(C.Structure):  # rbrt_comm_info
+    _fields_ = [("active", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("local_devices", C.c_int32),
+                ("transport", C.c_int32), ("nccl_version", C.c_int32), ("devices", C.c_int32 * 16)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "devices"}
+        d["devices"] = list(self.devices)[:max(self.local_devices, 0)]
+        return d
 
 
 class RenderOptsC(C.Structure):
@@ -88,7 +107,10 @@ HIT_DTYPE = [("kind", "<i4"), ("elem_idx", "<u4"), ("tri_idx", "<u4"), ("t", "<f
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
-TRACE_BVH, TRACE_BRUTE = 0, 1
+TRACE_BVH, TRACE_BRUTE, TRACE_WAVEFRONT = 0, 1, 2
+SCENE_LOCAL, SCENE_NO_SAH = 1, 2
+TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_PEER = 0, 1, 2
+COMM_ID_BYTES = 128
 OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL, OPT_POOL_SHIFT = 1, 2, 4, 3
 MAX_FRAMES = 4          # frames one wavefront batch can hold (rbrt_gpu_render_accum_device_frames)
 HIT_NONE, HIT_SPHERE, HIT_MESH, HIT_TRIANGLE = -1, 0, 1, 2
@@ -101,6 +123,15 @@ GPU_SIGNATURES = {
     "rbrt_camera_new": (C.c_int, [Vec3C, Vec3C, Vec3C, C.c_uint32, C.c_uint32, C.c_float, P(CameraC)]),
     "rbrt_transform_vertices": (C.c_int, [P(C.c_float), C.c_uint64, C.c_float, Vec3C, Vec3C]),
     "rbrt_gpu_init": (C.c_int, [C.c_int]),
+    "rbrt_gpu_init_multi": (C.c_int, [P(C.c_int), C.c_int, C.c_int]),
+    "rbrt_gpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rbrt_gpu_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rbrt_gpu_comm_info": (C.c_int, [P(CommInfoC)]),
+    "rbrt_gpu_comm_destroy": (C.c_int, []),
+    "rbrt_gpu_set_pool_limit": (C.c_int, [C.c_uint64]),
+    "rbrt_gpu_scatter": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "rbrt_gpu_render_frames_device": (C.c_int, [C.c_void_p, P(CameraC), P(C.c_uint64), C.c_uint32, C.c_uint32, P(RenderOptsC),
+                                                P(C.c_void_p), P(C.c_void_p), C.c_void_p, P(StatsC)]),
     "rbrt_gpu_scene_create": (C.c_int, [P(SphereDescC), C.c_uint32, P(MeshDescC), C.c_uint32, P(SceneOptsC), P(C.c_void_p)]),
     "rbrt_gpu_scene_create_elements": (C.c_int, [P(ElementRefC), C.c_uint32, P(SphereDescC), C.c_uint32, P(TriangleDescC), C.c_uint32,
                                                 P(MeshDescC), C.c_uint32, P(SceneOptsC), P(C.c_void_p)]),

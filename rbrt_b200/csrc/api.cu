@@ -1,12 +1,15 @@
 // api.cu — the C-ABI of include/rbrt_gpu.h: scene upload (+LBVH build) and the render entry points.
 // There is NO CPU fallback: without a usable CUDA device every GPU entry point fails with
 // RBRT_E_NODEVICE / RBRT_E_CUDA and a message.
+// Every entry point takes the process-wide lock (api_mutex): the library keeps per-device pools (scene blocks,
+// wavefront state, build scratch), and the reference's render_scene may be called from any thread.
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include "bvh_build.cuh"
 #include "engine.cuh"
+#include "multi.cuh"
 
 namespace rbrt {
 
@@ -19,12 +22,20 @@ int cuda_fail(cudaError_t e, const char* what) {
     cudaGetLastError();
     return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RBRT_E_NODEVICE : RBRT_E_CUDA;
 }
+std::recursive_mutex& api_mutex() { static std::recursive_mutex m; return m; }
+static uint64_t g_pool_limit = 0;
+uint64_t pool_limit_bytes() { return g_pool_limit; }
+
 static int g_device = -1;
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 #define CKA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
+#define LOCK std::lock_guard<std::recursive_mutex> lock_(api_mutex())
+
+int current_device() { return g_device; }
+void set_current_device(int d) { g_device = d; }
 
 static int ensure_device() {
     if (g_device >= 0) { CKA(cudaSetDevice(g_device)); return RBRT_OK; }
@@ -40,45 +51,81 @@ static int ensure_device() {
     return RBRT_OK;
 }
 
+int device_sm_count(int device, int* out) {
+    static int cached[64] = {0};                                           // cudaGetDeviceProperties is slow (tens of ms at times)
+    if (!cached[device & 63]) {
+        int smc = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+        cached[device & 63] = smc;
+    }
+    *out = cached[device & 63];
+    return RBRT_OK;
+}
+
 // All device buffers of a scene are carved from ONE allocation, and a destroyed scene's block is kept for the next
 // scene of the same device (cudaMalloc / cudaFree synchronise the device and occasionally take tens to hundreds of ms;
 // an application that re-creates its scene every frame should not pay that).  rbrt_gpu_release_cache() frees them.
-struct ArenaBlock { void* p; size_t bytes; int device; };
+// A pooled block remembers the last work that was enqueued against its scene (one event per stream): renders that were
+// only ENQUEUED (stats == NULL) on non-blocking streams may still be reading it, so the block is not handed out again
+// before those events have completed.
+struct ArenaBlock { void* p; size_t bytes; int device; std::vector<cudaEvent_t> pending; };
 static std::vector<ArenaBlock> g_arena_pool;
+static void wait_block(ArenaBlock& b) {
+    for (cudaEvent_t e : b.pending) { cudaEventSynchronize(e); cudaEventDestroy(e); }
+    b.pending.clear();
+}
 static void arena_release_all() {
     int cur = 0; cudaGetDevice(&cur);
-    for (auto& b : g_arena_pool) { cudaSetDevice(b.device); cudaFree(b.p); }
+    for (auto& b : g_arena_pool) { cudaSetDevice(b.device); wait_block(b); cudaFree(b.p); }
     g_arena_pool.clear();
     cudaSetDevice(cur);
 }
-static int arena_alloc(Scene* sc, size_t bytes, char** base) {
+// the caller has made `device` current
+int arena_alloc(int device, size_t bytes, char** base, size_t* got_bytes) {
     if (!bytes) bytes = 256;
     int best = -1;
     for (size_t i = 0; i < g_arena_pool.size(); ++i)
-        if (g_arena_pool[i].device == sc->device && g_arena_pool[i].bytes >= bytes && g_arena_pool[i].bytes <= bytes + bytes / 4 + (1u << 20) &&
+        if (g_arena_pool[i].device == device && g_arena_pool[i].bytes >= bytes && g_arena_pool[i].bytes <= bytes + bytes / 4 + (1u << 20) &&
             (best < 0 || g_arena_pool[i].bytes < g_arena_pool[best].bytes)) best = (int)i;
     void* q = nullptr; size_t got = bytes;
-    if (best >= 0) { q = g_arena_pool[best].p; got = g_arena_pool[best].bytes; g_arena_pool.erase(g_arena_pool.begin() + best); }
-    else {
+    if (best >= 0) {
+        wait_block(g_arena_pool[best]);
+        q = g_arena_pool[best].p; got = g_arena_pool[best].bytes; g_arena_pool.erase(g_arena_pool.begin() + best);
+    } else {
         cudaError_t e = cudaMalloc(&q, bytes);
-        if (e != cudaSuccess) { arena_release_all(); e = cudaMalloc(&q, bytes); }
+        if (e != cudaSuccess) { cudaGetLastError(); arena_release_all(); cudaSetDevice(device); e = cudaMalloc(&q, bytes); }
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     }
-    sc->allocs.push_back(q);
-    sc->arena_bytes = got;
-    sc->info.device_bytes += bytes;
-    *base = (char*)q;
+    *base = (char*)q; *got_bytes = got;
     return RBRT_OK;
 }
 static inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-static void destroy_scene(Scene* sc) {
+void destroy_scene(Scene* sc) {
     if (!sc) return;
-    for (void* p : sc->allocs) {
-        if (g_arena_pool.size() < 4) g_arena_pool.push_back(ArenaBlock{p, sc->arena_bytes, sc->device});
-        else cudaFree(p);
+    int cur = 0; cudaGetDevice(&cur);
+    for (Replica& r : sc->rep) {
+        if (!r.arena) continue;
+        ArenaBlock b{r.arena, r.arena_bytes, r.device, {}};
+        for (SceneUse& u : sc->uses) if (u.device == r.device && u.ev) { b.pending.push_back(u.ev); u.ev = nullptr; }
+        size_t pooled = 0;
+        for (auto& g : g_arena_pool) if (g.device == r.device) ++pooled;
+        if (pooled < 4) g_arena_pool.push_back(std::move(b));
+        else { cudaSetDevice(r.device); wait_block(b); cudaFree(b.p); }
     }
+    for (SceneUse& u : sc->uses) if (u.ev) cudaEventDestroy(u.ev);
+    cudaSetDevice(cur);
     delete sc;
+}
+
+SceneDev make_scene_dev(char* base, const ArenaLayout& lay, uint32_t n_elems, uint32_t n_meshes, uint32_t n_etris) {
+    SceneDev d;
+    d.spheres = (const float4*)(base + lay.sph); d.etris = (const float4*)(base + lay.etris); d.elem_kind = (const uint32_t*)(base + lay.ekind);
+    d.tris = (const float4*)(base + lay.tris); d.nodes = (const float4*)(base + lay.nodes); d.normals = (const float4*)(base + lay.nrm);
+    d.mat = (const float4*)(base + lay.mat); d.mat_kind = (const uint32_t*)(base + lay.kind); d.meshes = (const MeshDev*)(base + lay.mesh);
+    d.n_spheres = n_elems; d.n_meshes = n_meshes; d.n_etris = n_etris;
+    return d;
 }
 
 // N_eff of the reference's SIMD sweep: padding appends N % lanes copies (mesh.rs:136-144) and the
@@ -96,9 +143,10 @@ using namespace rbrt;
 extern "C" {
 
 const char* rbrt_last_error(void) { return g_err; }
-const char* rbrt_gpu_version(void) { return "rbrt_b200 0.1.0 sm_100a"; }
+const char* rbrt_gpu_version(void) { return "rbrt_b200 0.2.0 sm_100a"; }
 
 int rbrt_gpu_init(int device) {
+    LOCK;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -107,10 +155,13 @@ int rbrt_gpu_init(int device) {
         return RBRT_E_NODEVICE;
     }
     if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return RBRT_E_INVALID; }
+    if (comm().active && comm().devices[0] != device) { set_error("a communicator is active on device %d; rbrt_gpu_comm_destroy() first", comm().devices[0]); return RBRT_E_INVALID; }
     CKA(cudaSetDevice(device));
     g_device = device;
     return RBRT_OK;
 }
+
+int rbrt_gpu_set_pool_limit(uint64_t max_bytes_per_pool) { LOCK; g_pool_limit = max_bytes_per_pool; return RBRT_OK; }
 
 int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rbrt_mesh_desc* meshes, uint32_t nm,
                           const rbrt_scene_opts* opts, rbrt_scene** out) {
@@ -123,13 +174,16 @@ int rbrt_gpu_scene_create(const rbrt_sphere_desc* spheres, uint32_t ns, const rb
 int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, uint32_t n_sph,
                                    const rbrt_triangle_desc* triangles, uint32_t n_bt, const rbrt_mesh_desc* meshes, uint32_t nm,
                                    const rbrt_scene_opts* opts, rbrt_scene** out) {
+    LOCK;
     if (!out || (ne && !order) || (n_sph && !spheres) || (n_bt && !triangles) || (nm && !meshes)) { set_error("null argument"); return RBRT_E_INVALID; }
+    uint32_t n_et = 0;
     for (uint32_t i = 0; i < ne; ++i) {
         if (order[i].kind == RBRT_ELEM_SPHERE ? order[i].index >= n_sph : (order[i].kind == RBRT_ELEM_TRIANGLE ? order[i].index >= n_bt : true)) {
             set_error("element %u: bad kind or index", i); return RBRT_E_INVALID;
         }
         const rbrt_material& m = order[i].kind == RBRT_ELEM_SPHERE ? spheres[order[i].index].material : triangles[order[i].index].material;
         if (m.kind > 2) { set_error("element %u: unknown material kind", i); return RBRT_E_INVALID; }
+        if (order[i].kind == RBRT_ELEM_TRIANGLE) ++n_et;
     }
     const uint32_t ns = ne;                                               // below, `ns` counts ELEMENTS (spheres + basic triangles)
     *out = nullptr;
@@ -137,32 +191,29 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
     if (lanes != 8 && lanes != 4) { set_error("simd_lanes must be 8 (AVX) or 4 (SSE)"); return RBRT_E_INVALID; }
     uint32_t leaf_size = (opts && opts->leaf_size) ? opts->leaf_size : 1;   // swept 1..8 on C3 (profiles/): a triangle test costs a warp step like a node visit, so fewer tests win
     if (leaf_size > 8) { set_error("leaf_size must be <= 8"); return RBRT_E_INVALID; }
+    const uint32_t sflags = opts ? opts->flags : 0;
     float pad_rel = 2e-5f;
     if (opts && opts->box_pad_rel > 0.0f) pad_rel = opts->box_pad_rel;
     else if (opts && opts->box_pad_rel < 0.0f) pad_rel = 0.0f;
     if ((uint64_t)ns + nm > 65535) { set_error("more than 65535 scene elements"); return RBRT_E_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    const bool collective = comm().active && comm().world > 1 && !(sflags & RBRT_SCENE_LOCAL);
+    const bool is_root = !collective || comm().rank == 0;                 // this process uploads and builds
     uint64_t total_tris = 0, total_eff = 0;
     for (uint32_t i = 0; i < nm; ++i) {
         if (meshes[i].material.kind > 2) { set_error("mesh %u: unknown material kind", i); return RBRT_E_INVALID; }
-        if (meshes[i].num_triangles && !meshes[i].tri_vertices) { set_error("mesh %u: null tri_vertices", i); return RBRT_E_INVALID; }
+        if (meshes[i].num_triangles && !meshes[i].tri_vertices && is_root) { set_error("mesh %u: null tri_vertices", i); return RBRT_E_INVALID; }
         if (meshes[i].num_triangles > (1ull << 28)) { set_error("mesh %u: more than 2^28 triangles", i); return RBRT_E_INVALID; }
         total_tris += meshes[i].num_triangles;
         total_eff += tested_triangles(meshes[i].num_triangles, lanes);
     }
     if (total_eff > (1ull << 28)) { set_error("more than 2^28 triangles in the scene"); return RBRT_E_INVALID; }
-    int rc = ensure_device();
-    if (rc) return rc;
 
     Scene* sc = new Scene();
     sc->device = g_device;
-    static int sm_count_cached[64] = {0};                                  // cudaGetDeviceProperties is slow (tens of ms at times)
-    if (!sm_count_cached[g_device & 63]) {
-        int smc = 0;
-        cudaError_t e = cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, g_device);
-        if (e != cudaSuccess) { destroy_scene(sc); return cuda_fail(e, "cudaDeviceGetAttribute"); }
-        sm_count_cached[g_device & 63] = smc;
-    }
-    sc->sm_count = sm_count_cached[g_device & 63];
+    sc->collective = collective;
+    sc->n_elems = ns; sc->n_meshes = nm; sc->n_etris = n_et;
     sc->info.num_spheres = ns; sc->info.num_meshes = nm;
     sc->info.num_triangles = total_tris; sc->info.num_triangles_tested = total_eff;
     double t0 = now_ms();
@@ -170,102 +221,123 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
 #define CKS(x) do { int rc_ = (x); if (rc_) { destroy_scene(sc); return rc_; } } while (0)
 #define CKSC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { int rc_ = cuda_fail(e_, #x); destroy_scene(sc); return rc_; } } while (0)
 
-    // ---- elements: spheres + per-element materials (flattened SoA, 16-byte records)
-    std::vector<float4> sph(ns), mat(ns + nm), etris;
-    std::vector<uint32_t> kind(ns + nm), ekind(ns);
-    for (uint32_t i = 0; i < ns; ++i) {
-        rbrt_material m;
-        if (order[i].kind == RBRT_ELEM_SPHERE) {
-            const rbrt_sphere_desc& sp = spheres[order[i].index];
-            sph[i] = make_float4(sp.center.x, sp.center.y, sp.center.z, sp.radius);
-            m = sp.material; ekind[i] = RBRT_ELEM_SPHERE;
-        } else {                                                          // BasicTriangle::new (triangle.rs:19-27), host f32, no contraction
-            const rbrt_triangle_desc& t = triangles[order[i].index];
-            const rbrt_vec3 &a = t.corners[0], &b = t.corners[1], &c = t.corners[2];
-            float e1[3] = {b.x - a.x, b.y - a.y, b.z - a.z}, e2[3] = {c.x - a.x, c.y - a.y, c.z - a.z};
-            float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
-            float len = sqrtf(cx * cx + cy * cy + cz * cz);
-            uint32_t ti = (uint32_t)(etris.size() / 4);
-            float tif; memcpy(&tif, &ti, 4);
-            sph[i] = make_float4(tif, 0.0f, 0.0f, 0.0f);
-            etris.push_back(make_float4(a.x, a.y, a.z, 0.0f)); etris.push_back(make_float4(e1[0], e1[1], e1[2], 0.0f));
-            etris.push_back(make_float4(e2[0], e2[1], e2[2], 0.0f)); etris.push_back(make_float4(cx / len, cy / len, cz / len, 0.0f));
-            m = t.material; ekind[i] = RBRT_ELEM_TRIANGLE;
-        }
-        mat[i] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.param);
-        kind[i] = m.kind;
-    }
-    for (uint32_t i = 0; i < nm; ++i) {
-        mat[ns + i] = make_float4(meshes[i].material.albedo.x, meshes[i].material.albedo.y, meshes[i].material.albedo.z, meshes[i].material.param);
-        kind[ns + i] = meshes[i].material.kind;
-    }
-    float4 *d_sph, *d_mat, *d_tris, *d_nodes, *d_normals, *d_etris; uint32_t *d_kind, *d_ekind; MeshDev* d_meshes;
+    // ---- the scene's device block.  The LBVH nodes come LAST: only the live ones (about N/3 of the N slots) are
+    //      replicated to other GPUs.
     {
-        const size_t b_etris = a256(16ull * etris.size()), b_ekind = a256(4ull * ns);
-        const size_t b_sph = a256(16ull * ns), b_mat = a256(16ull * (ns + nm)), b_kind = a256(4ull * (ns + nm)), b_tris = a256(48ull * total_eff),
-                     b_nodes = a256(64ull * total_eff), b_nrm = a256(16ull * total_eff), b_mesh = a256(sizeof(MeshDev) * nm);
-        char* base = nullptr;
-        CKS(arena_alloc(sc, b_nodes + b_tris + b_nrm + b_sph + b_mat + b_kind + b_mesh + b_etris + b_ekind, &base));
-        d_nodes = (float4*)base; base += b_nodes;                          // nodes and triangles adjacent: the data every ray re-reads
-        d_tris = (float4*)base; base += b_tris;
-        d_normals = (float4*)base; base += b_nrm;
-        d_sph = (float4*)base; base += b_sph;
-        d_mat = (float4*)base; base += b_mat;
-        d_kind = (uint32_t*)base; base += b_kind;
-        d_meshes = (MeshDev*)base; base += b_mesh;
-        d_etris = (float4*)base; base += b_etris;
-        d_ekind = (uint32_t*)base;
+        ArenaLayout& L = sc->lay; size_t off = 0;
+        L.tris = off; off += a256(48ull * total_eff);
+        L.nrm = off; off += a256(16ull * total_eff);
+        L.sph = off; off += a256(16ull * ns);
+        L.mat = off; off += a256(16ull * (ns + nm));
+        L.kind = off; off += a256(4ull * (ns + nm));
+        L.mesh = off; off += a256(sizeof(MeshDev) * nm);
+        L.etris = off; off += a256(64ull * n_et);
+        L.ekind = off; off += a256(4ull * ns);
+        L.nodes = off; off += a256(64ull * total_eff);
+        L.total = off;
     }
-    if (ns) CKSC(cudaMemcpy(d_sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
-    if (!etris.empty()) {
-        CKSC(cudaMemcpy(d_etris, etris.data(), 16ull * etris.size(), cudaMemcpyHostToDevice));
-        CKSC(cudaMemcpy(d_ekind, ekind.data(), 4ull * ns, cudaMemcpyHostToDevice));
+    const int n_local = collective ? comm().local_n : 1;
+    sc->rep.resize(n_local);
+    for (int li = 0; li < n_local; ++li) {
+        Replica& r = sc->rep[li];
+        r.device = collective ? comm().devices[li] : g_device;
+        CKSC(cudaSetDevice(r.device));
+        CKS(device_sm_count(r.device, &r.sm_count));
+        CKS(arena_alloc(r.device, sc->lay.total, &r.arena, &r.arena_bytes));
+        r.dev = make_scene_dev(r.arena, sc->lay, ns, nm, n_et);
+        sc->info.device_bytes += sc->lay.total;
     }
-    if (ns + nm) {
-        CKSC(cudaMemcpy(d_mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice));
-        CKSC(cudaMemcpy(d_kind, kind.data(), 4ull * (ns + nm), cudaMemcpyHostToDevice));
-    }
-
-    // ---- meshes: exact AABB on the host (aabbox.rs:62-88, over ALL real triangles), then upload + LBVH
-    double ms_upload = 0, ms_build = 0;
-    uint64_t tri_off = 0, live_total = 0;
+    CKSC(cudaSetDevice(sc->rep[0].device));
+    sc->dev = sc->rep[0].dev; sc->sm_count = sc->rep[0].sm_count;
+    char* const base = sc->rep[0].arena;
     sc->meshes_h.resize(nm);
-    for (uint32_t i = 0; i < nm; ++i) {
-        const rbrt_mesh_desc& m = meshes[i];
-        MeshDev md; memset(&md, 0, sizeof(md));
-        float lo[3] = {3.40282347e+38f, 3.40282347e+38f, 3.40282347e+38f}, hi[3] = {-3.40282347e+38f, -3.40282347e+38f, -3.40282347e+38f};
-        uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
-        const float* d_raw = nullptr;
-        double t1 = now_ms();
-        // upload + exact AABB over ALL real triangles, including those the SIMD tail rule drops (aabbox.rs:62-88, mesh.rs:61)
-        CKSC(upload_mesh(m.tri_vertices, m.num_triangles, lo, hi, &d_raw, 0));
-        double t2 = now_ms();
-        for (int k = 0; k < 3; ++k) { md.lo[k] = lo[k]; md.hi[k] = hi[k]; }
-        md.tri_base = (uint32_t)tri_off; md.n_tris = (uint32_t)n_eff; md.node_base = (uint32_t)tri_off;
-        md.nrm_base = (uint32_t)tri_off; md.elem = ns + i; md.root_ref = make_leaf_ref(0, 1);
-        if (n_eff) {
-            float mx = 0.0f;
-            for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]); }
-            float pad = pad_rel * mx;
-            uint64_t live = 0; int height = 0;
-            cudaError_t ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, d_tris + 3 * tri_off, d_normals + tri_off,
-                                            d_nodes + 4 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
-            if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
-            if (3 * height + 2 > 192) { set_error("mesh %u: BVH depth %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
-            live_total += live;
+    uint64_t live_total = 0, nodes_end = 0;
+    double ms_upload = 0, ms_build = 0;
+
+    if (is_root) {
+        // ---- elements: spheres + per-element materials (flattened SoA, 16-byte records)
+        std::vector<float4> sph(ns), mat(ns + nm), etris;
+        std::vector<uint32_t> kind(ns + nm), ekind(ns);
+        for (uint32_t i = 0; i < ns; ++i) {
+            rbrt_material m;
+            if (order[i].kind == RBRT_ELEM_SPHERE) {
+                const rbrt_sphere_desc& sp = spheres[order[i].index];
+                sph[i] = make_float4(sp.center.x, sp.center.y, sp.center.z, sp.radius);
+                m = sp.material; ekind[i] = RBRT_ELEM_SPHERE;
+            } else {                                                          // BasicTriangle::new (triangle.rs:19-27), host f32, no contraction
+                const rbrt_triangle_desc& t = triangles[order[i].index];
+                const rbrt_vec3 &a = t.corners[0], &b = t.corners[1], &c = t.corners[2];
+                float e1[3] = {b.x - a.x, b.y - a.y, b.z - a.z}, e2[3] = {c.x - a.x, c.y - a.y, c.z - a.z};
+                float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+                float len = sqrtf(cx * cx + cy * cy + cz * cz);
+                uint32_t ti = (uint32_t)(etris.size() / 4);
+                float tif; memcpy(&tif, &ti, 4);
+                sph[i] = make_float4(tif, 0.0f, 0.0f, 0.0f);
+                etris.push_back(make_float4(a.x, a.y, a.z, 0.0f)); etris.push_back(make_float4(e1[0], e1[1], e1[2], 0.0f));
+                etris.push_back(make_float4(e2[0], e2[1], e2[2], 0.0f)); etris.push_back(make_float4(cx / len, cy / len, cz / len, 0.0f));
+                m = t.material; ekind[i] = RBRT_ELEM_TRIANGLE;
+            }
+            mat[i] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.param);
+            kind[i] = m.kind;
         }
-        ms_upload += t2 - t1; ms_build += now_ms() - t2;
-        sc->meshes_h[i] = md;
-        tri_off += n_eff;
+        for (uint32_t i = 0; i < nm; ++i) {
+            mat[ns + i] = make_float4(meshes[i].material.albedo.x, meshes[i].material.albedo.y, meshes[i].material.albedo.z, meshes[i].material.param);
+            kind[ns + i] = meshes[i].material.kind;
+        }
+        if (ns) CKSC(cudaMemcpy(base + sc->lay.sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
+        if (!etris.empty()) {
+            CKSC(cudaMemcpy(base + sc->lay.etris, etris.data(), 16ull * etris.size(), cudaMemcpyHostToDevice));
+            CKSC(cudaMemcpy(base + sc->lay.ekind, ekind.data(), 4ull * ns, cudaMemcpyHostToDevice));
+        }
+        if (ns + nm) {
+            CKSC(cudaMemcpy(base + sc->lay.mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice));
+            CKSC(cudaMemcpy(base + sc->lay.kind, kind.data(), 4ull * (ns + nm), cudaMemcpyHostToDevice));
+        }
+
+        // ---- meshes: exact AABB (aabbox.rs:62-88, over ALL real triangles), then upload + LBVH
+        float4* d_tris = (float4*)(base + sc->lay.tris); float4* d_normals = (float4*)(base + sc->lay.nrm); float4* d_nodes = (float4*)(base + sc->lay.nodes);
+        uint64_t tri_off = 0;
+        for (uint32_t i = 0; i < nm; ++i) {
+            const rbrt_mesh_desc& m = meshes[i];
+            MeshDev md; memset(&md, 0, sizeof(md));
+            float lo[3] = {3.40282347e+38f, 3.40282347e+38f, 3.40282347e+38f}, hi[3] = {-3.40282347e+38f, -3.40282347e+38f, -3.40282347e+38f};
+            uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
+            const float* d_raw = nullptr;
+            double t1 = now_ms();
+            // upload + exact AABB over ALL real triangles, including those the SIMD tail rule drops (aabbox.rs:62-88, mesh.rs:61)
+            CKSC(upload_mesh(m.tri_vertices, m.num_triangles, lo, hi, &d_raw, 0));
+            double t2 = now_ms();
+            for (int k = 0; k < 3; ++k) { md.lo[k] = lo[k]; md.hi[k] = hi[k]; }
+            md.tri_base = (uint32_t)tri_off; md.n_tris = (uint32_t)n_eff; md.node_base = (uint32_t)tri_off;
+            md.nrm_base = (uint32_t)tri_off; md.elem = ns + i; md.root_ref = make_leaf_ref(0, 1);
+            if (n_eff) {
+                float mx = 0.0f;
+                for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]); }
+                float pad = pad_rel * mx;
+                uint64_t live = 0; int height = 0;
+                cudaError_t ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, !(sflags & RBRT_SCENE_NO_SAH), d_tris + 3 * tri_off, d_normals + tri_off,
+                                                d_nodes + 4 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
+                if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
+                if (3 * height + 2 > 192) { set_error("mesh %u: BVH depth %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
+                live_total += live;
+                if (live) nodes_end = tri_off + live;
+            }
+            ms_upload += t2 - t1; ms_build += now_ms() - t2;
+            sc->meshes_h[i] = md;
+            tri_off += n_eff;
+        }
+        if (nm) CKSC(cudaMemcpy(base + sc->lay.mesh, sc->meshes_h.data(), sizeof(MeshDev) * nm, cudaMemcpyHostToDevice));
+        CKSC(cudaStreamSynchronize(0));                                   // upload + build ran on the default stream
     }
-    if (nm) CKSC(cudaMemcpy(d_meshes, sc->meshes_h.data(), sizeof(MeshDev) * nm, cudaMemcpyHostToDevice));
-    CKSC(cudaStreamSynchronize(0));                                       // upload + build ran on the default stream; renders in flight on other (non-blocking) streams are not waited for
-    sc->dev.etris = d_etris; sc->dev.elem_kind = d_ekind; sc->dev.n_etris = (uint32_t)(etris.size() / 4);
-    sc->dev.spheres = d_sph; sc->dev.tris = d_tris; sc->dev.nodes = d_nodes; sc->dev.normals = d_normals;
-    sc->dev.mat = d_mat; sc->dev.mat_kind = d_kind; sc->dev.meshes = d_meshes; sc->dev.n_spheres = ns; sc->dev.n_meshes = nm;
     sc->info.num_bvh_nodes = live_total;
+    if (collective) {                                                     // replicas on the other GPUs (multi.cu): NCCL broadcast / peer copies
+        double t3 = now_ms();
+        CKS(replicate_scene(sc, nodes_end));
+        ms_upload += now_ms() - t3;
+    }
     sc->info.ms_upload = ms_upload + (now_ms() - t0 - ms_upload - ms_build);
     sc->info.ms_build = ms_build;
+    CKSC(cudaSetDevice(sc->rep[0].device));
     *out = reinterpret_cast<rbrt_scene*>(sc);
     return RBRT_OK;
 #undef CKS
@@ -273,28 +345,29 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
 }
 
 int rbrt_gpu_scene_info(const rbrt_scene* scene, rbrt_scene_info* out) {
+    LOCK;
     if (!scene || !out) { set_error("null argument"); return RBRT_E_INVALID; }
     *out = reinterpret_cast<const Scene*>(scene)->info;
     return RBRT_OK;
 }
 
 int rbrt_gpu_scene_destroy(rbrt_scene* scene) {
+    LOCK;
     if (!scene) return RBRT_OK;
-    Scene* sc = reinterpret_cast<Scene*>(scene);
-    cudaSetDevice(sc->device);
-    destroy_scene(sc);
+    destroy_scene(reinterpret_cast<Scene*>(scene));
     return RBRT_OK;
 }
 
 int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
                                  void* d_accum, void* stream, rbrt_stats* stats) {
+    LOCK;
     if (!scene || !cam || !d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
     const Scene& sc = *reinterpret_cast<const Scene*>(scene);
     CKA(cudaSetDevice(sc.device));
     double t0 = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
     float4* acc1[1] = {(float4*)d_accum};
-    int rc = render_accum(sc, cam, nullptr, 1, spp, opts, acc1, (cudaStream_t)stream, stats);
+    int rc = render_accum(sc, 0, cam, nullptr, 1, spp, opts, acc1, (cudaStream_t)stream, stats);
     if (rc) return rc;
     if (stats) stats->ms_total = now_ms() - t0;
     return RBRT_OK;
@@ -302,6 +375,7 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
 
 int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames,
                                         uint32_t spp, const rbrt_render_opts* opts, void* const* d_accum, void* stream, rbrt_stats* stats) {
+    LOCK;
     if (!scene || !cams || !seeds || !d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
     if (!n_frames || n_frames > RBRT_MAX_FRAMES) { set_error("n_frames must be 1..%d", RBRT_MAX_FRAMES); return RBRT_E_INVALID; }
     float4* acc[RBRT_MAX_FRAMES];
@@ -310,13 +384,14 @@ int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_came
     CKA(cudaSetDevice(sc.device));
     double t0 = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
-    int rc = render_accum(sc, cams, seeds, n_frames, spp, opts, acc, (cudaStream_t)stream, stats);
+    int rc = render_accum(sc, 0, cams, seeds, n_frames, spp, opts, acc, (cudaStream_t)stream, stats);
     if (rc) return rc;
     if (stats) stats->ms_total = now_ms() - t0;
     return RBRT_OK;
 }
 
 int rbrt_gpu_release_cache(void) {
+    LOCK;
     release_device_wave_buffers();
     release_build_scratch();
     arena_release_all();
@@ -324,55 +399,84 @@ int rbrt_gpu_release_cache(void) {
 }
 
 int rbrt_gpu_finalize_device(const void* d_accum, uint32_t W, uint32_t H, uint32_t spp, void* d_rgb, void* d_hdr, void* stream) {
+    LOCK;
     if (!d_accum) { set_error("null argument"); return RBRT_E_INVALID; }
     int rc = ensure_device();
     if (rc) return rc;
     return finalize((const float4*)d_accum, W, H, spp, (uint8_t*)d_rgb, (float*)d_hdr, (cudaStream_t)stream);
 }
 
+int rbrt_gpu_render_frames_device(const rbrt_scene* scene, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames,
+                                  uint32_t spp, const rbrt_render_opts* opts, void* const* d_rgb, void* const* d_hdr, void* stream, rbrt_stats* stats) {
+    LOCK;
+    if (!scene || !cams || !seeds) { set_error("null argument"); return RBRT_E_INVALID; }
+    if (!n_frames || n_frames > RBRT_MAX_FRAMES) { set_error("n_frames must be 1..%d", RBRT_MAX_FRAMES); return RBRT_E_INVALID; }
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    CKA(cudaSetDevice(sc.device));
+    double t0 = now_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    int rc = render_frames(sc, cams, seeds, n_frames, spp, opts, (uint8_t* const*)d_rgb, (float* const*)d_hdr, (cudaStream_t)stream, stats);
+    cudaSetDevice(sc.device);
+    if (rc) return rc;
+    if (stats) stats->ms_total = now_ms() - t0;
+    return RBRT_OK;
+}
+
+// render_scene with HOST output: the collective render into the pool's own device image, then one copy to the host
 static int render_host(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
                        uint8_t* rgb_out, float* hdr_out, rbrt_stats* stats) {
-    if (!scene || !cam || (!rgb_out && !hdr_out)) { set_error("null argument"); return RBRT_E_INVALID; }
+    LOCK;
+    if (!scene || !cam) { set_error("null argument"); return RBRT_E_INVALID; }
     const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    const bool sharded = sc.collective && (!opts || opts->shard_count == 0);
+    const bool root = !sharded || comm().rank == 0;
+    if (root && !rgb_out && !hdr_out) { set_error("null output"); return RBRT_E_INVALID; }
     CKA(cudaSetDevice(sc.device));
     double t0 = now_ms();
     size_t n = (size_t)cam->img_width_pix * cam->img_height_pix;
     if (!n || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
-    WaveBuffers& wb = device_wave_buffers(sc.device);
-    if (wb.accum_px < n) { cudaFree(wb.accum); wb.accum = nullptr; wb.accum_px = 0; CKA(cudaMalloc(&wb.accum, 16 * n)); wb.accum_px = n; }
+    WaveBuffers& wb = device_wave_buffers(sc.device, opts ? (int)((opts->flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT) : 0);
     if (wb.out_px < n) {
         cudaFree(wb.rgb); cudaFree(wb.hdr); wb.rgb = nullptr; wb.hdr = nullptr; wb.out_px = 0;
         CKA(cudaMalloc(&wb.rgb, 3 * n)); CKA(cudaMalloc(&wb.hdr, 12 * n)); wb.out_px = n;
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     rbrt_stats local; memset(&local, 0, sizeof(local));
-    float4* acc1[1] = {wb.accum};
-    int rc = render_accum(sc, cam, nullptr, 1, spp, opts, acc1, 0, &local);
-    if (rc) return rc;
-    rc = finalize(wb.accum, cam->img_width_pix, cam->img_height_pix, spp, rgb_out ? wb.rgb : nullptr, hdr_out ? wb.hdr : nullptr, 0);
+    const uint64_t seed = opts ? opts->seed : 0;
+    uint8_t* rgb1[1] = {wb.rgb}; float* hdr1[1] = {wb.hdr};
+    const bool want_rgb = rgb_out || (!root && !hdr_out), want_hdr = hdr_out != nullptr;    // every rank must make the same choice: see below
+    int rc = render_frames(sc, cam, &seed, 1, spp, opts, want_rgb ? rgb1 : nullptr, want_hdr ? hdr1 : nullptr, 0, &local);
+    cudaSetDevice(sc.device);
     if (rc) return rc;
     double t1 = now_ms();
-    if (rgb_out) CKA(cudaMemcpy(rgb_out, wb.rgb, 3 * n, cudaMemcpyDeviceToHost));
-    if (hdr_out) CKA(cudaMemcpy(hdr_out, wb.hdr, 12 * n, cudaMemcpyDeviceToHost));
+    if (root && rgb_out) CKA(cudaMemcpy(rgb_out, wb.rgb, 3 * n, cudaMemcpyDeviceToHost));
+    if (root && hdr_out) CKA(cudaMemcpy(hdr_out, wb.hdr, 12 * n, cudaMemcpyDeviceToHost));
     double t2 = now_ms();
-    if (stats) { *stats = local; stats->ms_d2h = t2 - t1; stats->ms_total = t2 - t0; stats->launches += 1; }
+    if (stats) { *stats = local; stats->ms_d2h = t2 - t1; stats->ms_total = t2 - t0; }
     return RBRT_OK;
 }
 
 int rbrt_gpu_render(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
                     uint8_t* rgb_out, rbrt_stats* stats) {
-    if (!rgb_out) { set_error("null rgb_out"); return RBRT_E_INVALID; }
+    // non-root ranks of a collective render may pass NULL; the root must not
+    if (!rgb_out && !(scene && reinterpret_cast<const Scene*>(scene)->collective && comm().rank != 0 && (!opts || opts->shard_count == 0))) {
+        set_error("null rgb_out"); return RBRT_E_INVALID;
+    }
     return render_host(scene, cam, spp, opts, rgb_out, nullptr, stats);
 }
 
 int rbrt_gpu_render_hdr(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
                         float* hdr_out, rbrt_stats* stats) {
-    if (!hdr_out) { set_error("null rgb_f32_out"); return RBRT_E_INVALID; }
-    return render_host(scene, cam, spp, opts, nullptr, hdr_out, stats);
+    static float dummy;                                                   // non-root ranks: "an HDR render", without a buffer
+    const bool nonroot = scene && reinterpret_cast<const Scene*>(scene)->collective && comm().rank != 0 && (!opts || opts->shard_count == 0);
+    if (!hdr_out && !nonroot) { set_error("null rgb_f32_out"); return RBRT_E_INVALID; }
+    return render_host(scene, cam, spp, opts, nullptr, hdr_out ? hdr_out : (nonroot ? &dummy : nullptr), stats);
 }
 
 int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t n, uint32_t mode, rbrt_hit* hits, rbrt_stats* stats) {
+    LOCK;
     if (!scene || (n && (!rays || !hits))) { set_error("null argument"); return RBRT_E_INVALID; }
+    if (mode > RBRT_TRACE_WAVEFRONT) { set_error("unknown trace_mode %u", mode); return RBRT_E_INVALID; }
     const Scene& sc = *reinterpret_cast<const Scene*>(scene);
     CKA(cudaSetDevice(sc.device));
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -391,7 +495,8 @@ int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t 
         CKT(cudaMemcpy(d_rays, rays, sizeof(rbrt_ray) * n, cudaMemcpyHostToDevice));
         double t2 = now_ms();
         CKT(cudaEventRecord(e0, 0));
-        rc = trace_rays_device(sc, d_rays, n, mode, d_hits, stats ? d_stats : nullptr, 0);
+        rc = mode == RBRT_TRACE_WAVEFRONT ? trace_rays_wavefront(sc, d_rays, n, d_hits, stats ? d_stats : nullptr, 0)
+                                          : trace_rays_device(sc, d_rays, n, mode, d_hits, stats ? d_stats : nullptr, 0);
         if (rc) goto done;
         CKT(cudaEventRecord(e1, 0));
         CKT(cudaEventSynchronize(e1));
@@ -402,8 +507,8 @@ int rbrt_gpu_trace_rays(const rbrt_scene* scene, const rbrt_ray* rays, uint64_t 
             unsigned long long h[ST_COUNT];
             CKT(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
             float ms = 0; CKT(cudaEventElapsedTime(&ms, e0, e1));
-            stats->rays = n; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS];
-            stats->ms_device = ms; stats->ms_trace = ms; stats->ms_h2d = t2 - t1; stats->ms_d2h = t4 - t3; stats->launches = 1;
+            stats->rays = n; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS]; stats->traversed_rays = h[ST_CAND];
+            stats->ms_device = ms; stats->ms_trace = ms; stats->ms_h2d = t2 - t1; stats->ms_d2h = t4 - t3; stats->launches = mode == RBRT_TRACE_WAVEFRONT ? 3 : 1;
             stats->ms_total = now_ms() - t0;
         }
     }
@@ -415,7 +520,25 @@ done:
     return rc;
 }
 
+int rbrt_gpu_scatter(const rbrt_scatter_in* items, uint64_t n, uint64_t seed, rbrt_scatter_out* out) {
+    LOCK;
+    if (n && (!items || !out)) { set_error("null argument"); return RBRT_E_INVALID; }
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!n) return RBRT_OK;
+    for (uint64_t i = 0; i < n; ++i) if (items[i].material.kind > 2) { set_error("item %llu: unknown material kind", (unsigned long long)i); return RBRT_E_INVALID; }
+    rbrt_scatter_in* d_in = nullptr; rbrt_scatter_out* d_out = nullptr;
+    cudaError_t ce = cudaMalloc(&d_in, sizeof(rbrt_scatter_in) * n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_out, sizeof(rbrt_scatter_out) * n);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_in, items, sizeof(rbrt_scatter_in) * n, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) { rc = scatter_device(d_in, n, seed, d_out, 0); if (!rc) ce = cudaMemcpy(out, d_out, sizeof(rbrt_scatter_out) * n, cudaMemcpyDeviceToHost); }
+    cudaFree(d_in); cudaFree(d_out);
+    if (ce != cudaSuccess) return cuda_fail(ce, "rbrt_gpu_scatter");
+    return rc;
+}
+
 int rbrt_gpu_primary_rays(const rbrt_camera* cam, uint64_t seed, uint32_t sample, rbrt_ray* rays_out) {
+    LOCK;
     if (!cam || !rays_out) { set_error("null argument"); return RBRT_E_INVALID; }
     int rc = ensure_device();
     if (rc) return rc;

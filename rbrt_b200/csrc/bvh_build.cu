@@ -10,6 +10,7 @@
 #include "bvh_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cstring>
+#include <cstdlib>
 
 namespace rbrt {
 
@@ -100,28 +101,79 @@ __global__ void k_karras(const uint64_t* __restrict__ keys, int n, int2* __restr
     if (i == 0) parent_int[0] = -1;
 }
 
-// bottom-up refit: the second thread to arrive at a node merges its children (Karras 2012 §4)
-__global__ void k_refit(int n, const int2* __restrict__ children, const int* __restrict__ parent_int,
-                        const int* __restrict__ parent_leaf, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                        float4* __restrict__ node_lo, float4* __restrict__ node_hi, int* __restrict__ flags, int* __restrict__ height) {
+// bottom-up refit: the second thread to arrive at a node merges its children (Karras 2012 §4).
+// ROT: on the way up every node also tries the four TREE ROTATIONS that exchange one of its children with a grandchild
+// on the other side (Kensler 2008) and keeps the one that shrinks the surface area of the child being rebuilt most —
+// the SAH term that changes.  The Morton-order tree splits space at fixed planes; a rotation lets a subtree pair up with
+// the neighbour it overlaps least.  Safe without locks: a node is handled by exactly one thread, after both of its
+// subtrees are complete, and only that thread ever touches those subtrees again (on its way up).
+struct BoxH { float lx, ly, lz, hx, hy, hz; int h; };
+__device__ __forceinline__ BoxH load_box(int c, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                         volatile const float4* nl, volatile const float4* nh, volatile const int* height) {
+    BoxH b;
+    if (c >= 0) { b.lx = nl[c].x; b.ly = nl[c].y; b.lz = nl[c].z; b.hx = nh[c].x; b.hy = nh[c].y; b.hz = nh[c].z; b.h = height[c]; }
+    else { const float4 a = leaf_lo[~c], d = leaf_hi[~c]; b.lx = a.x; b.ly = a.y; b.lz = a.z; b.hx = d.x; b.hy = d.y; b.hz = d.z; b.h = 0; }
+    return b;
+}
+__device__ __forceinline__ BoxH merge_box(const BoxH& a, const BoxH& b) {
+    BoxH m; m.lx = fminf(a.lx, b.lx); m.ly = fminf(a.ly, b.ly); m.lz = fminf(a.lz, b.lz);
+    m.hx = fmaxf(a.hx, b.hx); m.hy = fmaxf(a.hy, b.hy); m.hz = fmaxf(a.hz, b.hz); m.h = max(a.h, b.h) + 1;
+    return m;
+}
+__device__ __forceinline__ float box_area(const BoxH& b) {
+    const float dx = b.hx - b.lx, dy = b.hy - b.ly, dz = b.hz - b.lz;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+template <bool ROT>
+__global__ void k_refit(int n, int2* children, int* parent_int,
+                        int* parent_leaf, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                        float4* node_lo, float4* node_hi, int* __restrict__ flags, int* height) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int cur = parent_leaf[p];
+    volatile const float4* nl = node_lo; volatile const float4* nh = node_hi; volatile const int* vh = height;
+    volatile int* vch = reinterpret_cast<volatile int*>(children);
     while (cur >= 0) {
         __threadfence();
         if (atomicAdd(&flags[cur], 1) == 0) return;
         __threadfence();
-        int2 ch = children[cur];
-        volatile const float4* nl = node_lo; volatile const float4* nh = node_hi;
-        float lx, ly, lz, hx, hy, hz; int hl, hr;
-        if (ch.x >= 0) { lx = nl[ch.x].x; ly = nl[ch.x].y; lz = nl[ch.x].z; hx = nh[ch.x].x; hy = nh[ch.x].y; hz = nh[ch.x].z; hl = ((volatile int*)height)[ch.x]; }
-        else { float4 a = leaf_lo[~ch.x], b = leaf_hi[~ch.x]; lx = a.x; ly = a.y; lz = a.z; hx = b.x; hy = b.y; hz = b.z; hl = 0; }
-        float rlx, rly, rlz, rhx, rhy, rhz;
-        if (ch.y >= 0) { rlx = nl[ch.y].x; rly = nl[ch.y].y; rlz = nl[ch.y].z; rhx = nh[ch.y].x; rhy = nh[ch.y].y; rhz = nh[ch.y].z; hr = ((volatile int*)height)[ch.y]; }
-        else { float4 a = leaf_lo[~ch.y], b = leaf_hi[~ch.y]; rlx = a.x; rly = a.y; rlz = a.z; rhx = b.x; rhy = b.y; rhz = b.z; hr = 0; }
-        node_lo[cur] = make_float4(fminf(lx, rlx), fminf(ly, rly), fminf(lz, rlz), 0.0f);
-        node_hi[cur] = make_float4(fmaxf(hx, rhx), fmaxf(hy, rhy), fmaxf(hz, rhz), 0.0f);
-        height[cur] = max(hl, hr) + 1;
+        int c0 = vch[2 * cur], c1 = vch[2 * cur + 1];
+        BoxH b0 = load_box(c0, leaf_lo, leaf_hi, nl, nh, vh), b1 = load_box(c1, leaf_lo, leaf_hi, nl, nh, vh);
+        if (ROT) {
+            float best = 0.0f; int bside = -1, bwhich = 0; BoxH bnew = b0;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {                         // X = the child that is rebuilt, Y = the other child, moved down
+                const int X = side ? c1 : c0;
+                if (X < 0) continue;
+                const BoxH& bx = side ? b1 : b0; const BoxH& by = side ? b0 : b1;
+                const int g0 = vch[2 * X], g1 = vch[2 * X + 1];
+                const BoxH bg0 = load_box(g0, leaf_lo, leaf_hi, nl, nh, vh), bg1 = load_box(g1, leaf_lo, leaf_hi, nl, nh, vh);
+                const float ax = box_area(bx);
+                const BoxH m0 = merge_box(by, bg1), m1 = merge_box(bg0, by);   // Y replaces g0 / Y replaces g1
+                const float d0 = box_area(m0) - ax, d1 = box_area(m1) - ax;
+                if (d0 < best) { best = d0; bside = side; bwhich = 0; bnew = m0; }
+                if (d1 < best) { best = d1; bside = side; bwhich = 1; bnew = m1; }
+            }
+            if (bside >= 0) {
+                const int X = bside ? c1 : c0, Y = bside ? c0 : c1;
+                const int g0 = vch[2 * X], g1 = vch[2 * X + 1];
+                const int up = bwhich ? g1 : g0;                              // the grandchild that moves up, Y takes its place
+                if (bwhich) vch[2 * X + 1] = Y; else vch[2 * X] = Y;
+                node_lo[X] = make_float4(bnew.lx, bnew.ly, bnew.lz, 0.0f); node_hi[X] = make_float4(bnew.hx, bnew.hy, bnew.hz, 0.0f);
+                height[X] = bnew.h;
+                const BoxH bup = load_box(up, leaf_lo, leaf_hi, nl, nh, vh);
+                if (bside) { c0 = up; b0 = bup; b1 = bnew; } else { c1 = up; b1 = bup; b0 = bnew; }
+                vch[2 * cur] = c0; vch[2 * cur + 1] = c1;
+                // parents of the two moved subtrees (both complete: nobody reads these again in this pass; the next pass walks them)
+                if (Y >= 0) parent_int[Y] = X; else parent_leaf[~Y] = X;
+                if (up >= 0) parent_int[up] = cur; else parent_leaf[~up] = cur;
+            }
+        }
+        const BoxH m = merge_box(b0, b1);
+        node_lo[cur] = make_float4(m.lx, m.ly, m.lz, 0.0f);
+        node_hi[cur] = make_float4(m.hx, m.hy, m.hz, 0.0f);
+        height[cur] = m.h;
         cur = parent_int[cur];
     }
 }
@@ -278,7 +330,7 @@ cudaError_t upload_mesh(const float* h_tris, uint64_t n_all, float lo[3], float 
     return cudaSuccess;
 }
 
-cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size,
+cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size, bool sah,
                            float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
                            int* tree_height, float qorg[3], float qstep[3], cudaStream_t st) {
     *live_nodes = 0; *tree_height = 0;
@@ -329,7 +381,15 @@ cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], co
     CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
     k_karras<<<(ni + B - 1) / B, B, 0, st>>>(keys_s, (int)n, children, range, parent_int, parent_leaf);
     CK(cudaGetLastError());
-    k_refit<<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+    // SAH pass: tree rotations during the refit; only with one-triangle leaves (a rotated subtree no longer covers a
+    // contiguous run of the Morton order, which multi-triangle leaves rely on).  RBRT_SAH_PASSES: tuning knob.
+    static const int sah_passes_env = getenv("RBRT_SAH_PASSES") ? atoi(getenv("RBRT_SAH_PASSES")) : 1;
+    const int passes = (sah && leaf_size == 1) ? sah_passes_env : 0;
+    if (passes <= 0) k_refit<false><<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+    for (int pass = 0; pass < passes; ++pass) {
+        if (pass) CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
+        k_refit<true><<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+    }
     CK(cudaGetLastError());
     int hbin = 0;                                                          // binary height bounds the number of BFS levels
     CK(cudaMemcpyAsync(&hbin, height, 4, cudaMemcpyDeviceToHost, st));

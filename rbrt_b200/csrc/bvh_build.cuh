@@ -14,7 +14,8 @@ void release_build_scratch();
 // Writes n triangle records (3 float4 each) in Morton order to d_tris, n unit normals in ORIGINAL
 // order to d_normals and up to n-1 64-byte 4-wide nodes to d_nodes (tree_height = depth of the wide tree); qorg/qstep = the 16-bit grid the node boxes are
 // quantised on.  lo/hi = exact mesh AABB.
-cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size,
+// sah: run the tree-rotation pass during the refit (one-triangle leaves only).
+cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size, bool sah,
                            float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
                            int* tree_height, float qorg[3], float qstep[3], cudaStream_t st);
 

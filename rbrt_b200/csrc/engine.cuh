@@ -1,13 +1,12 @@
 // engine.cuh — host-side objects behind the opaque rbrt_scene handle and the wavefront state.
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/rbrt_gpu.h"
 #include "common.cuh"
 
 namespace rbrt {
-
-#define RBRT_MAX_FRAMES 4    // frames one wavefront batch can hold (rbrt_gpu_render_accum_device_frames)
 
 // Per-iteration queue counters.  All iterations of a batch get their own slot, so one memset per
 // batch resets everything and no kernel ever has to reset a counter another kernel still reads.
@@ -44,14 +43,23 @@ struct WaveBuffers {
     size_t bytes = 0;
 };
 
+// A scene's device data is ONE allocation ("arena"); every array sits at a fixed offset, so a replica on another GPU is
+// the same bytes at another base address (multi.cu broadcasts the arena instead of rebuilding the LBVH on every GPU).
+struct ArenaLayout { size_t nodes = 0, tris = 0, nrm = 0, sph = 0, mat = 0, kind = 0, mesh = 0, etris = 0, ekind = 0, total = 0; };
+struct Replica { int device = 0; char* arena = nullptr; size_t arena_bytes = 0; SceneDev dev{}; int sm_count = 148; };
+struct SceneUse { int device; cudaStream_t stream; cudaEvent_t ev; };   // last work enqueued on a stream that reads the scene
+
 struct Scene {
-    int device = 0;
-    SceneDev dev{};
+    int device = 0;              // device of replica 0 (the one that uploaded and built)
+    SceneDev dev{};              // = rep[0].dev
     std::vector<MeshDev> meshes_h;
-    std::vector<void*> allocs;   // every cudaMalloc owned by the scene (one arena)
-    size_t arena_bytes = 0;
+    std::vector<Replica> rep;    // one per local device of the communicator the scene was created under (else one)
+    ArenaLayout lay{};
+    uint32_t n_elems = 0, n_meshes = 0, n_etris = 0;
     rbrt_scene_info info{};
     int sm_count = 148;
+    bool collective = false;     // created under a communicator: renders with shard_count == 0 are sharded over its ranks
+    mutable std::vector<SceneUse> uses;
 };
 
 // Everything a wavefront kernel needs, passed by value (kernel parameter space).
@@ -78,9 +86,29 @@ struct WaveParams {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
+std::recursive_mutex& api_mutex();          // serialises every entry point (api.cu)
+uint64_t pool_limit_bytes();                // rbrt_gpu_set_pool_limit
+SceneDev make_scene_dev(char* base, const ArenaLayout& lay, uint32_t n_elems, uint32_t n_meshes, uint32_t n_etris);
+
 // render.cu
-int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
-                 const rbrt_render_opts* opts, float4* const* d_accum, cudaStream_t st, rbrt_stats* stats);
+// What a render left behind for its statistics (device counters, events); collect_stats() waits for the frame and reads them.
+struct RenderJob {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    WaveBuffers* wb = nullptr;
+    ShardDev sh{};
+    uint32_t P = 0, n_frames = 0, W = 0, H = 0, launches = 0, iterations = 0, batch_iters = 0, flags = 0, max_depth = 0;
+    bool rendered = false;
+    ~RenderJob() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
+};
+int make_shard(const rbrt_render_opts& o, uint32_t W, uint32_t H, uint32_t spp, ShardDev* out);
+// Renders replica `li` of the scene on that replica's device (the caller has made it current).  With `job` the call only
+// enqueues and fills *job (collect_stats later); without, stats (may be NULL = enqueue only) are collected before returning.
+int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
+                 const rbrt_render_opts* opts, float4* const* d_accum, cudaStream_t st, rbrt_stats* stats, RenderJob* job = nullptr);
+int collect_stats(RenderJob& job, rbrt_stats* stats);
+int trace_rays_wavefront(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, rbrt_hit* d_hits, unsigned long long* d_stats, cudaStream_t st);
+int scatter_device(const rbrt_scatter_in* d_in, uint64_t n, uint64_t seed, rbrt_scatter_out* d_out, cudaStream_t st);
+void note_scene_use(const Scene& sc, int device, cudaStream_t st);   // records the scene's last-use event on `st`
 int finalize(const float4* d_accum, uint32_t W, uint32_t H, uint32_t spp, uint8_t* d_rgb, float* d_hdr, cudaStream_t st);
 int trace_rays_device(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, uint32_t mode, rbrt_hit* d_hits,
                       unsigned long long* d_stats, cudaStream_t st);

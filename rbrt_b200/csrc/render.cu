@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include "engine.cuh"
 #include "intersect.cuh"
 #include "shade.cuh"
@@ -745,6 +746,80 @@ __global__ void __launch_bounds__(256) k_primary_rays(CamDev cam, uint32_t key0,
     rays[px] = r;
 }
 
+// scatter() in isolation (materials.rs:4-12): the same device function the shade kernels call, one item per thread
+__global__ void __launch_bounds__(256) k_scatter_kat(const rbrt_scatter_in* __restrict__ in, uint64_t n, uint32_t key0, uint32_t key1,
+                                                     rbrt_scatter_out* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const rbrt_scatter_in q = in[i];
+    RngKey key; key.k0 = key0; key.k1 = key1;
+    const f3 point = mk3(q.hit_point.x, q.hit_point.y, q.hit_point.z), normal = mk3(q.hit_normal.x, q.hit_normal.y, q.hit_normal.z);
+    f3 out_d = mk3(0, 0, 0);
+    const bool ok = scatter(q.material.kind, make_float4(q.material.albedo.x, q.material.albedo.y, q.material.albedo.z, q.material.param),
+                            mk3(q.in_ray.direction.x, q.in_ray.direction.y, q.in_ray.direction.z), point, normal, key, q.pixel, q.sample, q.bounce, out_d);
+    rbrt_scatter_out r;
+    r.scattered = ok ? 1 : 0;
+    const bool glass = q.material.kind == 2u;                             // attenuation: albedo, or (1,1,1) for dielectrics (dielectric.rs:19)
+    r.attenuation.x = glass ? 1.0f : q.material.albedo.x; r.attenuation.y = glass ? 1.0f : q.material.albedo.y; r.attenuation.z = glass ? 1.0f : q.material.albedo.z;
+    r.out_ray.origin = q.hit_point;
+    r.out_ray.direction.x = out_d.x; r.out_ray.direction.y = out_d.y; r.out_ray.direction.z = out_d.z;
+    out[i] = r;
+}
+
+// ------------------------------------------------------------------ parity hook through the renderer's own kernels
+// Caller-supplied rays become "paths" pid = ray index at bounce iteration 0: stage A exactly as k_generate runs it, then
+// k_trace itself (persistent warps, quota, dynamic fetch, warp-voted traversal), then the records are read back.
+// out[pid].w is pre-set to a NaN pattern; a path that ended (miss -> sky, NaN -> black) has it overwritten with 0.
+template <bool ET>
+__global__ void __launch_bounds__(256) k_rays_stage_a(WaveParams P, const rbrt_ray* __restrict__ rays, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_groups = (n + 31) >> 5;
+    uint32_t nan_count = 0;
+    for (uint32_t g0 = warp * ROUNDS; g0 < n_groups; g0 += n_warps * ROUNDS) {
+        Deferred df; df.clear();
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            const uint32_t pid = ((g0 + r) << 5) + lane;
+            if (g0 + r >= n_groups || pid >= n) continue;
+            const rbrt_ray q = rays[pid];
+            df.set(r, stage_a<ET>(P, 0, pid, mk3(q.origin.x, q.origin.y, q.origin.z), mk3(q.direction.x, q.direction.y, q.direction.z), nan_count), pid);
+        }
+        flush(P, 0, df);
+    }
+    for (int off = 16; off; off >>= 1) nan_count += __shfl_down_sync(FULL_MASK, nan_count, off);
+    if (lane == 0 && nan_count) atomicAdd(&P.stats[ST_NAN], (unsigned long long)nan_count);
+}
+
+__global__ void __launch_bounds__(256) k_rays_collect(WaveParams P, const rbrt_ray* __restrict__ rays, uint32_t n, rbrt_hit* __restrict__ hits) {
+    const uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= n) return;
+    rbrt_hit out;
+    out.kind = RBRT_HIT_NONE; out.elem_idx = 0; out.tri_idx = 0; out.t = 0.0f; out.dist = 0.0f;
+    out.point.x = out.point.y = out.point.z = 0.0f; out.normal.x = out.normal.y = out.normal.z = 0.0f;
+    if (__float_as_uint(P.out[pid].w) == 0xFFFFFFFFu) {                   // the path did not end: a hit is waiting to be shaded
+        const uint4 h = load_hit(P, pid);
+        const rbrt_ray q = rays[pid];
+        const f3 o = mk3(q.origin.x, q.origin.y, q.origin.z), d = mk3(q.direction.x, q.direction.y, q.direction.z);
+        const float t = __uint_as_float(h.x);
+        const f3 p = o + t * d;
+        f3 nrm;
+        if (h.w == 0u) {
+            nrm = element_normal(P.S, h.y, p);
+            out.kind = (P.S.n_etris && __ldg(P.S.elem_kind + h.y)) ? RBRT_HIT_TRIANGLE : RBRT_HIT_SPHERE;
+            out.elem_idx = h.y;
+        } else {
+            const uint32_t mi = h.y - P.S.n_spheres;
+            const float4 nn = __ldg(P.S.normals + P.S.meshes[mi].nrm_base + h.z); nrm = mk3(nn.x, nn.y, nn.z);
+            out.kind = RBRT_HIT_MESH; out.elem_idx = mi; out.tri_idx = h.z;
+        }
+        out.t = t; out.dist = len3(o - p);                                // sphere.rs:50, mesh.rs:248
+        out.point.x = p.x; out.point.y = p.y; out.point.z = p.z;
+        out.normal.x = nrm.x; out.normal.y = nrm.y; out.normal.z = nrm.z;
+    }
+    hits[pid] = out;
+}
+
 // ====================================================================== host side
 static CamDev make_cam(const rbrt_camera& c) {
     CamDev d;
@@ -801,19 +876,17 @@ static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
 // 0.3-1 M rays that run at a third of the dense rate and each end in a drain as long as their slowest ray), and two
 // or four frames per batch give the kernels the size they have on fewer GPUs.  Every path keeps its own (pixel,
 // sample, frame) identity, so each image is bit-identical to a lone render of that frame.
-int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
-                 const rbrt_render_opts* opts, float4* const* d_accum, cudaStream_t st, rbrt_stats* stats) {
-    if (!n_frames || n_frames > RBRT_MAX_FRAMES) { set_error("n_frames must be 1..%d", RBRT_MAX_FRAMES); return RBRT_E_INVALID; }
-    const rbrt_camera& cam = cams[0];
-    const uint32_t W = cam.img_width_pix, H = cam.img_height_pix;
-    for (uint32_t f = 1; f < n_frames; ++f)
-        if (cams[f].img_width_pix != W || cams[f].img_height_pix != H) { set_error("frames of one batch must have the same image size"); return RBRT_E_INVALID; }
-    if (!W || !H || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
-    if ((uint64_t)W * H > 0x7FFFFFFFull) { set_error("image too large"); return RBRT_E_INVALID; }
-    rbrt_render_opts o{}; if (opts) o = *opts;
-    const uint32_t max_depth = o.max_depth ? o.max_depth : 50;
-    if (max_depth > 1024) { set_error("max_depth > 1024"); return RBRT_E_INVALID; }
-    if (o.integrator != 0) { set_error("unknown integrator %u", o.integrator); return RBRT_E_INVALID; }
+void note_scene_use(const Scene& sc, int device, cudaStream_t st) {
+    for (SceneUse& u : sc.uses)
+        if (u.device == device && u.stream == st) { cudaEventRecord(u.ev, st); return; }
+    SceneUse u{device, st, nullptr};
+    if (cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEventRecord(u.ev, st);
+    sc.uses.push_back(u);
+}
+
+// Pixel / sample shard of one rank (common.cuh ShardDev) from the render options
+int make_shard(const rbrt_render_opts& o, uint32_t W, uint32_t H, uint32_t spp, ShardDev* out) {
     ShardDev sh;
     sh.rank = 0; sh.count = 1; sh.s0 = 0; sh.s1 = spp;
     sh.tiles_x = (W + 7) / 8;
@@ -828,12 +901,34 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
         } else { set_error("shard_count > 1 needs shard_mode TILES or SAMPLES"); return RBRT_E_INVALID; }
     }
     sh.tiles_mine = sh.tiles_total > sh.rank ? (sh.tiles_total - sh.rank + sh.count - 1) / sh.count : 0;
+    *out = sh;
+    return RBRT_OK;
+}
+
+int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
+                 const rbrt_render_opts* opts, float4* const* d_accum, cudaStream_t st, rbrt_stats* stats, RenderJob* job_out) {
+    const Replica& rp = sc.rep[li];
+    RenderJob local_job;
+    RenderJob& job = job_out ? *job_out : local_job;
+    if (!n_frames || n_frames > RBRT_MAX_FRAMES) { set_error("n_frames must be 1..%d", RBRT_MAX_FRAMES); return RBRT_E_INVALID; }
+    const rbrt_camera& cam = cams[0];
+    const uint32_t W = cam.img_width_pix, H = cam.img_height_pix;
+    for (uint32_t f = 1; f < n_frames; ++f)
+        if (cams[f].img_width_pix != W || cams[f].img_height_pix != H) { set_error("frames of one batch must have the same image size"); return RBRT_E_INVALID; }
+    if (!W || !H || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
+    if ((uint64_t)W * H > 0x7FFFFFFFull) { set_error("image too large"); return RBRT_E_INVALID; }
+    rbrt_render_opts o{}; if (opts) o = *opts;
+    const uint32_t max_depth = o.max_depth ? o.max_depth : 50;
+    if (max_depth > 1024) { set_error("max_depth > 1024"); return RBRT_E_INVALID; }
+    if (o.integrator != 0) { set_error("unknown integrator %u", o.integrator); return RBRT_E_INVALID; }
+    ShardDev sh;
+    { int rc_sh = make_shard(o, W, H, spp, &sh); if (rc_sh) return rc_sh; }
     const uint32_t P = sh.tiles_mine * 32;
-    cudaEvent_t ev0, ev1;
-    CKR(cudaEventCreate(&ev0)); CKR(cudaEventCreate(&ev1));
+    CKR(cudaEventCreate(&job.ev0)); CKR(cudaEventCreate(&job.ev1));
+    const cudaEvent_t ev0 = job.ev0, ev1 = job.ev1;
     for (uint32_t f = 0; f < n_frames; ++f) CKR(cudaMemsetAsync(d_accum[f], 0, 16ull * W * H, st));
     uint32_t launches = 0, iterations = 0, batch_iters = 0;
-    WaveBuffers& wb = device_wave_buffers(sc.device, (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT));
+    WaveBuffers& wb = device_wave_buffers(rp.device, (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT));
     CKR(cudaEventRecord(ev0, st));
     if (P && sh.s1 > sh.s0) {
         // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is
@@ -841,10 +936,12 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
         // small batch as for a large one: the default is therefore "as many paths as fit" — up to 2^27 paths
         // (108 + 2*(max_depth - 12) bytes of wavefront state each: 24.7 GB at depth 50) and at most half of the free HBM.
         uint32_t target = o.batch_paths;
+        const uint64_t PF = (uint64_t)P * n_frames;                                           // paths of one sample of every frame of the batch
+        if (PF > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
+        const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
+        const uint64_t limit_paths = pool_limit_bytes() ? std::max<uint64_t>(pool_limit_bytes() / per_path, 1) : ~0ull;   // rbrt_gpu_set_pool_limit
         if (!target) {
-            const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
-            const uint64_t PF = (uint64_t)P * n_frames;                                       // paths of one sample of every frame of the batch
-            const uint64_t want = std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * PF, 1ull << 27);
+            const uint64_t want = std::min<uint64_t>(std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * PF, 1ull << 27), limit_paths);
             const uint64_t want_sb = std::max<uint64_t>(want / PF, 1);                      // whole samples per batch
             if (wb.cap >= want_sb * PF && wb.depth_cap >= max_depth) target = (uint32_t)want;  // the pool already holds it: no driver query
                                                                                             // (cudaMemGetInfo takes tens of ms at times)
@@ -856,14 +953,16 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
                 target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
             }
         }
-        uint32_t S_b = target / (P * n_frames); if (S_b < 1) S_b = 1; if (S_b > sh.s1 - sh.s0) S_b = sh.s1 - sh.s0;
-        if ((uint64_t)S_b * P * n_frames > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
-        const uint32_t cap = S_b * P * n_frames;
+        if ((uint64_t)target > limit_paths) target = (uint32_t)limit_paths;
+        uint64_t S_b64 = (uint64_t)target / PF; if (S_b64 < 1) S_b64 = 1; if (S_b64 > sh.s1 - sh.s0) S_b64 = sh.s1 - sh.s0;
+        if (S_b64 * PF > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
+        const uint32_t S_b = (uint32_t)S_b64;
+        const uint32_t cap = (uint32_t)(S_b64 * PF);
         int rc = ensure_wave_buffers(wb, cap, max_depth);
         if (rc) return rc;
         CKR(cudaMemsetAsync(wb.stats, 0, 8 * ST_COUNT, st));
         WaveParams wp;
-        wp.S = sc.dev; wp.sh = sh; wp.n_frames = n_frames;
+        wp.S = rp.dev; wp.sh = sh; wp.n_frames = n_frames;
         for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) {
             const uint32_t g = f < n_frames ? f : 0;
             const uint64_t seed = seeds ? seeds[g] : o.seed;
@@ -878,23 +977,24 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
         wp.rec = wb.rec; wp.candq = wb.candq;
         for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
-        const int grid = sc.sm_count * 8;                                  // producers / brute: 256-thread blocks
+        const int sm_count = rp.sm_count;
+        const int grid = sm_count * 8;                                     // producers / brute: 256-thread blocks
         int per_sm = 0;                                                   // k_trace: persistent blocks, exactly one resident wave
         static int per_sm_cached = 0, fin_per_sm_cached = 0;             // occupancy queries are pure functions of the kernels
         if (!per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_trace<false>, TRACE_THREADS, 0));
         per_sm = per_sm_cached;
-        const int grid_trace = sc.sm_count * (per_sm > 0 ? per_sm : 4);
+        const int grid_trace = sm_count * (per_sm > 0 ? per_sm : 4);
         if (!fin_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm_cached, k_finish<false, false, false>, 256, 0));
         const int fin_per_sm = fin_per_sm_cached;                         // k_finish: one resident wave of 256-thread blocks
-        const int grid_fin = sc.sm_count * (fin_per_sm > 0 ? fin_per_sm : 2);
+        const int grid_fin = sm_count * (fin_per_sm > 0 ? fin_per_sm : 2);
         static int tail_per_sm_cached = 0;
         if (!tail_per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm_cached, k_tail<false, true>, TAIL_THREADS, 0));
-        const int grid_tail = sc.sm_count * (tail_per_sm_cached > 0 ? tail_per_sm_cached : 2);
+        const int grid_tail = sm_count * (tail_per_sm_cached > 0 ? tail_per_sm_cached : 2);
         const char* tail_env = getenv("RBRT_TAIL_RAYS");                  // tuning knob
         // hand-over threshold: brute mode one ray per resident lane of k_finish; BVH mode (asynchronous k_tail) 2^18 rays (swept on C2, C3, C4 at 1 and 8 ranks: scripts/tail_sweep.py)
         const uint32_t tail_rays = (o.flags & RBRT_OPT_NO_TAIL_KERNEL) ? 0u : (tail_env ? (uint32_t)atoi(tail_env) : (o.trace_mode == RBRT_TRACE_BRUTE ? (uint32_t)grid_fin * 256u : (1u << 18)));
         const bool brute = o.trace_mode == RBRT_TRACE_BRUTE;
-        const bool et = sc.dev.n_etris > 0;                               // BasicTriangle elements present: the ET kernel instantiations
+        const bool et = rp.dev.n_etris > 0;                               // BasicTriangle elements present: the ET kernel instantiations
         const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
         const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
         size_t ev_used = 0;
@@ -937,11 +1037,23 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
         }
     }
     CKR(cudaEventRecord(ev1, st));
-    if (stats) {
+    note_scene_use(sc, rp.device, st);
+    job.wb = &wb; job.sh = sh; job.P = P; job.n_frames = n_frames; job.W = W; job.H = H; job.launches = launches; job.iterations = iterations;
+    job.batch_iters = batch_iters; job.flags = o.flags; job.max_depth = max_depth; job.rendered = P && sh.s1 > sh.s0;
+    if (stats && !job_out) return collect_stats(job, stats);
+    return RBRT_OK;
+}
+
+int collect_stats(RenderJob& job, rbrt_stats* stats) {
+    WaveBuffers& wb = *job.wb;
+    const ShardDev& sh = job.sh;
+    const uint32_t W = job.W, H = job.H, iterations = job.iterations, max_depth = job.max_depth;
+    const cudaEvent_t ev0 = job.ev0, ev1 = job.ev1;
+    {
         CKR(cudaEventSynchronize(ev1));
         float ms = 0; CKR(cudaEventElapsedTime(&ms, ev0, ev1));
         unsigned long long h[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (wb.stats && P && sh.s1 > sh.s0) CKR(cudaMemcpy(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost));
+        if (wb.stats && job.rendered) CKR(cudaMemcpy(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost));
         stats->rays = h[ST_RAYS]; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS] + h[ST_TAIL_TRIS]; stats->traversed_rays = h[ST_CAND] + h[ST_TAIL_CAND];
         stats->node_visits += h[ST_TAIL_NODES];
         stats->tail_node_visits = h[ST_TAIL_NODES]; stats->tail_tri_tests = h[ST_TAIL_TRIS]; stats->tail_traversed_rays = h[ST_TAIL_CAND];
@@ -951,9 +1063,9 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
             uint32_t w = W - tx * 8 < 8 ? W - tx * 8 : 8, hh = H - ty * 4 < 4 ? H - ty * 4 : 4;
             valid_px += (uint64_t)w * hh;
         }
-        stats->paths = valid_px * (sh.s1 - sh.s0) * n_frames;
-        stats->ms_device = ms; stats->launches = launches; stats->iterations = iterations;
-        if (P && sh.s1 > sh.s0 && (o.flags & RBRT_OPT_TIME_KERNELS)) {
+        stats->paths = valid_px * (sh.s1 - sh.s0) * job.n_frames;
+        stats->ms_device = ms; stats->launches = job.launches; stats->iterations = iterations;
+        if (job.rendered && (job.flags & RBRT_OPT_TIME_KERNELS)) {
             double tr = 0;
             for (size_t i = 0; i + 1 < wb.ev.size() && i + 1 < 2ull * iterations; i += 2) {
                 float t = 0; CKR(cudaEventElapsedTime(&t, wb.ev[i], wb.ev[i + 1])); tr += t;
@@ -962,7 +1074,7 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
             if (getenv("RBRT_DEBUG_ITERS")) {                              // per-iteration trace time + queue sizes of the LAST batch
                 std::vector<IterCtr> hc(max_depth + 2);
                 CKR(cudaMemcpy(hc.data(), wb.ctr, sizeof(IterCtr) * (max_depth + 2), cudaMemcpyDeviceToHost));
-                size_t per_batch = batch_iters, first = 2 * (iterations - per_batch);
+                size_t per_batch = job.batch_iters, first = 2 * (iterations - per_batch);
                 float t_first = 0; cudaEventElapsedTime(&t_first, ev0, wb.ev[first]);
                 fprintf(stderr, "setup + generate (ev0 -> first trace): %.3f ms; tail kernel ran at it %d\n", t_first, (int)hc[0].pad - 1);
                 for (uint32_t it = 0; it < per_batch; ++it) {
@@ -975,7 +1087,6 @@ int render_accum(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds
             }
         }
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     return RBRT_OK;
 }
 
@@ -995,6 +1106,55 @@ int trace_rays_device(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, uint3
     if (mode == RBRT_TRACE_BRUTE) k_trace_rays<true><<<g, 256, 0, st>>>(sc.dev, d_rays, n, d_hits, d_stats);
     else k_trace_rays<false><<<g, 256, 0, st>>>(sc.dev, d_rays, n, d_hits, d_stats);
     CKR(cudaGetLastError());
+    return RBRT_OK;
+}
+
+int scatter_device(const rbrt_scatter_in* d_in, uint64_t n, uint64_t seed, rbrt_scatter_out* d_out, cudaStream_t st) {
+    if (!n) return RBRT_OK;
+    k_scatter_kat<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, n, (uint32_t)seed, (uint32_t)(seed >> 32), d_out);
+    CKR(cudaGetLastError());
+    return RBRT_OK;
+}
+
+// RBRT_TRACE_WAVEFRONT: the caller's rays through stage A + k_trace (see k_rays_stage_a).  Uses wavefront pool 0 of the device.
+int trace_rays_wavefront(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, rbrt_hit* d_hits, unsigned long long* d_stats, cudaStream_t st) {
+    const Replica& rp = sc.rep[0];
+    WaveBuffers& wb = device_wave_buffers(rp.device, 0);
+    const uint64_t chunk = 1ull << 24;
+    static int per_sm_cached = 0;
+    if (!per_sm_cached) CKR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, k_trace<false>, TRACE_THREADS, 0));
+    const bool et = rp.dev.n_etris > 0;
+    for (uint64_t base = 0; base < n; base += chunk) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - base);
+        const uint32_t cap = (m + 31u) & ~31u;
+        int rc = ensure_wave_buffers(wb, std::max<uint32_t>(cap, 1u << 16), 50);
+        if (rc) return rc;
+        WaveParams wp;
+        memset(&wp, 0, sizeof(wp));
+        wp.S = rp.dev; wp.n_frames = 1; wp.cap = wb.cap; wp.paths_px = cap; wp.fd_paths_px = make_fastdiv(cap); wp.fd_s_count = make_fastdiv(1);
+        wp.s_count = 1; wp.max_depth = 50; wp.fetch_thr = FETCH_THRESHOLD; wp.tail_thr = TAIL_FETCH_THRESHOLD;
+        wp.rec = wb.rec; wp.candq = wb.candq;
+        for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
+        wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
+        CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * 52, st));
+        CKR(cudaMemsetAsync(wb.stats, 0, 8 * ST_COUNT, st));
+        CKR(cudaMemsetAsync(wb.out, 0xFF, 16ull * cap, st));
+        const int grid = rp.sm_count * 8;
+        if (et) k_rays_stage_a<true><<<grid, 256, 0, st>>>(wp, d_rays + base, m); else k_rays_stage_a<false><<<grid, 256, 0, st>>>(wp, d_rays + base, m);
+        if (d_stats) k_trace<true><<<rp.sm_count * std::max(per_sm_cached, 1), TRACE_THREADS, 0, st>>>(wp, 0);
+        else k_trace<false><<<rp.sm_count * std::max(per_sm_cached, 1), TRACE_THREADS, 0, st>>>(wp, 0);
+        k_rays_collect<<<(m + 255) / 256, 256, 0, st>>>(wp, d_rays + base, m, d_hits + base);
+        CKR(cudaGetLastError());
+        if (d_stats) {                                                    // accumulate this chunk's counters into the caller's block
+            CKR(cudaStreamSynchronize(st));
+            unsigned long long h[ST_COUNT], acc[ST_COUNT];
+            CKR(cudaMemcpy(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost));
+            CKR(cudaMemcpy(acc, d_stats, sizeof(acc), cudaMemcpyDeviceToHost));
+            for (int k = 0; k < ST_COUNT; ++k) acc[k] += h[k];
+            CKR(cudaMemcpy(d_stats, acc, sizeof(acc), cudaMemcpyHostToDevice));
+        }
+    }
+    note_scene_use(sc, rp.device, st);
     return RBRT_OK;
 }
 

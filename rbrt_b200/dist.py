@@ -1,12 +1,13 @@
-"""Multi-GPU rendering: one process per GPU (torch.distributed), the image sharded by interleaved
-8x4-pixel tiles or by sample range, no data-path collective except ONE reduce of the per-pixel f32
-accumulation buffers to rank 0 (NCCL over NVLink on GPUs; gloo on CPU in tests).
+"""Multi-GPU rendering, one process per GPU.  The sharding, the per-GPU finalise and the gather / reduce on rank 0 live INSIDE
+the C library (csrc/multi.cu: NCCL over NVLink); this module only brings the library's communicator up from an existing
+torch.distributed process group (torch is the plumbing that carries the 128-byte NCCL unique id between the ranks).
 
-The reference's only parallelism is rayon over image columns (lib.rs:84-86): pixels and samples are
-independent, so the path shards without any exchange step.  Tile sharding gives an image bit-identical
-to the 1-GPU render (every pixel is summed by exactly one rank, the others add +0.0); sample sharding
-changes the f32 summation order across ranks only.
+The reference's only parallelism is rayon over image columns (lib.rs:84-86): pixels and samples are independent, so the path
+shards without any exchange step.  Tile sharding gives an image bit-identical to the 1-GPU render (every pixel is summed and
+finalised by exactly one rank); sample sharding changes the f32 summation order across ranks only.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _abi
@@ -23,42 +24,56 @@ def tile_owner(row, col, width, count):
     return ((row // 4) * tiles_x + (col // 8)) % count
 
 
-def reduce_and_finalize(accum, width, height, num_samples, finalize_fn, dist=None, dst=0):
-    """Sum the ranks' accumulation buffers on `dst` and apply lib.rs:101,116-122 there.
-    accum: torch tensor [H*W*4] f32 on the backend's device.  Returns finalize_fn(accum) on dst, None elsewhere."""
-    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
-        if dist.get_rank() != dst:
-            return None
-    return finalize_fn(accum, width, height, num_samples)
+def exchange_unique_id(dist, make_id, nbytes=_abi.COMM_ID_BYTES):
+    """Rank 0 calls make_id() -> bytes; every rank returns those bytes (one broadcast over the torch process group, any backend)."""
+    import torch
+    rank = dist.get_rank()
+    buf = torch.zeros(nbytes, dtype=torch.uint8)
+    if rank == 0:
+        raw = make_id()
+        if len(raw) != nbytes:
+            raise ValueError(f"unique id must be {nbytes} bytes")
+        buf = torch.tensor(list(raw), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        buf = buf.cuda()
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().tolist())
+
+
+def init_comm(dist=None):
+    """Bring up the library's communicator over the ranks of the default torch.distributed process group.  Call after
+    torch.cuda.set_device(local_rank) and rbrt_b200.gpu_init(local_rank).  Returns the rbrt_comm_info dict."""
+    if dist is None:
+        import torch.distributed as dist
+    lib = _abi.lib()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        def make_id():
+            raw = (C.c_uint8 * _abi.COMM_ID_BYTES)()
+            _abi.check(lib.rbrt_gpu_comm_unique_id(raw))
+            return bytes(raw)
+        uid = exchange_unique_id(dist, make_id)
+        raw = (C.c_uint8 * _abi.COMM_ID_BYTES)(*uid)
+        _abi.check(lib.rbrt_gpu_comm_init_rank(raw, dist.get_rank(), dist.get_world_size()))
+    info = _abi.CommInfoC()
+    _abi.check(lib.rbrt_gpu_comm_info(info))
+    return info.as_dict()
 
 
 def render_scene_distributed(cam, num_samples, scene, shard_mode=_abi.SHARD_TILES, stats=None, hdr=False, **opts):
-    """render_scene across all ranks of the default process group; rank 0 returns the ImageBuffer
-    (or the HDR array), other ranks return None.  Call after torch.cuda.set_device(local_rank) and
-    rbrt_gpu_init(local_rank)."""
-    import torch
-    import torch.distributed as dist
-
+    """render_scene across all ranks of the library's communicator; rank 0 returns the ImageBuffer (or the HDR array), other
+    ranks return None.  Without a communicator this is the 1-GPU render."""
     lib = _abi.lib()
+    info = _abi.CommInfoC()
+    _abi.check(lib.rbrt_gpu_comm_info(info))
+    root = not info.active or info.rank == 0
     W, H = cam.img_width_pix, cam.img_height_pix
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    o = make_opts(shard_mode=shard_mode if world > 1 else _abi.SHARD_NONE, shard_rank=rank, shard_count=world, **opts)
-    accum = torch.empty(H * W * 4, dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    o = make_opts(shard_mode=shard_mode, **opts)
     st = _abi.StatsC()
-    _abi.check(lib.rbrt_gpu_render_accum_device(scene.handle(), cam.to_c(), int(num_samples), o, accum.data_ptr(), stream, st))
+    out = np.empty((H, W, 3), dtype=np.float32 if hdr else np.uint8) if root else None
+    fn = lib.rbrt_gpu_render_hdr if hdr else lib.rbrt_gpu_render
+    _abi.check(fn(scene.handle(), cam.to_c(), int(num_samples), o, out.ctypes.data if root else None, st))
     if stats is not None:
         stats.update(st.as_dict())
-
-    def fin(acc, w, h, spp):
-        if hdr:
-            out = torch.empty(h * w * 3, dtype=torch.float32, device="cuda")
-            _abi.check(lib.rbrt_gpu_finalize_device(acc.data_ptr(), w, h, spp, None, out.data_ptr(), stream))
-            return out.cpu().numpy().reshape(h, w, 3)
-        out = torch.empty(h * w * 3, dtype=torch.uint8, device="cuda")
-        _abi.check(lib.rbrt_gpu_finalize_device(acc.data_ptr(), w, h, spp, out.data_ptr(), None, stream))
-        return ImageBuffer(out.cpu().numpy().reshape(h, w, 3))
-
-    return reduce_and_finalize(accum, W, H, int(num_samples), fin, dist if world > 1 else None)
+    if not root:
+        return None
+    return out if hdr else ImageBuffer(out)

@@ -20,8 +20,9 @@ Every frame is computed by the same kernels on the same inputs as a lone render_
             ...
     rest = pipe.drain()
 
-With torch.distributed initialised every rank calls submit() in the same order; the reduce of the f32 accumulation
-buffers to rank 0 (dist.py; one per group) is enqueued on the group's stream and rank 0 gets the images.
+Multi-GPU: under a library communicator (rbrt_gpu_init_multi, or rbrt_b200.dist.init_comm() for one process per GPU) every
+rank calls submit() in the same order; a group is ONE call of rbrt_gpu_render_frames_device — shard render, per-GPU
+finalise, gather on rank 0, all enqueued on the group's stream — and rank 0 gets the images.
 """
 import ctypes as C
 
@@ -32,7 +33,6 @@ from .render import ImageBuffer, make_opts
 class _Slot:
     def __init__(self, torch, n_px, fpb, host_output, hdr):
         self.stream = torch.cuda.Stream()
-        self.accum = torch.empty((fpb, n_px * 4), dtype=torch.float32, device="cuda")
         self.out = torch.empty((fpb, n_px * 3), dtype=torch.float32 if hdr else torch.uint8, device="cuda")
         self.host = torch.empty((fpb, n_px * 3), dtype=self.out.dtype, pin_memory=True) if host_output else None
         self.done = torch.cuda.Event()
@@ -44,22 +44,23 @@ class _Slot:
 class FramePipeline:
     def __init__(self, width, height, depth=2, host_output=True, hdr=False, shard_mode=_abi.SHARD_TILES, frames_per_batch=1):
         import torch
-        import torch.distributed as dist
         if depth not in (1, 2, 3, 4):
             raise ValueError("depth must be 1..4 (the library keeps four pools of wavefront state per device)")
         if not 1 <= frames_per_batch <= _abi.MAX_FRAMES:
             raise ValueError(f"frames_per_batch must be 1..{_abi.MAX_FRAMES}")
-        self._torch, self._dist = torch, dist
+        self._torch = torch
         self.width, self.height, self.depth, self.hdr, self.fpb = int(width), int(height), depth, hdr, int(frames_per_batch)
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self._lib = _abi.lib()
+        info = _abi.CommInfoC()
+        _abi.check(self._lib.rbrt_gpu_comm_info(info))
+        self.world = info.world if info.active else 1
+        self.rank = info.rank if info.active else 0
         self.shard_mode = shard_mode
         self._slots = [self._make_slot(host_output and self.rank == 0) for _ in range(depth)]
         self._n = 0                  # groups launched
         self._pending = []           # frames of the group being collected: (cam_c, seed, tag)
         self._pending_key = None     # (scene, spp, opts) the pending frames share
         self._pending_hv = None
-        self._lib = _abi.lib()
 
     # ------------------------------------------------------------------ internals
     def _make_slot(self, host_output):
@@ -80,6 +81,7 @@ class FramePipeline:
                 else:
                     with self._torch.cuda.stream(slot.stream):   # a copy ordered before the slot's next group overwrites it
                         img = slot.out[k].clone()
+                    img.record_stream(self._torch.cuda.current_stream())   # the caller reads it on ITS stream: keep the block until then
             res.append((img, tag))
         if self.rank == 0 and slot.host is None and tags:
             slot.stream.synchronize()                          # the copies above (the group itself finished long ago)
@@ -97,34 +99,22 @@ class FramePipeline:
         return finished
 
     def _enqueue(self, slot, frames, scene, spp, opts):
-        """Enqueue one group of frames (render -> [reduce] -> finalize -> [copy to pinned host memory]) on the slot's stream."""
-        torch, dist = self._torch, self._dist
-        sm, sr, sc = opts.pop("shard_mode", _abi.SHARD_NONE), opts.pop("shard_rank", 0), opts.pop("shard_count", 1)
-        if self.world > 1:                                    # one process per GPU: the process group decides the shard
-            sm, sr, sc = self.shard_mode, self.rank, self.world
-        o = make_opts(shard_mode=sm, shard_rank=sr, shard_count=sc, pool=self._n % self.depth, **opts)
+        """Enqueue one group of frames (render -> finalise -> [gather on rank 0] -> [copy to pinned host memory]) on the slot's stream."""
+        torch = self._torch
+        opts.setdefault("shard_mode", self.shard_mode if self.world > 1 else _abi.SHARD_NONE)
+        o = make_opts(pool=self._n % self.depth, **opts)    # shard_count 0 (default): the library shards over its communicator
         handle = scene.handle() if hasattr(scene, "handle") else scene
-        nf, W, H = len(frames), self.width, self.height
+        nf = len(frames)
         s = slot.stream
         with torch.cuda.stream(s):
-            # stats = NULL: the calls only enqueue (no event synchronisation inside the library)
-            if nf == 1:
-                cam_c, seed, _ = frames[0]
-                o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-                _abi.check(self._lib.rbrt_gpu_render_accum_device(handle, cam_c, int(spp), o, slot.accum[0].data_ptr(), s.cuda_stream, None))
-            else:
-                cams = (_abi.CameraC * nf)(*[f[0] for f in frames])
-                seeds = (C.c_uint64 * nf)(*[int(f[1]) & 0xFFFFFFFFFFFFFFFF for f in frames])
-                accs = (C.c_void_p * nf)(*[slot.accum[k].data_ptr() for k in range(nf)])
-                _abi.check(self._lib.rbrt_gpu_render_accum_device_frames(handle, cams, seeds, nf, int(spp), o, accs, s.cuda_stream, None))
-            if self.world > 1:
-                dist.reduce(slot.accum[:nf], dst=0, op=dist.ReduceOp.SUM)
-            if self.rank == 0:
-                for k in range(nf):
-                    rgb, hdr = (None, slot.out[k].data_ptr()) if self.hdr else (slot.out[k].data_ptr(), None)
-                    _abi.check(self._lib.rbrt_gpu_finalize_device(slot.accum[k].data_ptr(), W, H, int(spp), rgb, hdr, s.cuda_stream))
-                if slot.host is not None:
-                    slot.host[:nf].copy_(slot.out[:nf], non_blocking=True)
+            cams = (_abi.CameraC * nf)(*[f[0] for f in frames])
+            seeds = (C.c_uint64 * nf)(*[int(f[1]) & 0xFFFFFFFFFFFFFFFF for f in frames])
+            outs = (C.c_void_p * nf)(*[slot.out[k].data_ptr() for k in range(nf)])
+            rgb, hdr = (None, outs) if self.hdr else (outs, None)
+            # stats = NULL: the call only enqueues (no event synchronisation inside the library)
+            _abi.check(self._lib.rbrt_gpu_render_frames_device(handle, cams, seeds, nf, int(spp), o, rgb, hdr, s.cuda_stream, None))
+            if self.rank == 0 and slot.host is not None:
+                slot.host[:nf].copy_(slot.out[:nf], non_blocking=True)
             slot.done.record(s)
 
     # ------------------------------------------------------------------ API

@@ -41,7 +41,7 @@ class ImageBuffer:
             f.write(data)
 
 
-def make_opts(seed=0, max_depth=0, trace_mode=_abi.TRACE_BVH, shard_mode=_abi.SHARD_NONE, shard_rank=0, shard_count=1,
+def make_opts(seed=0, max_depth=0, trace_mode=_abi.TRACE_BVH, shard_mode=_abi.SHARD_NONE, shard_rank=0, shard_count=0,
               batch_paths=0, integrator=0, count_visits=False, time_kernels=False, no_tail_kernel=False, pool=0):
     return _abi.RenderOptsC(int(seed) & 0xFFFFFFFFFFFFFFFF, max_depth, trace_mode, shard_mode, shard_rank, shard_count,
                             batch_paths, integrator,

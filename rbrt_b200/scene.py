@@ -24,11 +24,12 @@ def element_arrays(elements):
 
 
 class Scene:
-    def __init__(self, elements=None, triangle_meshes=None, lights=None, simd_lanes=8, leaf_size=0, box_pad_rel=0.0):
+    def __init__(self, elements=None, triangle_meshes=None, lights=None, simd_lanes=8, leaf_size=0, box_pad_rel=0.0, local=False, sah=True):
         self.elements = list(elements or [])
         self.triangle_meshes = list(triangle_meshes or [])
         self.lights = list(lights or [])
         self.simd_lanes, self.leaf_size, self.box_pad_rel = simd_lanes, leaf_size, box_pad_rel
+        self.local, self.sah = local, sah     # RBRT_SCENE_LOCAL (no replication under a communicator), RBRT_SCENE_NO_SAH
         self._handle = None
 
     # ---- GPU handle -----------------------------------------------------------------------
@@ -38,7 +39,8 @@ class Scene:
             order, spheres, tris, ne, ns, nt = element_arrays(self.elements)
             nm = len(self.triangle_meshes)
             meshes = (_abi.MeshDescC * max(nm, 1))(*[m.to_c() for m in self.triangle_meshes])
-            opts = _abi.SceneOptsC(self.simd_lanes, self.leaf_size, self.box_pad_rel, 0)
+            opts = _abi.SceneOptsC(self.simd_lanes, self.leaf_size, self.box_pad_rel,
+                                   (_abi.SCENE_LOCAL if self.local else 0) | (0 if self.sah else _abi.SCENE_NO_SAH))
             h = C.c_void_p()
             _abi.check(lib.rbrt_gpu_scene_create_elements(order, ne, spheres, ns, tris, nt, meshes, nm, opts, C.byref(h)))
             self._handle = h
@@ -71,3 +73,25 @@ class Scene:
         if stats is not None:
             stats.update(st.as_dict())
         return hits
+
+
+def scatter(items, seed=0):
+    """Parity hook for RayScattering::scatter (materials.rs:4-12).  items: iterable of (material, in_ray_direction(3),
+    hit_point(3), hit_normal(3), pixel, sample, bounce); returns (scattered [N] i32, attenuation [N,3], out_dir [N,3])."""
+    items = list(items)
+    n = len(items)
+    arr = (_abi.ScatterInC * max(n, 1))()
+    for k, (mat, d, p, nrm, pixel, sample, bounce) in enumerate(items):
+        a = arr[k]
+        a.material = mat.to_c()
+        a.in_ray.origin = _abi.Vec3C(0.0, 0.0, 0.0)
+        a.in_ray.direction = _abi.Vec3C(*[float(x) for x in d])
+        a.hit_point = _abi.Vec3C(*[float(x) for x in p])
+        a.hit_normal = _abi.Vec3C(*[float(x) for x in nrm])
+        a.pixel, a.sample, a.bounce = int(pixel), int(sample), int(bounce)
+    out = (_abi.ScatterOutC * max(n, 1))()
+    _abi.check(_abi.lib().rbrt_gpu_scatter(C.cast(arr, C.c_void_p), n, int(seed) & 0xFFFFFFFFFFFFFFFF, C.cast(out, C.c_void_p)))
+    sc = np.array([out[k].scattered for k in range(n)], np.int32)
+    att = np.array([[out[k].attenuation.x, out[k].attenuation.y, out[k].attenuation.z] for k in range(n)], np.float32).reshape(n, 3)
+    od = np.array([[out[k].out_ray.direction.x, out[k].out_ray.direction.y, out[k].out_ray.direction.z] for k in range(n)], np.float32).reshape(n, 3)
+    return sc, att, od

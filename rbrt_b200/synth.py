@@ -98,6 +98,39 @@ def example_scene_blueprint(obj_path):
     return SceneBlueprint(example_camera_blueprint(), [mesh], example_sphere_blueprints())
 
 
+def header_card_blueprint(obj_path):
+    """= scenes/header_card.yaml of the reference (the scene of its README banner: 7 spheres + a red lambertian bunny at scale 45,
+    translation (3.5, -1.8, -14)) with `obj_path` substituted for bunny.obj.  tests/test_host.py compares it field by field
+    with the reference's file when the reference tree is mounted."""
+    mesh = TriangleMeshBlueprint(obj_path, 45.0, Vec3(3.5, -1.8, -14.0), Vec3(0.0, 0.0, 0.0), "lambertian", Vec3(1.0, 0.0, 0.0), None)
+    spheres = [
+        SphereBlueprint(1000.0, Vec3(0.0, -1000.0, -12.0), "lambertian", Vec3(0.02, 0.2, 0.1), None),
+        SphereBlueprint(1.5, Vec3(-7.5, 1.5, -10.5), "lambertian", Vec3(0.1, 0.1, 0.9), None),
+        SphereBlueprint(0.7, Vec3(3.0, 0.7, -9.5), "lambertian", Vec3(0.5, 0.5, 0.1), None),
+        SphereBlueprint(2.5, Vec3(-4.5, 2.5, -16.0), "metal", Vec3(0.9, 0.9, 0.9), 0.005),
+        SphereBlueprint(4.0, Vec3(9.5, 4.0, -20.0), "metal", Vec3(0.9, 0.9, 0.9), 0.001),
+        SphereBlueprint(1.0, Vec3(-1.5, 1.0, -8.0), "dielectric", None, 1.8),
+        SphereBlueprint(1.5, Vec3(7.0, 1.5, -10.0), "dielectric", None, 1.8),
+    ]
+    return SceneBlueprint(example_camera_blueprint(), [mesh], spheres)
+
+
+def blueprint_to_yaml(bp):
+    """A SceneBlueprint as the YAML text load_blueprints_from_yaml_file reads (blueprints.rs:15-48 field names)."""
+    import yaml
+    v = lambda a: None if a is None else {"x": float(a.x), "y": float(a.y), "z": float(a.z)}
+    opt = lambda d: {k: x for k, x in d.items() if x is not None}
+    c = bp.camera_blueprint
+    return yaml.safe_dump({
+        "camera_blueprint": {"camera_up": v(c.camera_up), "camera_look_at": v(c.camera_look_at), "camera_position": v(c.camera_position),
+                             "camera_focal_length_mm": float(c.camera_focal_length_mm)},
+        "mesh_blueprints": [opt({"obj_filepath": m.obj_filepath, "scale": float(m.scale), "translation": v(m.translation),
+                                 "rotation_rad": v(m.rotation_rad), "material_type": m.material_type, "albedo": v(m.albedo),
+                                 "material_param": m.material_param}) for m in bp.mesh_blueprints],
+        "sphere_blueprints": [opt({"radius": float(sp.radius), "center": v(sp.center), "material_type": sp.material_type, "albedo": v(sp.albedo),
+                                   "material_param": sp.material_param}) for sp in bp.sphere_blueprints]}, sort_keys=False)
+
+
 def spheres_only_blueprint():
     """Config C1: example_scene.yaml with the mesh removed."""
     return SceneBlueprint(example_camera_blueprint(), [], example_sphere_blueprints())

@@ -82,3 +82,30 @@ def hits_equal(a, b):
     return ((a["kind"] == b["kind"]) & (a["elem_idx"] == b["elem_idx"]) & (a["tri_idx"] == b["tri_idx"])
             & (a["t"].view(u) == b["t"].view(u)) & (a["dist"].view(u) == b["dist"].view(u))
             & (a["point"].view(u) == b["point"].view(u)).all(1) & (a["normal"].view(u) == b["normal"].view(u)).all(1))
+
+
+_BIG = {}
+
+
+def big_scene(subdiv, sah=True):
+    """Configs C3 (subdiv 8: 1 310 720 triangles, radius 40) / C5 (subdiv 9: 5 242 880 triangles, radius 100) exactly as
+    bench.py builds them (synth.big_mesh_config); the triangle soup is cached per process.  Returns (scene, camera at the
+    config's full size)."""
+    radius, (W, H) = {8: (40.0, (1920, 1080)), 9: (100.0, (3840, 2160))}[subdiv]
+    if subdiv not in _BIG:
+        _BIG[subdiv] = synth.big_mesh_config(subdiv, radius)
+    camkw, spheres, tris, mat = _BIG[subdiv]
+    scene = R.Scene(sah=sah)
+    scene.elements += [R.Sphere(c, r, m) for c, r, m in spheres]
+    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, mat))
+    cam = R.Camera.new(camkw["position"], camkw["look_at"], camkw["up"], H, W, camkw["focal_len_mm"])
+    return scene, cam
+
+
+def stress_scene():
+    """Config C4 exactly as bench.py builds it (synth.stress_config): 33 glass / metal spheres + a 20 480-triangle glass mesh."""
+    spheres, tris, mat = synth.stress_config()
+    scene = R.Scene()
+    scene.elements += [R.Sphere(c, r, m) for c, r, m in spheres]
+    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, mat))
+    return scene

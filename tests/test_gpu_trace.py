@@ -12,7 +12,7 @@ from . import golden_util as G
 from . import scenes as S
 
 pytestmark = pytest.mark.gpu
-MODES = [_abi.TRACE_BRUTE, _abi.TRACE_BVH]
+MODES = [_abi.TRACE_BRUTE, _abi.TRACE_BVH, _abi.TRACE_WAVEFRONT]   # WAVEFRONT = the renderer's own stage A + k_trace kernels
 
 
 def assert_same(a, b, what):
@@ -137,34 +137,47 @@ def test_c2_full_size_bvh_equals_brute(gpu):
     bvh = scene.hit(prim, _abi.TRACE_BVH, stats=st)
     brute = scene.hit(prim, _abi.TRACE_BRUTE)
     assert_same(bvh, brute, "C2 primary rays")
+    assert_same(scene.hit(prim, _abi.TRACE_WAVEFRONT), brute, "C2 primary rays through k_trace")
     assert (bvh["kind"] == 1).sum() > 50000
     on = bvh["kind"] == 1
     n = bvh["normal"][on]
     refl = prim[on, 3:] - 2 * (prim[on, 3:] * n).sum(1, keepdims=True) * n
     sec = np.concatenate([bvh["point"][on], refl.astype(np.float32)], 1)[:200000]
-    assert_same(scene.hit(sec, _abi.TRACE_BVH), scene.hit(sec, _abi.TRACE_BRUTE), "C2 reflected rays")
+    sec_brute = scene.hit(sec, _abi.TRACE_BRUTE)
+    assert_same(scene.hit(sec, _abi.TRACE_BVH), sec_brute, "C2 reflected rays")
+    assert_same(scene.hit(sec, _abi.TRACE_WAVEFRONT), sec_brute, "C2 reflected rays through k_trace")
     assert 0 < st["node_visits"] < 60 * len(prim) and st["tri_tests"] < 20 * len(prim)
 
 
 def test_c3_million_triangles_bvh_equals_brute(gpu):
     """Config C3's mesh (displaced icosphere, subdivision 8 = 1 310 720 triangles, radius 40): BVH == brute on a
     stratified subset of the 1920x1080 primary rays plus reflected rays."""
-    camkw, spheres, tris, mat = synth.big_mesh_config(8, 40.0)
-    scene = R.Scene()
-    scene.elements += [R.Sphere(c, r, m) for c, r, m in spheres]
-    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, mat))
+    scene, cam = S.big_scene(8)
     info = scene.info()
     assert info["num_triangles_tested"] == 1310720
-    cam = R.Camera.new(camkw["position"], camkw["look_at"], camkw["up"], 1080, 1920, camkw["focal_len_mm"])
     prim = R.primary_rays(cam, 1, 0)[::23]
     bvh = scene.hit(prim, _abi.TRACE_BVH)
     assert_same(bvh, scene.hit(prim, _abi.TRACE_BRUTE), "C3 primary subset")
+    # the hot kernel itself (k_trace: persistent warps, warp-voted traversal, dynamic fetch) on ALL 2 073 600 primary rays
+    # against the plain one-lane-one-ray traversal, and on the subset against brute force
+    full = R.primary_rays(cam, 1, 0)
+    st = {}
+    wf = scene.hit(full, _abi.TRACE_WAVEFRONT, stats=st)
+    assert_same(wf[::23], bvh, "C3 primary subset through k_trace")
+    assert_same(wf, scene.hit(full, _abi.TRACE_BVH), "C3 all primary rays: k_trace vs plain traversal")
+    assert st["traversed_rays"] > 500000 and st["node_visits"] > st["traversed_rays"]
     on = bvh["kind"] == 1
     assert on.sum() > 10000
     n = bvh["normal"][on]
     refl = prim[on, 3:] - 2 * (prim[on, 3:] * n).sum(1, keepdims=True) * n
     sec = np.concatenate([bvh["point"][on], refl.astype(np.float32)], 1)[:30000]
-    assert_same(scene.hit(sec, _abi.TRACE_BVH), scene.hit(sec, _abi.TRACE_BRUTE), "C3 reflected subset")
+    sec_brute = scene.hit(sec, _abi.TRACE_BRUTE)
+    assert_same(scene.hit(sec, _abi.TRACE_BVH), sec_brute, "C3 reflected subset")
+    assert_same(scene.hit(sec, _abi.TRACE_WAVEFRONT), sec_brute, "C3 reflected subset through k_trace")
+    # the same tree without the SAH rotation pass gives the same answers
+    plain = S.big_scene(8, sah=False)[0]
+    assert_same(plain.hit(sec, _abi.TRACE_WAVEFRONT), sec_brute, "C3 reflected subset, plain LBVH")
+    plain.close()
 
 
 def test_builder_edge_cases(gpu, oracle):

@@ -71,6 +71,24 @@ def test_reference_scene_files_parse():
     assert ex.camera_blueprint.camera_position.as_tuple() == mine.camera_blueprint.camera_position.as_tuple()
     hc = R.load_blueprints_from_yaml_file(os.path.join(d, "header_card.yaml"))
     assert len(hc.sphere_blueprints) == 7 and len(hc.mesh_blueprints) == 1
+    # synth.header_card_blueprint (what the GPU parity test renders, the reference tree being absent on the GPU box) restates it exactly
+    mine = synth.header_card_blueprint("bunny.obj")
+    key = lambda s: (s.radius, s.center.as_tuple(), s.material_type, None if s.albedo is None else s.albedo.as_tuple(), s.material_param)
+    assert [key(s) for s in hc.sphere_blueprints] == [key(s) for s in mine.sphere_blueprints]
+    m, n = hc.mesh_blueprints[0], mine.mesh_blueprints[0]
+    assert (m.obj_filepath, m.scale, m.translation.as_tuple(), m.rotation_rad.as_tuple(), m.material_type, m.albedo.as_tuple(), m.material_param) == \
+           (n.obj_filepath, n.scale, n.translation.as_tuple(), n.rotation_rad.as_tuple(), n.material_type, n.albedo.as_tuple(), n.material_param)
+    cb, cm = hc.camera_blueprint, mine.camera_blueprint
+    assert (cb.camera_up.as_tuple(), cb.camera_look_at.as_tuple(), cb.camera_position.as_tuple(), cb.camera_focal_length_mm) == \
+           (cm.camera_up.as_tuple(), cm.camera_look_at.as_tuple(), cm.camera_position.as_tuple(), cm.camera_focal_length_mm)
+
+
+def test_blueprint_yaml_round_trip(tmp_path):
+    bp = synth.header_card_blueprint("some.obj")
+    p = tmp_path / "scene.yaml"
+    p.write_text(synth.blueprint_to_yaml(bp))
+    back = R.load_blueprints_from_yaml_file(str(p))
+    assert back == bp
 
 
 def test_material_description_errors():

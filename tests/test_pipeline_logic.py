@@ -35,6 +35,7 @@ class RecordingPipeline(FramePipeline):
     def __init__(self, depth, fpb, rank=1):
         self.width, self.height, self.depth, self.hdr, self.fpb = 16, 8, depth, False, fpb
         self.world, self.rank, self.shard_mode = 1, rank, _abi.SHARD_TILES      # rank != 0: _collect hands out None images
+        self._torch = None
         self._slots = [_FakeSlot() for _ in range(depth)]
         self._n, self._pending, self._pending_key, self._pending_hv = 0, [], None, None
         self.groups = []
