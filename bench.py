@@ -10,25 +10,27 @@ path) — the reference's `render_scene(cam, spp, scene)` (lib.rs:75-124).  Rays
 (`Scene::hit` calls, primary + bounces), counted on the device.
 
   value      whole-job Mrays/s with the scene (SoA buffers + LBVH) already resident in HBM; the timed region is
-             K x (render -> [NCCL reduce to rank 0] -> finalize (1/spp, sqrt, x256, saturating u8) on the device), with
-             --frames-in-flight frames (default 2) in flight on their own streams (rbrt_b200.FramePipeline): the sparse,
-             latency-bound last bounces of one frame overlap the dense first bounces of the next; on 4 / 8 GPUs 2 / 4
-             consecutive frames are also rendered in the same wavefront batches (--frames-per-batch), which gives a rank's
-             launches the size they have on fewer GPUs.  `single_frame` is the same measurement one frame at a time.  The
-             last pipelined image is checked against the single-frame one.
+             K x collective render_scene (shard render -> per-GPU finalise (1/spp, sqrt, x256, saturating u8) -> gather on rank 0,
+             all inside librbrt_gpu.so), with --frames-in-flight groups (default 2) of --frames-per-batch frames (default 4, THE SAME
+             at every N) in flight on their own streams (rbrt_b200.FramePipeline): the sparse, latency-bound last bounces of one
+             group overlap the dense first bounces of the next.  The K-step region is repeated (>= ~0.6 s in total) and the median
+             region is reported.  `single_frame` is one frame at a time, `frames_per_batch_1` the pipelined figure with one frame
+             per batch.  The last pipelined image is checked against the single-frame one.
   e2e        the same metric through the reference-facing call with HOST buffers: every step uploads the
-             triangle soup from pinned host memory (rbrt_gpu_scene_create: H2D + LBVH build), renders
-             (rbrt_gpu_render / the multi-rank building blocks) and copies the RGB8 image back to the host.
+             triangle soup from pinned host memory (rbrt_gpu_scene_create: H2D + LBVH build on rank 0, NCCL broadcast of the
+             scene block to the other ranks), renders and copies the RGB8 image back to the host.
   roofline   the trace kernel (BVH traversal + intersection tests): algorithmic bytes per step from an
              instrumented counting pass (64 B per node visit, 48 B per triangle test, 64 B of queue / path-record traffic per
-             traversed ray) / the summed CUDA-event durations of that kernel's
-             launches inside the timed region, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+             traversed ray) / the summed CUDA-event durations of that kernel's launches, against the measured HBM copy
+             bandwidth (MEASURED_PEAKS.json); `traffic` / `dram_frac` / `ncu` from the committed ncu capture for this N.
+  image_check at EVERY N: the collective render vs the CPU oracle on a pixel lattice (bit-identical expected).
   cpu_baseline / --impl reference
              the CPU oracle (C++/AVX restatement of the reference; the Rust reference cannot be built here) on all
-             host threads, on a bounded stratified pixel sample of the same workload.
+             host threads, on a bounded stratified pixel sample of the same workload.  That arm never loads librbrt_gpu.so.
 
-Multi-GPU: one process per GPU, the image sharded by interleaved 8x4-pixel tiles (fixed total work => "strong"
-scaling), scene + LBVH replicated, ONE NCCL reduce of the f32 accumulation buffer to rank 0 per step.
+Multi-GPU: one process per GPU (torchrun); torch.distributed only carries the NCCL unique id to the library
+(rbrt_b200.dist.init_comm); sharding by interleaved 8x4-pixel tiles (fixed total work => "strong" scaling), gather and scene
+broadcast run inside librbrt_gpu.so (csrc/multi.cu).
 """
 import argparse
 import json
@@ -218,6 +220,11 @@ def oracle_scene(spheres, meshes):
     return O, O.OracleScene(els, ms, 8)
 
 
+def oracle_camera(O, camkw, H, W):
+    """Camera::new (cam.rs:22-62) computed by the ORACLE (the reference arm never touches the product library)."""
+    return O.camera_new(camkw["position"], camkw["look_at"], camkw["up"], H, W, camkw["focal_len_mm"])
+
+
 def choose_stride(O, osc, cam_c, spp_full, target_s):
     """Pick a pixel lattice (stride, stride) and a sample count so that one oracle pass takes about target_s."""
     from rbrt_b200 import _abi
@@ -241,25 +248,38 @@ def cpu_leg(O, osc, cam_c, stride, spp, want_image=False):
     return (st, acc) if want_image else st
 
 
+def product_lib_loaded():
+    try:
+        return "librbrt_gpu" in open("/proc/self/maps").read()
+    except OSError:
+        return None
+
+
 def run_reference(args):
-    """--impl reference: the oracle on all host threads, each step a bounded stratified sample of the workload."""
+    """--impl reference: the oracle on all host threads, each step a bounded stratified sample of the workload.  The product
+    library (librbrt_gpu.so) is never loaded in this arm: camera and vertex transform come from the oracle's own twins."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import rbrt_b200 as R
+    from oracle import oracle_ffi as O
+    import rbrt_b200.mesh as M
+
+    def oracle_transform(ptr, n_vertices, scale, rot_c, tr_c):
+        O.check(O.lib().rbrt_ref_transform_vertices(ptr, n_vertices, scale, rot_c, tr_c))
+    M._transform_in_place = oracle_transform
     desc, W, H, spp = WORKLOADS[args.workload]
     spheres, meshes, camkw = build_workload(args.workload)
     O, osc = oracle_scene(spheres, meshes)
-    cam = R.Camera.new(camkw["position"], camkw["look_at"], camkw["up"], H, W, camkw["focal_len_mm"])
+    cam_c = oracle_camera(O, camkw, H, W)
     cores = O.lib().rbrt_ref_hardware_threads()
     budget = 150.0 / max(1, args.steps + args.warmup)
-    stride, s_spp = choose_stride(O, osc, cam.to_c(), spp, min(8.0, budget))
+    stride, s_spp = choose_stride(O, osc, cam_c, spp, min(8.0, budget))
     for _ in range(args.warmup):
-        cpu_leg(O, osc, cam.to_c(), stride, s_spp)
+        cpu_leg(O, osc, cam_c, stride, s_spp)
     t0 = time.perf_counter()
     rays = paths = 0
     for _ in range(args.steps):
-        st = cpu_leg(O, osc, cam.to_c(), stride, s_spp)
+        st = cpu_leg(O, osc, cam_c, stride, s_spp)
         rays += st["rays"]; paths += st["paths"]
     dt = time.perf_counter() - t0
     val = rays / dt / 1e6
@@ -270,6 +290,7 @@ def run_reference(args):
             "config": workload_config(args.workload, spheres, meshes, args.gpus),
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": int(cores), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_lib_loaded": product_lib_loaded(),
             "note": "CPU oracle (C++/AVX restatement; rustc/cargo absent so the Rust reference cannot be built); full-frame time is "
                     "extrapolated only in DESIGN.md, this value is measured rays / measured seconds on the sample"}
     print(json.dumps(line), file=_STDOUT, flush=True)
@@ -280,19 +301,39 @@ def workload_config(name, spheres, meshes, n_gpus):
     desc, W, H, spp = WORKLOADS[name]
     return {"workload": desc, "width": W, "height": H, "spp": spp, "max_depth": 50, "spheres": len(spheres),
             "triangles": int(sum(len(t) for t, _ in meshes)), "seed": SEED,
-            "sharding": "none" if n_gpus == 1 else (f"sample ranges over {n_gpus} ranks + one NCCL reduce (sum) of the f32 accumulator" if name in SAMPLE_SHARDED
-                                                    else f"interleaved 8x4-pixel tiles over {n_gpus} ranks + one NCCL reduce of the f32 accumulator"),
+            "sharding": "none" if n_gpus == 1 else (f"sample ranges over {n_gpus} ranks + one NCCL reduce (sum) of the f32 accumulators, inside librbrt_gpu.so" if name in SAMPLE_SHARDED
+                                                    else f"interleaved 8x4-pixel tiles over {n_gpus} ranks, every rank finalises its own pixels, NCCL gather of 3 B/pixel on rank 0, inside librbrt_gpu.so"),
             "l2_policy": "no explicit flush: per step the wavefront streams >400 MB of ray/hit queues and the scene (nodes+triangles+normals) "
                          "is larger than or comparable to L2; inputs larger than L2"}
 
 
+def ncu_evidence(workload, world):
+    """What ncu measured for the dominant kernel, from the COMMITTED summary profiles/r2_ncu_summary.json (written by
+    scripts/ncu_summary.py from the raw CSVs next to it; the file names the exact ncu command).  Keyed by workload and by the tile-shard
+    denominator N (one GPU rendering 1/N of the frame = what one rank of N renders).  None when no capture exists for this (workload, N)."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        e = d.get(workload, {}).get(str(world))
+        if e is not None:
+            e = dict(e, source="profiles/r2_ncu_summary.json", command=d.get("command"))
+        return e
+    except (ValueError, OSError):
+        return None
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     import rbrt_b200 as R
     from rbrt_b200 import _abi
+    from rbrt_b200 import dist as D
     from rbrt_b200.render import make_opts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -304,38 +345,42 @@ def run_gpu(args):
         args.gpus = world
     torch.cuda.set_device(local)
     R.gpu_init(local)
+    comm = {"active": 0, "transport": 0, "nccl_version": 0}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = D.init_comm(dist)                               # the library's own NCCL communicator (torch only carries the unique id)
+        assert comm["active"] and comm["world"] == world and comm["rank"] == rank
     lib = _abi.lib()
     desc, W, H, spp = WORKLOADS[args.workload]
     spheres, meshes, camkw = build_workload(args.workload)
     cam = R.Camera.new(camkw["position"], camkw["look_at"], camkw["up"], H, W, camkw["focal_len_mm"])
     cam_c = cam.to_c()
-    scene = make_scene(spheres, meshes)
+    scene = make_scene(spheres, meshes)                        # under the communicator: rank 0 uploads + builds, the block is broadcast
     info = scene.info()
     stream = torch.cuda.current_stream()
-    accum = torch.empty(H * W * 4, dtype=torch.float32, device="cuda")
     rgb = torch.empty(H * W * 3, dtype=torch.uint8, device="cuda")
     shard_mode = _abi.SHARD_SAMPLES if args.workload in SAMPLE_SHARDED else _abi.SHARD_TILES
-    shard = dict(shard_mode=shard_mode, shard_rank=rank, shard_count=world) if world > 1 else {}
+    mode_kw = dict(shard_mode=shard_mode) if world > 1 else {}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(handle, flags_kw, st):
-        _abi.check(lib.rbrt_gpu_render_accum_device(handle, cam_c, spp, make_opts(seed=SEED, **shard, **flags_kw), accum.data_ptr(),
-                                                    stream.cuda_stream, st))
-        if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            _abi.check(lib.rbrt_gpu_finalize_device(accum.data_ptr(), W, H, spp, rgb.data_ptr(), None, stream.cuda_stream))
+    cams1 = (_abi.CameraC * 1)(cam_c)
+    seeds1 = (C.c_uint64 * 1)(SEED)
+    rgb1 = (C.c_void_p * 1)(rgb.data_ptr())
+
+    def step_single(flags_kw, st, n_spp=spp, out=rgb1, hdr=None):
+        """ONE collective render_scene: shard render -> per-GPU finalise -> gather on rank 0 (rbrt_gpu_render_frames_device);
+        with st it waits for the frame."""
+        _abi.check(lib.rbrt_gpu_render_frames_device(scene.handle(), cams1, seeds1, 1, n_spp, make_opts(seed=SEED, **mode_kw, **flags_kw),
+                                                     out, hdr, stream.cuda_stream, st))
 
     # ---- counting pass (untimed): node visits / triangle tests per step, identical every step (fixed seed)
     cst = _abi.StatsC()
-    step_resident(scene.handle(), dict(count_visits=True), cst)
+    step_single(dict(count_visits=True), cst)
     barrier()
     counts = cst.as_dict()
 
@@ -345,49 +390,69 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
     for _ in range(max(args.warmup, 3)):
-        step_resident(scene.handle(), dict(time_kernels=True), _abi.StatsC())
+        step_single(dict(time_kernels=True), _abi.StatsC())
     barrier()
-    n_single = 3
-    e0.record(stream)
+    n_single = 5
+    single_ms = []
     for _ in range(n_single):
         st = _abi.StatsC()
-        step_resident(scene.handle(), dict(time_kernels=True), st)
+        e0.record(stream)
+        step_single(dict(time_kernels=True), st)
+        e1.record(stream)
+        barrier()
+        single_ms.append(e0.elapsed_time(e1))
         stats.append(st.as_dict())
-    e1.record(stream)
-    barrier()
-    ms_single = e0.elapsed_time(e1) / n_single
+    ms_single = statistics.median(single_ms)
     rgb_ref = rgb.clone() if rank == 0 else None
     frame = stats[-1]
     assert all(s_["rays"] == frame["rays"] and s_["paths"] == frame["paths"] for s_ in stats), "frames of one seed differ"
 
-    # ---- resident arm (timed region): `steps` frames through the FramePipeline, `frames_in_flight` of them in flight on
-    #      their own streams and wavefront pools, so the sparse last bounces of one frame overlap the next frame's first
-    fpb = args.frames_per_batch or (1 if world == 1 else 2 if world < 8 else 4)     # measured: 2 GPUs 17.10 -> 16.55 ms/frame, 4 GPUs 9.22 -> 8.60 with 2;
-                                                                                    # 1/8 shard on one GPU 5.15 -> 4.29 with 4 (profiles/r1_summary.md)
-    if args.workload in SAMPLE_SHARDED:
-        fpb = args.frames_per_batch or 1
-    pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode, frames_per_batch=fpb)
-    with ClockSampler(local) as clk:
-        time.sleep(0.3)                                       # let nvidia-smi deliver its first samples
-        for _ in range(max(args.warmup, 3) * fpb):
+    # ---- resident arm (timed region): `steps` frames through the FramePipeline, `frames_in_flight` groups in flight on their own
+    #      streams and wavefront pools, `frames_per_batch` frames per group — THE SAME at every N (a rank's launches on 8 GPUs
+    #      then have about the size they have on one GPU with one frame).  The K-step region is repeated until >= ~0.6 s have been
+    #      timed, each repeat bracketed by barrier + synchronize; the MEDIAN region is reported.
+    fpb = args.frames_per_batch or (1 if args.workload in SAMPLE_SHARDED else 4)
+
+    def timed_pipeline(fpb_, budget_s):
+        pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode, frames_per_batch=fpb_)
+        for _ in range(max(args.warmup, 3) * fpb_):
             pipe.submit(cam_c, spp, scene, seed=SEED)
         pipe.drain()
         barrier()
+        regions = []
+        t_all = time.perf_counter()
+        while True:
+            e0.record(stream)
+            for _ in range(args.steps):
+                pipe.submit(cam_c, spp, scene, seed=SEED)
+            pipe.flush()                                      # a last, partially filled group of frames
+            pipe.wait_on(stream)
+            e1.record(stream)
+            last = pipe.drain()[-1][0]
+            barrier()
+            regions.append(e0.elapsed_time(e1))
+            go = torch.tensor([1.0 if (time.perf_counter() - t_all < budget_s and len(regions) < 60) else 0.0], device="cuda")
+            if world > 1:
+                dist.broadcast(go, src=0)                     # every rank runs the same number of repeats
+            if go.item() == 0.0:
+                break
+        return regions, last
+
+    with ClockSampler(local) as clk:
+        time.sleep(0.3)                                       # let nvidia-smi deliver its first samples
         clk.mark_begin()
-        e0.record(stream)
-        for _ in range(args.steps):
-            pipe.submit(cam_c, spp, scene, seed=SEED)
-        pipe.flush()                                          # a last, partially filled group of frames
-        pipe.wait_on(stream)
-        e1.record(stream)
-        barrier()
+        regions, last = timed_pipeline(fpb, 0.7)
         clk.mark_end()
-    last = pipe.drain()[-1][0]
     if rank == 0:
         assert torch.equal(last, rgb_ref), "pipelined frame differs from the single-frame render"
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms, ms_single], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([frame["rays"] * args.steps, frame["paths"] * args.steps, (frame["launches"] + (1 if rank == 0 else 0)) * args.steps,
+    ms = statistics.median(regions)
+    regions1 = None
+    if fpb != 1:                                              # the same measurement with ONE frame per batch, for the record
+        regions1, last1 = timed_pipeline(1, 0.4)
+        if rank == 0:
+            assert torch.equal(last1, rgb_ref), "pipelined frame (1 per batch) differs from the single-frame render"
+    t = torch.tensor([ms, ms_single, statistics.median(regions1) if regions1 else 0.0, min(regions), max(regions)], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([frame["rays"] * args.steps, frame["paths"] * args.steps, (frame["launches"]) * args.steps,
                         counts["node_visits"] - counts["tail_node_visits"], counts["tri_tests"] - counts["tail_tri_tests"], counts["rays"],
                         counts["traversed_rays"] - counts["tail_traversed_rays"]], dtype=torch.float64, device="cuda")
     trace_ms = torch.tensor([sum(s_["ms_trace"] for s_ in stats) / n_single * args.steps], dtype=torch.float64, device="cuda")
@@ -395,14 +460,14 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         dist.all_reduce(trace_ms, op=dist.ReduceOp.MAX)
-    ms, ms_single = (float(x) for x in t.tolist())
+    ms, ms_single, ms_fpb1, ms_min, ms_max = (float(x) for x in t.tolist())
     rays, paths, launches, V, T, Rc, Cc = (float(x) for x in agg.tolist())
     trace_ms = float(trace_ms.item())
     clocks = clk.summary()
 
-    # ---- e2e arm: host buffers in, host image out, every step (scene upload + LBVH build inside the timed region)
+    # ---- e2e arm: host buffers in, host image out, every step (scene upload + LBVH build [+ broadcast] inside the timed region)
     pinned, keep = pin_meshes(meshes)
-    h2d = sum(t.nbytes for t in pinned) + 36 * len(spheres) + 20 * (len(spheres) + len(meshes)) + 64
+    h2d = sum(t_.nbytes for t_ in pinned) + 36 * len(spheres) + 20 * (len(spheres) + len(meshes)) + 64
     d2h = H * W * 3
 
     pipe_e = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=True, shard_mode=shard_mode)
@@ -417,9 +482,9 @@ def run_gpu(args):
     def step_e2e():
         t_a = time.perf_counter()
         sc = make_scene(spheres, meshes, pinned)
-        sc.handle()                                           # rbrt_gpu_scene_create: H2D of the triangle soup + LBVH build
+        sc.handle()                                           # rbrt_gpu_scene_create: rank 0 H2D of the triangle soup + LBVH build, NCCL broadcast of the block
         t_b = time.perf_counter()
-        # render -> [reduce] -> finalize -> RGB8 image to pinned host memory, enqueued on the frame's stream; the image of
+        # render -> finalise -> [gather] -> RGB8 image to pinned host memory, enqueued on the frame's stream; the image of
         # the frame submitted `frames_in_flight` steps ago is collected (host buffer ready) and its scene destroyed
         for fin in pipe_e.submit(cam_c, spp, sc, tag=sc, seed=SEED):
             retire(fin)
@@ -432,16 +497,26 @@ def run_gpu(args):
         retire(fin)
     barrier()
     e_steps = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(e_steps):
-        ms_create, ms_render = step_e2e()
-        print(f"[e2e rank {rank}] scene_create {ms_create:.1f} ms, submit (+ wait for the frame {args.frames_in_flight} steps back) {ms_render:.1f} ms", file=sys.stderr)
-    for fin in pipe_e.drain():                                # every image of the timed steps is on the host when the clock stops
-        retire(fin)
-    e1.record(stream)
-    barrier()
-    e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # host-side work (malloc, sync copies) counts too
+    e_regions = []
+    t_all = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(e_steps):
+            ms_create, ms_render = step_e2e()
+        for fin in pipe_e.drain():                            # every image of the timed steps is on the host when the clock stops
+            retire(fin)
+        e1.record(stream)
+        barrier()
+        e_regions.append(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))   # host-side work (malloc, sync copies) counts too
+        go = torch.tensor([1.0 if (time.perf_counter() - t_all < 0.6 and len(e_regions) < 30) else 0.0], device="cuda")
+        if world > 1:
+            dist.broadcast(go, src=0)
+        if go.item() == 0.0:
+            break
+    print(f"[e2e rank {rank}] last step: scene_create {ms_create:.1f} ms, submit (+ wait for the frame {args.frames_in_flight} steps back) {ms_render:.1f} ms; "
+          f"{len(e_regions)} regions of {e_steps} steps", file=sys.stderr)
+    e_ms = statistics.median(e_regions)
     if rank == 0:
         assert np.array_equal(e2e_last[0].pixels.reshape(-1), rgb_ref.cpu().numpy()), "e2e image differs from the single-frame render"
     e_rays = frame["rays"] * e_steps
@@ -452,8 +527,52 @@ def run_gpu(args):
         dist.all_reduce(re, op=dist.ReduceOp.SUM)
     e_val = float(re.item()) / (float(te.item()) / 1e3) / 1e6
 
+    # ---- image check at EVERY N: rank 0 renders a pixel lattice of the same frame with the CPU oracle; all ranks render that
+    #      frame collectively at the same seed and sample count; the lattice pixels must agree bit for bit.  At N = 1 the oracle
+    #      pass is the cpu_baseline sample (~20 s); at N > 1 it is a few seconds.
+    plan = [0, 0]
+    O = osc = None
+    if rank == 0 and not args.no_cpu:
+        O, osc = oracle_scene(spheres, meshes)
+        plan = list(choose_stride(O, osc, cam_c, spp, 22.0 if world == 1 else 3.0))
+    if world > 1:
+        pl = torch.tensor(plan, dtype=torch.int64, device="cuda")
+        dist.broadcast(pl, src=0)
+        plan = [int(x) for x in pl.tolist()]
+    stride, s_spp = plan
+    image_check = cpu_baseline = None
+    if stride:
+        hdr = torch.empty(H * W * 3, dtype=torch.float32, device="cuda")
+        hdr1 = (C.c_void_p * 1)(hdr.data_ptr())
+        if rank == 0:
+            cpu_st, acc_cpu = cpu_leg(O, osc, cam_c, stride, s_spp, want_image=True)
+            if world == 1 and cpu_st["ms_total"] < 10e3 and stride > 1 and s_spp == 1:   # the probe under-estimated the cost per path: one denser pass (~18 s)
+                stride2 = max(1, int(stride * (cpu_st["ms_total"] / 18e3) ** 0.5))
+                if stride2 < stride:
+                    stride = stride2
+                    cpu_st, acc_cpu = cpu_leg(O, osc, cam_c, stride, s_spp, want_image=True)
+        step_single({}, _abi.StatsC(), n_spp=s_spp, out=None, hdr=hdr1)
+        barrier()
+        if rank == 0:
+            hdr_gpu = hdr.cpu().numpy().reshape(H, W, 3)[::stride, ::stride]
+            acc_ref = np.asarray(acc_cpu, np.float32).reshape(H, W, 4)[::stride, ::stride, :3]
+            hdr_ref = acc_ref * np.float32(1.0 / s_spp)                                  # lib.rs:101
+            to_u8 = lambda h_: np.clip(np.nan_to_num(np.sqrt(np.maximum(h_, 0)) * 256.0), 0, 255).astype(np.uint8).astype(np.float64)
+            image_check = {"pixels": int(acc_ref.shape[0] * acc_ref.shape[1]), "spp": int(s_spp), "n_gpus": world,
+                           "bit_identical": bool(np.array_equal(np.ascontiguousarray(hdr_gpu).view(np.uint32), np.ascontiguousarray(hdr_ref).view(np.uint32))),
+                           "hdr_rmse": float(np.sqrt(np.mean((hdr_gpu.astype(np.float64) - hdr_ref) ** 2))),
+                           "u8_rmse": float(np.sqrt(np.mean((to_u8(hdr_gpu) - to_u8(hdr_ref)) ** 2))),
+                           "note": "the N-GPU collective render vs the CPU oracle on a pixel lattice, same seed and spp (equal Philox streams => RMSE 0 "
+                                   "expected); the criterion for independent seeds, RMSE(gpu, cpu_a) <= 1.10 RMSE(cpu_b, cpu_a), is in tests/"}
+            if world == 1:
+                cores = int(O.lib().rbrt_ref_hardware_threads())
+                cpu_baseline = {"value": cpu_st["rays"] / (cpu_st["ms_total"] / 1e3) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                "sample": f"pixel lattice stride {stride}x{stride} of the {W}x{H} frame, {s_spp} of {spp} spp: {cpu_st['paths']} paths, "
+                                          f"{cpu_st['rays']} rays in {cpu_st['ms_total'] / 1e3:.1f} s"}
+
     if rank != 0:
         if world > 1:
+            lib.rbrt_gpu_comm_destroy()
             dist.destroy_process_group()
         return 0
 
@@ -464,67 +583,51 @@ def run_gpu(args):
     flops_step = algorithmic_flops(cstep, ns, nm)
     trace_ms_step = trace_ms / args.steps          # max over ranks of the per-rank sum; ranks run concurrently
     achieved = bytes_step / max(world, 1) / (trace_ms_step / 1e3) / 1e9 if trace_ms_step > 0 else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
+    ev = ncu_evidence(args.workload, world)
+    traffic = ev.get("dram_bytes_per_step") if ev else None
     line = {
         "metric": "Mrays/s", "value": rays / (ms / 1e3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args.workload, spheres, meshes, world), frames_in_flight=args.frames_in_flight, frames_per_batch=fpb),
+        "timed_region": {"repeats": len(regions), "steps_per_repeat": args.steps, "ms_median": ms, "ms_min": ms_min, "ms_max": ms_max,
+                         "note": "the K-step region (barrier + synchronize on both sides, CUDA events, max over ranks) is repeated; value uses the median region"},
         "single_frame": {"ms_per_step": ms_single, "value": rays / args.steps / (ms_single / 1e3) / 1e6, "unit": "Mrays/s",
-                         "note": "one frame at a time, host waits for each (latency of a lone render_scene call); `value` keeps "
+                         "note": "one frame at a time, host waits for each (latency of a lone render_scene call, gather on rank 0 included); `value` keeps "
                                  "`frames_in_flight` groups of `frames_per_batch` frames in flight on separate streams"},
+        "frames_per_batch_1": ({"ms_per_step": ms_fpb1 / args.steps, "value": rays / (ms_fpb1 / 1e3) / 1e6, "unit": "Mrays/s"} if regions1 else None),
         "samples_per_s": paths / (ms / 1e3), "rays_per_step": rays / args.steps, "rays_per_sample": rays / max(paths, 1),
         "clocks": clocks,
-        "e2e": {"value": e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-                "ms_per_step": float(te.item()) / e_steps, "includes": "scene upload from pinned host memory + LBVH build + render + RGB8 image to pinned host memory, per step; "
-                            "frames_in_flight frames overlap (FramePipeline), all images on the host when the clock stops"},
+        "e2e": {"value": e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps, "repeats": len(e_regions),
+                "ms_per_step": float(te.item()) / e_steps, "includes": "scene upload from pinned host memory + LBVH build (rank 0) [+ NCCL broadcast of the scene block] + render + "
+                            "RGB8 image to pinned host memory, per step; frames_in_flight frames overlap (FramePipeline), all images on the host when the clock stops"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_trace (stage B: persistent LBVH traversal with dynamic fetch + Moeller-Trumbore tests)",
+        "multi_gpu": {"inside_library": True, "transport": {0: "none", 1: "nccl", 2: "peer"}.get(comm["transport"], "?"), "nccl_version": comm["nccl_version"]},
+        "roofline": {"bound": "hbm", "limiter": "issue / ALU pipe under partial lane occupancy, NOT memory (see `ncu`): the kernel's requested bytes are served by L1/L2",
+                     "kernel": "k_trace (stage B: persistent LBVH traversal with dynamic fetch + Moeller-Trumbore tests)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "dram_frac": (traffic / (trace_ms_step / 1e3) / 1e9 / peak) if (traffic and trace_ms_step > 0) else None,
+                     "ncu": ev,
                      "peak_source": peak_src, "algorithmic_bytes_per_traversed_ray": bytes_step / max(Cc, 1),
                      "traversed_rays_per_step": Cc, "traversed_share_of_rays": Cc / max(Rc, 1),
                      "node_visits_per_traversed_ray": V / max(Cc, 1), "tri_tests_per_traversed_ray": T / max(Cc, 1),
                      "trace_ms_per_step": trace_ms_step, "trace_share_of_step": trace_ms_step / ms_single,
                      "fp32_achieved_tflops": flops_step / max(world, 1) / (trace_ms_step / 1e3) / 1e12 if trace_ms_step > 0 else None,
                      "fp32_peak_tflops": 37.2, "fp32_frac": (flops_step / max(world, 1) / (trace_ms_step / 1e3) / 1e12 / 37.2) if trace_ms_step > 0 else None,
-                     "fp32_note": "secondary bound of SURVEY.md 8(d): 148 SMs x 128 lanes x 1.965 GHz = 37.2 T lane-ops/s without FMA contraction "
-                                  "(parity forbids it); the bandwidth fraction above is the larger one and is reported as `frac`",
-                     "note": "achieved = per-GPU algorithmic bytes of all trace launches of a step / their summed CUDA-event time (per-launch "
-                             "average x launches), events taken in this run's single-frame pass (frames of the timed region overlap, which "
-                             "would smear per-kernel times); nodes+triangles mostly hit in L2, so this is requested bandwidth against the HBM copy peak"},
+                     "fp32_note": "secondary bound of SURVEY.md 8(d): 148 SMs x 128 lanes x 1.965 GHz = 37.2 T lane-ops/s without FMA contraction (parity forbids it)",
+                     "note": "achieved = per-GPU ALGORITHMIC bytes of all trace launches of a step / their summed CUDA-event time (events on the launching stream, "
+                             "this run's single-frame pass); `frac` is that REQUESTED bandwidth against the HBM copy peak as the contract defines it. `traffic` = "
+                             "dram__bytes_read+write of the same launches from the committed ncu capture for THIS N (`ncu`), `dram_frac` = traffic / trace time / peak: "
+                             "what HBM actually sees"},
         "scene": {"bvh_nodes": info["num_bvh_nodes"], "device_bytes": info["device_bytes"], "ms_upload": info["ms_upload"], "ms_build": info["ms_build"]},
     }
-    if world == 1 and not args.no_cpu:
-        O, osc = oracle_scene(spheres, meshes)
-        cores = int(O.lib().rbrt_ref_hardware_threads())
-        stride, s_spp = choose_stride(O, osc, cam_c, spp, 22.0)
-        st, acc_cpu = cpu_leg(O, osc, cam_c, stride, s_spp, want_image=True)
-        if st["ms_total"] < 10e3 and stride > 1 and s_spp == 1:       # the probe under-estimated the cost per path: one denser pass (~18 s)
-            stride2 = max(1, int(stride * (st["ms_total"] / 18e3) ** 0.5))
-            if stride2 < stride:
-                stride = stride2
-                st, acc_cpu = cpu_leg(O, osc, cam_c, stride, s_spp, want_image=True)
-        # image check (BASELINE.json's metric names the image RMSE): the pixels the oracle just rendered against the GPU's
-        # render of the same frame at the same seed and sample count — same Philox streams, so the sums must agree bit for bit
-        _abi.check(lib.rbrt_gpu_render_accum_device(scene.handle(), cam_c, s_spp, make_opts(seed=SEED), accum.data_ptr(), stream.cuda_stream, _abi.StatsC()))
-        acc_gpu = accum.cpu().numpy().reshape(H, W, 4)[::stride, ::stride, :3]
-        acc_ref = np.asarray(acc_cpu, np.float32).reshape(H, W, 4)[::stride, ::stride, :3]
-        hdr_gpu, hdr_ref = acc_gpu * np.float32(1.0 / s_spp), acc_ref * np.float32(1.0 / s_spp)
-        to_u8 = lambda h_: np.clip(np.nan_to_num(np.sqrt(np.maximum(h_, 0)) * 256.0), 0, 255).astype(np.uint8).astype(np.float64)
-        line["image_check"] = {"pixels": int(acc_ref.shape[0] * acc_ref.shape[1]), "spp": int(s_spp),
-                               "bit_identical": bool(np.array_equal(acc_gpu.view(np.uint32), acc_ref.view(np.uint32))),
-                               "hdr_rmse": float(np.sqrt(np.mean((hdr_gpu.astype(np.float64) - hdr_ref) ** 2))),
-                               "u8_rmse": float(np.sqrt(np.mean((to_u8(hdr_gpu) - to_u8(hdr_ref)) ** 2))),
-                               "note": "GPU vs CPU oracle on the cpu_baseline sample's pixels, same seed and spp (equal Philox streams => RMSE 0 "
-                                       "expected); the criterion for independent seeds, RMSE(gpu, cpu_a) <= 1.10 RMSE(cpu_b, cpu_a), is in tests/"}
-        line["cpu_baseline"] = {"value": st["rays"] / (st["ms_total"] / 1e3) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                "sample": f"pixel lattice stride {stride}x{stride} of the {W}x{H} frame, {s_spp} of {spp} spp: {st['paths']} paths, "
-                                          f"{st['rays']} rays in {st['ms_total'] / 1e3:.1f} s"}
+    if image_check:
+        line["image_check"] = image_check
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line), file=_STDOUT, flush=True)
     if world > 1:
+        lib.rbrt_gpu_comm_destroy()
         dist.destroy_process_group()
     return 0
 
@@ -536,12 +639,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle legs (cpu_baseline, image_check): profiling runs")
     ap.add_argument("--frames-per-batch", type=int, default=0, choices=[0, 1, 2, 3, 4],
-                    help="frames rendered together in the same wavefront batches in the timed region (0 = 1 on one GPU, 2 on 2-7, 4 on 8: "
-                         "a rank's launches then have about the size they have on fewer GPUs)")
+                    help="frames rendered together in the same wavefront batches in the timed region (0 = 4 at EVERY N; sample-sharded workloads 1)")
     ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2, 3, 4],
-                    help="frames kept in flight on separate streams in the timed region (1 = one frame at a time)")
+                    help="groups of frames kept in flight on separate streams in the timed region (1 = one group at a time)")
     args = ap.parse_args()
     # exactly ONE line goes to stdout (the JSON); the host mirror's progress prints (lib.rs:80,114, mesh.rs:115) go to stderr
     # (NCCL and the host mirror also write to fd 1 from C: redirect the descriptor itself, keep a private duplicate for the JSON)

@@ -29,7 +29,19 @@ pub struct RbrtRenderOpts { pub seed: u64, pub max_depth: u32, pub trace_mode: u
 pub struct RbrtStats { pub rays: u64, pub paths: u64, pub nan_rays: u64, pub node_visits: u64, pub tri_tests: u64, pub ms_total: f64,
                        pub ms_device: f64, pub ms_trace: f64, pub ms_h2d: f64, pub ms_d2h: f64, pub launches: u32, pub iterations: u32,
                        pub traversed_rays: u64, pub tail_node_visits: u64, pub tail_tri_tests: u64, pub tail_traversed_rays: u64 }
+#[repr(C)] #[derive(Copy, Clone, Debug, Default)]
+pub struct RbrtSceneOpts { pub simd_lanes: u32, pub leaf_size: u32, pub box_pad_rel: f32, pub flags: u32 }
+#[repr(C)] #[derive(Copy, Clone, Debug, Default)]
+pub struct RbrtCommInfo { pub active: i32, pub world: i32, pub rank: i32, pub local_devices: i32, pub transport: i32, pub nccl_version: i32,
+                          pub devices: [i32; 16] }
 pub enum RbrtScene {}
+pub const RBRT_MAX_FRAMES: u32 = 4;
+pub const RBRT_COMM_ID_BYTES: usize = 128;
+pub const RBRT_TRANSPORT_AUTO: c_int = 0;
+pub const RBRT_TRANSPORT_NCCL: c_int = 1;
+pub const RBRT_TRANSPORT_PEER: c_int = 2;
+pub const RBRT_SCENE_LOCAL: u32 = 1;
+pub const RBRT_SCENE_NO_SAH: u32 = 2;
 pub const RBRT_OPT_COUNT_VISITS: u32 = 1;
 pub const RBRT_OPT_TIME_KERNELS: u32 = 2;
 pub const RBRT_OPT_NO_TAIL_KERNEL: u32 = 4;
@@ -41,6 +53,14 @@ extern "C" {
                            focal_len_mm: f32, out: *mut RbrtCamera) -> c_int;
     pub fn rbrt_transform_vertices(xyz: *mut f32, n_vertices: u64, scale: f32, rotation_rad: RbrtVec3, translation: RbrtVec3) -> c_int;
     pub fn rbrt_gpu_init(device: c_int) -> c_int;
+    /// Multi-GPU inside the library: one process driving n GPUs (devices = null: 0..n-1) ...
+    pub fn rbrt_gpu_init_multi(devices: *const c_int, n_devices: c_int, transport: c_int) -> c_int;
+    /// ... or one process per GPU: rank 0 makes the id, every rank joins (the id travels over any side channel, e.g. MPI or a file).
+    pub fn rbrt_gpu_comm_unique_id(id_out: *mut u8) -> c_int;
+    pub fn rbrt_gpu_comm_init_rank(id: *const u8, rank: c_int, world: c_int) -> c_int;
+    pub fn rbrt_gpu_comm_info(out: *mut RbrtCommInfo) -> c_int;
+    pub fn rbrt_gpu_comm_destroy() -> c_int;
+    pub fn rbrt_gpu_set_pool_limit(max_bytes_per_pool: u64) -> c_int;
     pub fn rbrt_gpu_scene_create(spheres: *const RbrtSphereDesc, num_spheres: u32, meshes: *const RbrtMeshDesc, num_meshes: u32,
                                  opts: *const c_void, out: *mut *mut RbrtScene) -> c_int;
     pub fn rbrt_gpu_scene_create_elements(order: *const RbrtElementRef, num_elements: u32, spheres: *const RbrtSphereDesc, num_spheres: u32,
@@ -60,6 +80,10 @@ extern "C" {
     pub fn rbrt_gpu_render_accum_device_frames(scene: *const RbrtScene, cams: *const RbrtCamera, seeds: *const u64, n_frames: u32,
                                                num_samples: u32, opts: *const RbrtRenderOpts, d_accum: *const *mut c_void,
                                                stream: *mut c_void, stats: *mut RbrtStats) -> c_int;
+    /// The collective render with device outputs on rank 0 (shard render -> per-GPU finalise -> gather), enqueue-only when stats = null.
+    pub fn rbrt_gpu_render_frames_device(scene: *const RbrtScene, cams: *const RbrtCamera, seeds: *const u64, n_frames: u32, num_samples: u32,
+                                         opts: *const RbrtRenderOpts, d_rgb_u8: *const *mut c_void, d_hdr_f32: *const *mut c_void,
+                                         stream: *mut c_void, stats: *mut RbrtStats) -> c_int;
     pub fn rbrt_gpu_finalize_device(d_accum: *const c_void, width: u32, height: u32, num_samples: u32, d_rgb: *mut c_void,
                                     d_hdr: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn rbrt_gpu_release_cache() -> c_int;
@@ -77,6 +101,8 @@ pub fn check(rc: c_int) {
 
 /// Owning handle of a GPU scene (flattened SoA buffers + one BVH per mesh).
 pub struct GpuScene(*mut RbrtScene);
+// Sound since library version 0.2: every entry point takes one process-wide lock (the per-device pools behind the handle are
+// shared), so a handle may be created, used and dropped on any thread.  It is NOT Sync-free state: concurrent renders serialise.
 unsafe impl Send for GpuScene {}
 impl Drop for GpuScene { fn drop(&mut self) { unsafe { rbrt_gpu_scene_destroy(self.0); } } }
 
@@ -89,6 +115,10 @@ impl GpuScene {
         check(unsafe { rbrt_gpu_scene_create(spheres.as_ptr(), spheres.len() as u32, descs.as_ptr(), descs.len() as u32, std::ptr::null(), &mut h) });
         GpuScene(h)
     }
+
+    /// All GPUs of the box behind the same call: `GpuScene::init_all_gpus(8)` once, BEFORE creating scenes; `render` is then
+    /// sharded over them inside the library (the reference spreads render_scene over all cores with rayon, lib.rs:84-86).
+    pub fn init_all_gpus(n: i32) { check(unsafe { rbrt_gpu_init_multi(std::ptr::null(), n, RBRT_TRANSPORT_AUTO) }); }
 
     /// Twin of `render_scene(cam, num_samples, scene)` (lib.rs:75-79): row-major RGB8, W*H*3 bytes =
     /// the buffer of `image::ImageBuffer<Rgb<u8>, Vec<u8>>` (wrap with `ImageBuffer::from_raw(w, h, buf)`).

@@ -102,12 +102,48 @@ int arena_alloc(int device, size_t bytes, char** base, size_t* got_bytes) {
 }
 static inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// pinned 4 KB blocks for the per-scene build results (cudaMallocHost is slow: recycled)
+static std::vector<void*> g_pinned_free;
+static void* pinned_get(size_t bytes) {
+    if (bytes <= 4096 && !g_pinned_free.empty()) { void* p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes <= 4096 ? 4096 : bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+static void pinned_put(void* p, size_t bytes) { if (!p) return; if (bytes <= 4096 && g_pinned_free.size() < 16) g_pinned_free.push_back(p); else cudaFreeHost(p); }
+
+void wait_scene_ready(const Scene& sc, int li, cudaStream_t st) { if (sc.rep[li].ready) cudaStreamWaitEvent(st, sc.rep[li].ready, 0); }
+
+int resolve_scene_info(const Scene& sc, bool wait) {
+    Scene& m = const_cast<Scene&>(sc);                                     // lazily filled cache behind the handle (under the API lock)
+    if (!m.info_resolved) {
+        if (!m.info_ev) { m.info_resolved = true; return RBRT_OK; }
+        if (!wait && cudaEventQuery(m.info_ev) != cudaSuccess) { cudaGetLastError(); return RBRT_OK; }
+        cudaError_t e = cudaEventSynchronize(m.info_ev);
+        if (e != cudaSuccess) return cuda_fail(e, "scene build");
+        const BuildResult* r = (const BuildResult*)m.res_h;
+        uint64_t live = 0;
+        for (uint32_t i = 0; i < m.n_meshes; ++i) { live += r[i].live_nodes; if (r[i].error && !m.build_error) m.build_error = (int)i + 1; }
+        m.info.num_bvh_nodes = live;
+        float up = 0, bu = 0;
+        if (m.t_up0 && cudaEventElapsedTime(&up, m.t_up0, m.t_up1) != cudaSuccess) { cudaGetLastError(); up = 0; }
+        if (m.t_b0 && cudaEventElapsedTime(&bu, m.t_b0, m.t_b1) != cudaSuccess) { cudaGetLastError(); bu = 0; }
+        m.info.ms_upload = up; m.info.ms_build = bu;                       // device times: H2D of the triangle soup / build kernels (+ replication)
+        m.info_resolved = true;
+    }
+    if (m.build_error) { set_error("mesh %d: BVH deeper than the traversal stack allows (the mesh was left out of the scene)", m.build_error - 1); return RBRT_E_INVALID; }
+    return RBRT_OK;
+}
+
 void destroy_scene(Scene* sc) {
     if (!sc) return;
     int cur = 0; cudaGetDevice(&cur);
+    for (cudaEvent_t* e : {&sc->info_ev, &sc->t_up0, &sc->t_up1, &sc->t_b0, &sc->t_b1}) if (*e) { cudaEventSynchronize(*e); cudaEventDestroy(*e); *e = nullptr; }
+    pinned_put(sc->res_h, 16ull * sc->n_meshes); sc->res_h = nullptr;
     for (Replica& r : sc->rep) {
-        if (!r.arena) continue;
+        if (!r.arena) { if (r.ready) cudaEventDestroy(r.ready); continue; }
         ArenaBlock b{r.arena, r.arena_bytes, r.device, {}};
+        if (r.ready) { b.pending.push_back(r.ready); r.ready = nullptr; }  // the build / replication that writes the block
         for (SceneUse& u : sc->uses) if (u.device == r.device && u.ev) { b.pending.push_back(u.ev); u.ev = nullptr; }
         size_t pooled = 0;
         for (auto& g : g_arena_pool) if (g.device == r.device) ++pooled;
@@ -233,6 +269,7 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
         L.mesh = off; off += a256(sizeof(MeshDev) * nm);
         L.etris = off; off += a256(64ull * n_et);
         L.ekind = off; off += a256(4ull * ns);
+        L.result = off; off += a256(sizeof(BuildResult) * (nm ? nm : 1));
         L.nodes = off; off += a256(64ull * total_eff);
         L.total = off;
     }
@@ -251,10 +288,20 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
     sc->dev = sc->rep[0].dev; sc->sm_count = sc->rep[0].sm_count;
     char* const base = sc->rep[0].arena;
     sc->meshes_h.resize(nm);
-    uint64_t live_total = 0, nodes_end = 0;
-    double ms_upload = 0, ms_build = 0;
+    for (Replica& r : sc->rep) { CKSC(cudaSetDevice(r.device)); CKSC(cudaEventCreateWithFlags(&r.ready, cudaEventDisableTiming)); }
+    CKSC(cudaSetDevice(sc->rep[0].device));
+    sc->res_h = pinned_get(sizeof(BuildResult) * (nm ? nm : 1));
+    if (!sc->res_h) { set_error("out of pinned host memory"); destroy_scene(sc); return RBRT_E_ALLOC; }
+    memset(sc->res_h, 0, sizeof(BuildResult) * (nm ? nm : 1));
+    CKSC(cudaEventCreate(&sc->info_ev));
 
+    // Everything below is ENQUEUED: uploads on the device's copy stream, kernels on its build stream (bvh_build.cu).  The call
+    // returns when the caller's arrays have been read; readers of the scene wait for Replica::ready on their own streams.
+    BuildCtx ctx;
+    CKSC(build_begin(sc->rep[0].device, &ctx));
     if (is_root) {
+        CKSC(cudaEventCreate(&sc->t_up0)); CKSC(cudaEventCreate(&sc->t_up1)); CKSC(cudaEventCreate(&sc->t_b0)); CKSC(cudaEventCreate(&sc->t_b1));
+        CKSC(cudaEventRecord(sc->t_up0, ctx.copy)); CKSC(cudaEventRecord(sc->t_b0, ctx.build));
         // ---- elements: spheres + per-element materials (flattened SoA, 16-byte records)
         std::vector<float4> sph(ns), mat(ns + nm), etris;
         std::vector<uint32_t> kind(ns + nm), ekind(ns);
@@ -284,59 +331,44 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
             mat[ns + i] = make_float4(meshes[i].material.albedo.x, meshes[i].material.albedo.y, meshes[i].material.albedo.z, meshes[i].material.param);
             kind[ns + i] = meshes[i].material.kind;
         }
-        if (ns) CKSC(cudaMemcpy(base + sc->lay.sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice));
+        // small pageable arrays: cudaMemcpyAsync stages them before it returns, so the vectors may die at the end of this block
+        if (ns) CKSC(cudaMemcpyAsync(base + sc->lay.sph, sph.data(), 16ull * ns, cudaMemcpyHostToDevice, ctx.copy));
         if (!etris.empty()) {
-            CKSC(cudaMemcpy(base + sc->lay.etris, etris.data(), 16ull * etris.size(), cudaMemcpyHostToDevice));
-            CKSC(cudaMemcpy(base + sc->lay.ekind, ekind.data(), 4ull * ns, cudaMemcpyHostToDevice));
+            CKSC(cudaMemcpyAsync(base + sc->lay.etris, etris.data(), 16ull * etris.size(), cudaMemcpyHostToDevice, ctx.copy));
+            CKSC(cudaMemcpyAsync(base + sc->lay.ekind, ekind.data(), 4ull * ns, cudaMemcpyHostToDevice, ctx.copy));
         }
         if (ns + nm) {
-            CKSC(cudaMemcpy(base + sc->lay.mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice));
-            CKSC(cudaMemcpy(base + sc->lay.kind, kind.data(), 4ull * (ns + nm), cudaMemcpyHostToDevice));
+            CKSC(cudaMemcpyAsync(base + sc->lay.mat, mat.data(), 16ull * (ns + nm), cudaMemcpyHostToDevice, ctx.copy));
+            CKSC(cudaMemcpyAsync(base + sc->lay.kind, kind.data(), 4ull * (ns + nm), cudaMemcpyHostToDevice, ctx.copy));
         }
+        CKSC(cudaStreamSynchronize(ctx.copy));                            // (these few KB only; keeps the staging assumption out of the contract)
 
-        // ---- meshes: exact AABB (aabbox.rs:62-88, over ALL real triangles), then upload + LBVH
+        // ---- meshes: upload, exact AABB (aabbox.rs:62-88, over ALL real triangles), MeshDev record and LBVH, all on the device
         float4* d_tris = (float4*)(base + sc->lay.tris); float4* d_normals = (float4*)(base + sc->lay.nrm); float4* d_nodes = (float4*)(base + sc->lay.nodes);
+        MeshDev* d_meshes = (MeshDev*)(base + sc->lay.mesh); BuildResult* d_res = (BuildResult*)(base + sc->lay.result);
         uint64_t tri_off = 0;
         for (uint32_t i = 0; i < nm; ++i) {
             const rbrt_mesh_desc& m = meshes[i];
             MeshDev md; memset(&md, 0, sizeof(md));
-            float lo[3] = {3.40282347e+38f, 3.40282347e+38f, 3.40282347e+38f}, hi[3] = {-3.40282347e+38f, -3.40282347e+38f, -3.40282347e+38f};
-            uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
-            const float* d_raw = nullptr;
-            double t1 = now_ms();
-            // upload + exact AABB over ALL real triangles, including those the SIMD tail rule drops (aabbox.rs:62-88, mesh.rs:61)
-            CKSC(upload_mesh(m.tri_vertices, m.num_triangles, lo, hi, &d_raw, 0));
-            double t2 = now_ms();
-            for (int k = 0; k < 3; ++k) { md.lo[k] = lo[k]; md.hi[k] = hi[k]; }
+            const uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
             md.tri_base = (uint32_t)tri_off; md.n_tris = (uint32_t)n_eff; md.node_base = (uint32_t)tri_off;
             md.nrm_base = (uint32_t)tri_off; md.elem = ns + i; md.root_ref = make_leaf_ref(0, 1);
-            if (n_eff) {
-                float mx = 0.0f;
-                for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]); }
-                float pad = pad_rel * mx;
-                uint64_t live = 0; int height = 0;
-                cudaError_t ce = build_mesh_bvh(d_raw, (uint32_t)n_eff, lo, hi, pad, leaf_size, !(sflags & RBRT_SCENE_NO_SAH), d_tris + 3 * tri_off, d_normals + tri_off,
-                                                d_nodes + 4 * tri_off, &md.root_ref, &live, &height, md.qorg, md.qstep, 0);
-                if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh_bvh"); destroy_scene(sc); return rc_; }
-                if (3 * height + 2 > 192) { set_error("mesh %u: BVH depth %d exceeds the traversal stack", i, height); destroy_scene(sc); return RBRT_E_INVALID; }
-                live_total += live;
-                if (live) nodes_end = tri_off + live;
-            }
-            ms_upload += t2 - t1; ms_build += now_ms() - t2;
+            cudaError_t ce = build_mesh(ctx, m.tri_vertices, m.num_triangles, (uint32_t)n_eff, pad_rel, leaf_size, !(sflags & RBRT_SCENE_NO_SAH), md, d_meshes + i,
+                                        d_tris + 3 * tri_off, d_normals + tri_off, d_nodes + 4 * tri_off, d_res + i);
+            if (ce != cudaSuccess) { int rc_ = cuda_fail(ce, "build_mesh"); destroy_scene(sc); return rc_; }
             sc->meshes_h[i] = md;
             tri_off += n_eff;
         }
-        if (nm) CKSC(cudaMemcpy(base + sc->lay.mesh, sc->meshes_h.data(), sizeof(MeshDev) * nm, cudaMemcpyHostToDevice));
-        CKSC(cudaStreamSynchronize(0));                                   // upload + build ran on the default stream
+        CKSC(cudaEventRecord(sc->t_up1, ctx.copy));
+        CKSC(cudaEventRecord(sc->t_b1, ctx.build));
     }
-    sc->info.num_bvh_nodes = live_total;
-    if (collective) {                                                     // replicas on the other GPUs (multi.cu): NCCL broadcast / peer copies
-        double t3 = now_ms();
-        CKS(replicate_scene(sc, nodes_end));
-        ms_upload += now_ms() - t3;
-    }
-    sc->info.ms_upload = ms_upload + (now_ms() - t0 - ms_upload - ms_build);
-    sc->info.ms_build = ms_build;
+    if (collective) CKS(replicate_scene(sc, ctx.build));                  // replicas on the other GPUs (multi.cu): NCCL broadcast / peer copies, enqueued behind the build
+    else CKSC(cudaEventRecord(sc->rep[0].ready, ctx.build));
+    // the per-mesh results: device -> pinned host, behind everything else on the build stream
+    if (nm) CKSC(cudaMemcpyAsync(sc->res_h, base + sc->lay.result, sizeof(BuildResult) * nm, cudaMemcpyDeviceToHost, ctx.build));
+    CKSC(cudaEventRecord(sc->info_ev, ctx.build));
+    if (is_root) CKSC(cudaEventSynchronize(sc->t_up1));                   // the caller's triangle arrays have been read (copy engine: does not wait for busy SMs)
+    sc->ms_host_create = now_ms() - t0;
     CKSC(cudaSetDevice(sc->rep[0].device));
     *out = reinterpret_cast<rbrt_scene*>(sc);
     return RBRT_OK;
@@ -347,8 +379,10 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
 int rbrt_gpu_scene_info(const rbrt_scene* scene, rbrt_scene_info* out) {
     LOCK;
     if (!scene || !out) { set_error("null argument"); return RBRT_E_INVALID; }
-    *out = reinterpret_cast<const Scene*>(scene)->info;
-    return RBRT_OK;
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    int rc = resolve_scene_info(sc, true);                                // waits for the (asynchronous) build; reports a refused mesh
+    *out = sc.info;
+    return rc;
 }
 
 int rbrt_gpu_scene_destroy(rbrt_scene* scene) {
@@ -367,9 +401,10 @@ int rbrt_gpu_render_accum_device(const rbrt_scene* scene, const rbrt_camera* cam
     double t0 = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
     float4* acc1[1] = {(float4*)d_accum};
-    int rc = render_accum(sc, 0, cam, nullptr, 1, spp, opts, acc1, (cudaStream_t)stream, stats);
+    int rc = resolve_scene_info(sc, false);
+    if (!rc) rc = render_accum(sc, 0, cam, nullptr, 1, spp, opts, acc1, (cudaStream_t)stream, stats);
     if (rc) return rc;
-    if (stats) stats->ms_total = now_ms() - t0;
+    if (stats) { stats->ms_total = now_ms() - t0; return resolve_scene_info(sc, true); }
     return RBRT_OK;
 }
 
@@ -384,9 +419,10 @@ int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_came
     CKA(cudaSetDevice(sc.device));
     double t0 = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
-    int rc = render_accum(sc, 0, cams, seeds, n_frames, spp, opts, acc, (cudaStream_t)stream, stats);
+    int rc = resolve_scene_info(sc, false);
+    if (!rc) rc = render_accum(sc, 0, cams, seeds, n_frames, spp, opts, acc, (cudaStream_t)stream, stats);
     if (rc) return rc;
-    if (stats) stats->ms_total = now_ms() - t0;
+    if (stats) { stats->ms_total = now_ms() - t0; return resolve_scene_info(sc, true); }
     return RBRT_OK;
 }
 

@@ -25,10 +25,17 @@ __device__ __forceinline__ uint64_t expand21(uint32_t v) {   // spread the low 2
     return x;
 }
 
-__global__ void k_prepare(const float* __restrict__ raw, uint32_t n, float3 lo, float3 inv_ext,
+// traversal node emission: child boxes quantised OUTWARD (plus one step of margin, see intersect.cuh) onto the mesh's
+// 16-bit grid  bound = qorg + q * qstep
+struct QGrid { float org[3], step[3]; };
+// Per-mesh build parameters, produced ON THE DEVICE by k_mesh_setup from the exact AABB (no host round trip)
+struct BuildParams { float lo[3], inv_ext[3]; float pad; QGrid grid; };
+
+__global__ void k_prepare(const float* __restrict__ raw, uint32_t n, const BuildParams* __restrict__ bp,
                           float4* __restrict__ normals, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float3 lo = make_float3(bp->lo[0], bp->lo[1], bp->lo[2]), inv_ext = make_float3(bp->inv_ext[0], bp->inv_ext[1], bp->inv_ext[2]);
     const float* t = raw + 9 * (size_t)i;
     f3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
     f3 e1 = b - a, e2 = c - a;
@@ -48,10 +55,11 @@ __global__ void k_prepare(const float* __restrict__ raw, uint32_t n, float3 lo, 
 }
 
 // sorted position p -> triangle record {v0|orig, e1, e2} and padded leaf box
-__global__ void k_emit_tris(const float* __restrict__ raw, const uint32_t* __restrict__ order, uint32_t n, float pad,
+__global__ void k_emit_tris(const float* __restrict__ raw, const uint32_t* __restrict__ order, uint32_t n, const BuildParams* __restrict__ bp,
                             float4* __restrict__ tris, float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    const float pad = bp->pad;
     uint32_t orig = order[p];
     const float* t = raw + 9 * (size_t)orig;
     f3 a = mk3(t[0], t[1], t[2]), b = mk3(t[3], t[4], t[5]), c = mk3(t[6], t[7], t[8]);
@@ -178,10 +186,6 @@ __global__ void k_refit(int n, int2* children, int* parent_int,
     }
 }
 
-// traversal node emission: child boxes quantised OUTWARD (plus one step of margin, see intersect.cuh) onto the mesh's
-// 16-bit grid  bound = qorg + q * qstep
-struct QGrid { float org[3], step[3]; };
-
 __device__ __forceinline__ uint32_t quant_lo(float v, float org, float step) {
     float q = floorf((v - org) / step) - 1.0f;
     while (q > 0.0f && __fmaf_rn(q, step, org) > v) q -= 1.0f;             // never above the true bound
@@ -205,11 +209,16 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
     return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void k_collapse4(uint32_t level, uint32_t leaf_size, QGrid g, const int2* __restrict__ children, const int2* __restrict__ range,
+__global__ void k_collapse4(uint32_t level, uint32_t leaf_size, const BuildParams* __restrict__ bp, const int2* __restrict__ children, const int2* __restrict__ range,
                             const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                             const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
                             uint32_t* __restrict__ queue, CollapseState* st, uint4* __restrict__ out) {
     const uint32_t begin = st->begin[level & 1], end = st->end[level & 1];
+    if (begin == end) {                                                    // the tree is complete: the remaining launches of the fixed sequence only
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->begin[(level + 1) & 1] = end; st->end[(level + 1) & 1] = end; }   // pass the empty level on
+        return;
+    }
+    const QGrid g = bp->grid;
     for (uint32_t j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
         const int i = (int)queue[j];
         int src[4]; int32_t ref[4]; int nc = 2;
@@ -291,125 +300,174 @@ __global__ void k_aabb(const float* __restrict__ raw, uint64_t n_vertices, int* 
     }
 }
 
-// Grow-only device scratch shared by all builds of the process (one allocation instead of ~16 per build).
-static void* g_scratch[64] = {nullptr};
-static size_t g_scratch_bytes[64] = {0};
-void release_build_scratch() {
-    int cur = 0; cudaGetDevice(&cur);
-    for (int d = 0; d < 64; ++d) if (g_scratch[d]) { cudaSetDevice(d); cudaFree(g_scratch[d]); g_scratch[d] = nullptr; g_scratch_bytes[d] = 0; }
-    cudaSetDevice(cur);
-}
-static cudaError_t scratch(size_t bytes, char** out) {
-    int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
-    dev &= 63;
-    if (g_scratch_bytes[dev] < bytes) {
-        cudaFree(g_scratch[dev]); g_scratch[dev] = nullptr; g_scratch_bytes[dev] = 0;
-        e = cudaMalloc(&g_scratch[dev], bytes); if (e != cudaSuccess) return e;
-        g_scratch_bytes[dev] = bytes;
+// ------------------------------------------------------------------ device-side set-up / wrap-up of one mesh
+// MeshDev record + build parameters from the exact AABB (mm: ordered-int min/max cell filled by k_aabb)
+__global__ void k_mesh_setup(const int* __restrict__ mm, MeshDev proto, float pad_rel, MeshDev* __restrict__ out, BuildParams* __restrict__ bp) {
+    if (threadIdx.x || blockIdx.x) return;
+    MeshDev md = proto;
+    float lo[3], hi[3], mx = 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = ord2f(mm[k]); hi[k] = ord2f(mm[3 + k]);
+        md.lo[k] = lo[k]; md.hi[k] = hi[k];
+        mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]);
     }
-    *out = (char*)g_scratch[dev];
-    return cudaSuccess;
-}
-
-#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
-
-// Upload one mesh's triangle soup (host pointer, n_all triangles) into the scratch and return its exact AABB.
-cudaError_t upload_mesh(const float* h_tris, uint64_t n_all, float lo[3], float hi[3], const float** d_raw_out, cudaStream_t st) {
-    char* base = nullptr;
-    size_t raw_bytes = (36ull * n_all + 255) & ~255ull;
-    CK(scratch(raw_bytes + 256 + 160ull * (n_all + 64) + (64ull << 20), &base));     // raw + AABB cell + build arrays + sort temp (see build_mesh_bvh)
-    CK(cudaMemcpyAsync(base, h_tris, 36ull * n_all, cudaMemcpyHostToDevice, st));
-    int* mm = (int*)(base + raw_bytes);
-    k_aabb_init<<<1, 32, 0, st>>>(mm);
-    if (n_all) k_aabb<<<148 * 4, 256, 0, st>>>((const float*)base, n_all * 3, mm);
-    int h[6];
-    CK(cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int k = 0; k < 3; ++k) { lo[k] = ord2f(h[k]); hi[k] = ord2f(h[3 + k]); }
-    *d_raw_out = (const float*)base;
-    return cudaSuccess;
-}
-
-cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size, bool sah,
-                           float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
-                           int* tree_height, float qorg[3], float qstep[3], cudaStream_t st) {
-    *live_nodes = 0; *tree_height = 0;
-    QGrid grid;
+    const float pad = pad_rel * mx;
+    bp->pad = pad;
     for (int k = 0; k < 3; ++k) {                                          // 16-bit grid over the padded mesh box, 8 steps of slack per side
         float ext = (hi[k] + pad) - (lo[k] - pad);
         float step = ext / 65500.0f;
         if (!(step > 1e-30f)) step = 1e-30f;
-        grid.step[k] = qstep[k] = step;
-        grid.org[k] = qorg[k] = (lo[k] - pad) - 8.0f * step;
+        bp->grid.step[k] = step; bp->grid.org[k] = (lo[k] - pad) - 8.0f * step;
+        md.qstep[k] = md.n_tris ? step : 0.0f; md.qorg[k] = md.n_tris ? bp->grid.org[k] : 0.0f;
+        bp->lo[k] = lo[k]; bp->inv_ext[k] = hi[k] > lo[k] ? 1.0f / (hi[k] - lo[k]) : 0.0f;
     }
-    if (n == 0) { *root_ref = make_leaf_ref(0, 1); return cudaSuccess; }
-    const int B = 256;
-    const uint32_t g = (n + B - 1) / B, ni = n > 1 ? n - 1 : 1;
-    // carve the scratch: d_raw sits at its start (upload_mesh), the AABB cell after it
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 63, st));
-    char* base = nullptr;
-    int dev = 0; CK(cudaGetDevice(&dev));
-    base = (char*)g_scratch[dev & 63];
-    if (!base || (const char*)d_raw != base) return cudaErrorInvalidValue;                 // build_mesh_bvh follows upload_mesh
-    size_t off = ((36ull * n + 36ull * 8 + 255) & ~255ull) + 256;                           // raw (n_eff <= n_all <= n_eff + 7) + AABB cell
-    auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 255) & ~255ull; return p; };
-    uint64_t* keys = (uint64_t*)take(8ull * n); uint64_t* keys_s = (uint64_t*)take(8ull * n);
-    uint32_t* vals = (uint32_t*)take(4ull * n); uint32_t* vals_s = (uint32_t*)take(4ull * n);
-    float4* leaf_lo = (float4*)take(16ull * n); float4* leaf_hi = (float4*)take(16ull * n);
-    float4* node_lo = (float4*)take(16ull * ni); float4* node_hi = (float4*)take(16ull * ni);
-    int2* children = (int2*)take(8ull * ni); int2* range = (int2*)take(8ull * ni);
-    int* parent_int = (int*)take(4ull * ni); int* parent_leaf = (int*)take(4ull * n);
-    int* flags = (int*)take(4ull * ni); int* height = (int*)take(4ull * ni);
-    uint32_t* queue = (uint32_t*)take(4ull * ni); CollapseState* cstate = (CollapseState*)take(sizeof(CollapseState));
-    void* tmp = take(tmp_bytes ? tmp_bytes : 16);
-    if (off > g_scratch_bytes[dev & 63]) return cudaErrorMemoryAllocation;
+    *out = md;
+}
 
-    float3 flo = make_float3(lo[0], lo[1], lo[2]);
-    float3 inv = make_float3(hi[0] > lo[0] ? 1.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1.0f / (hi[1] - lo[1]) : 0.0f,
-                             hi[2] > lo[2] ? 1.0f / (hi[2] - lo[2]) : 0.0f);
-    k_prepare<<<g, B, 0, st>>>(d_raw, n, flo, inv, d_normals, keys, vals);
-    CK(cudaGetLastError());
-    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
-    k_emit_tris<<<g, B, 0, st>>>(d_raw, vals_s, n, pad, d_tris, leaf_lo, leaf_hi);
-    CK(cudaGetLastError());
-    if (n <= leaf_size || n == 1) {
-        *root_ref = make_leaf_ref(0, n);
-        CK(cudaStreamSynchronize(st));
-        return cudaSuccess;
+__global__ void k_collapse_init(CollapseState* st, uint32_t* queue) {
+    if (threadIdx.x || blockIdx.x) return;
+    CollapseState init; init.begin[0] = 0; init.begin[1] = 0; init.end[0] = 1; init.end[1] = 0; init.tail = 1; init.done = 0; init.depth = 0; init.pad = 0;
+    *st = init; queue[0] = 0u;
+}
+
+// The tree is in place: publish its root, or — if it is deeper than the traversal stack allows (pathological input) — take the
+// mesh out of the scene (n_tris = 0: never traversed) and raise the error the host reports at its next synchronising call.
+__global__ void k_build_finish(const CollapseState* __restrict__ st, uint32_t levels_run, MeshDev* __restrict__ md, BuildResult* __restrict__ res) {
+    if (threadIdx.x || blockIdx.x) return;
+    BuildResult r; r.pad = 0;
+    if (!st) { r.live_nodes = 0; r.depth = 0; r.error = 0; *res = r; return; }   // the whole mesh is one leaf (root_ref came with the proto)
+    const bool unfinished = st->begin[levels_run & 1] != st->end[levels_run & 1];
+    const bool bad = unfinished || 3 * st->depth + 2 > RBRT_STACK;
+    r.live_nodes = bad ? 0u : st->tail; r.depth = st->depth; r.error = bad ? 1u : 0u;
+    if (bad) md->n_tris = 0; else md->root_ref = 0;
+    *res = r;
+}
+
+// ------------------------------------------------------------------ scratch + streams, per device
+// Two grow-only scratch slots per device: a scene's create uploads into one while the previous scene's build may still be
+// reading the other.  A slot's `busy` event marks the last build kernel that reads it.
+struct ScratchSlot { void* p = nullptr; size_t bytes = 0; cudaEvent_t busy = nullptr, up = nullptr; };
+struct DeviceBuild { ScratchSlot slot[2]; int next = 0; cudaStream_t copy = nullptr, build = nullptr; };
+static DeviceBuild g_build[64];
+
+void release_build_scratch() {
+    int cur = 0; cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+        DeviceBuild& B = g_build[d];
+        if (!B.copy && !B.slot[0].p && !B.slot[1].p) continue;
+        cudaSetDevice(d);
+        if (B.build) cudaStreamSynchronize(B.build);
+        if (B.copy) cudaStreamSynchronize(B.copy);
+        for (auto& s : B.slot) { cudaFree(s.p); if (s.busy) cudaEventDestroy(s.busy); if (s.up) cudaEventDestroy(s.up); s = ScratchSlot(); }
+        if (B.copy) cudaStreamDestroy(B.copy);
+        if (B.build) cudaStreamDestroy(B.build);
+        B = DeviceBuild();
     }
-    CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
-    k_karras<<<(ni + B - 1) / B, B, 0, st>>>(keys_s, (int)n, children, range, parent_int, parent_leaf);
-    CK(cudaGetLastError());
-    // SAH pass: tree rotations during the refit; only with one-triangle leaves (a rotated subtree no longer covers a
-    // contiguous run of the Morton order, which multi-triangle leaves rely on).  RBRT_SAH_PASSES: tuning knob.
-    static const int sah_passes_env = getenv("RBRT_SAH_PASSES") ? atoi(getenv("RBRT_SAH_PASSES")) : 1;
-    const int passes = (sah && leaf_size == 1) ? sah_passes_env : 0;
-    if (passes <= 0) k_refit<false><<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
-    for (int pass = 0; pass < passes; ++pass) {
-        if (pass) CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
-        k_refit<true><<<g, B, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+    cudaSetDevice(cur);
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t build_begin(int device, BuildCtx* ctx) {
+    DeviceBuild& B = g_build[device & 63];
+    if (!B.copy) {
+        CK(cudaStreamCreateWithFlags(&B.copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&B.build, cudaStreamNonBlocking));
+        for (auto& s : B.slot) { CK(cudaEventCreateWithFlags(&s.busy, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming)); }
     }
-    CK(cudaGetLastError());
-    int hbin = 0;                                                          // binary height bounds the number of BFS levels
-    CK(cudaMemcpyAsync(&hbin, height, 4, cudaMemcpyDeviceToHost, st));
-    {
-        CollapseState init; memset(&init, 0, sizeof(init));
-        init.end[0] = 1; init.tail = 1;
-        const uint32_t root = 0;
-        CK(cudaMemcpyAsync(cstate, &init, sizeof(init), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(queue, &root, 4, cudaMemcpyHostToDevice, st));
+    ctx->device = device; ctx->slot = B.next; B.next ^= 1;
+    ctx->copy = B.copy; ctx->build = B.build;
+    return cudaSuccess;
+}
+
+cudaError_t build_uploads_done(BuildCtx& ctx, cudaEvent_t ev) { return cudaEventRecord(ev, ctx.copy); }
+
+#define COLLAPSE_LEVELS 64       // launches of the level-synchronous collapse: the wide tree may be at most 63 deep (RBRT_STACK), deeper ones are refused
+
+cudaError_t build_mesh(BuildCtx& ctx, const float* h_tris, uint64_t n_all, uint32_t n, float pad_rel, uint32_t leaf_size, bool sah,
+                       const MeshDev& proto, MeshDev* d_mesh, float4* d_tris, float4* d_normals, float4* d_nodes, BuildResult* d_res) {
+    DeviceBuild& B = g_build[ctx.device & 63];
+    ScratchSlot& S = B.slot[ctx.slot];
+    cudaStream_t cs = ctx.copy, st = ctx.build;
+    const int Bk = 256;
+    const uint32_t g = (n + Bk - 1) / Bk, ni = n > 1 ? n - 1 : 1;
+    size_t tmp_bytes = 0;
+    if (n) CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 63, st));
+    // carve the slot: raw triangle soup | AABB cell + build parameters | build arrays | sort temp
+    const size_t raw_bytes = (36ull * n_all + 255) & ~255ull;
+    size_t off = raw_bytes + 512;
+    auto take_off = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~255ull; return o; };
+    const size_t o_keys = take_off(8ull * n), o_keys_s = take_off(8ull * n), o_vals = take_off(4ull * n), o_vals_s = take_off(4ull * n);
+    const size_t o_leaf_lo = take_off(16ull * n), o_leaf_hi = take_off(16ull * n), o_node_lo = take_off(16ull * ni), o_node_hi = take_off(16ull * ni);
+    const size_t o_children = take_off(8ull * ni), o_range = take_off(8ull * ni), o_parent_int = take_off(4ull * ni), o_parent_leaf = take_off(4ull * n);
+    const size_t o_flags = take_off(4ull * ni), o_height = take_off(4ull * ni), o_queue = take_off(4ull * ni), o_cstate = take_off(sizeof(CollapseState));
+    const size_t o_tmp = take_off(tmp_bytes ? tmp_bytes : 16);
+    if (S.bytes < off) {                                                   // grow (rare): nothing may still be using the slot
+        CK(cudaEventSynchronize(S.busy));
+        CK(cudaStreamSynchronize(cs));
+        cudaFree(S.p); S.p = nullptr; S.bytes = 0;
+        const size_t want = off + off / 8 + (1u << 20);
+        CK(cudaMalloc(&S.p, want)); S.bytes = want;
     }
-    CK(cudaStreamSynchronize(st));
-    uint32_t gcol = (ni + B - 1) / B; if (gcol > 148u * 8u) gcol = 148u * 8u;
-    for (int level = 0; level < hbin; ++level)
-        k_collapse4<<<gcol, B, 0, st>>>((uint32_t)level, leaf_size, grid, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate,
-                                        reinterpret_cast<uint4*>(d_nodes));
+    char* base = (char*)S.p;
+    // ---- upload (copy stream): after the previous build that read this slot
+    CK(cudaStreamWaitEvent(cs, S.busy, 0));
+    if (n_all) CK(cudaMemcpyAsync(base, h_tris, 36ull * n_all, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(S.up, cs));
+    // ---- build (build stream)
+    CK(cudaStreamWaitEvent(st, S.up, 0));
+    const float* d_raw = (const float*)base;
+    int* mm = (int*)(base + raw_bytes);
+    BuildParams* bp = (BuildParams*)(base + raw_bytes + 64);
+    k_aabb_init<<<1, 32, 0, st>>>(mm);
+    if (n_all) k_aabb<<<148 * 4, 256, 0, st>>>(d_raw, n_all * 3, mm);    // exact AABB over ALL real triangles, also those the SIMD tail rule drops (aabbox.rs:62-88, mesh.rs:61)
+    MeshDev pr = proto;
+    const bool one_leaf = n && (n <= leaf_size || n == 1);
+    if (one_leaf) pr.root_ref = make_leaf_ref(0, n);
+    k_mesh_setup<<<1, 32, 0, st>>>(mm, pr, pad_rel, d_mesh, bp);
     CK(cudaGetLastError());
-    CollapseState fin;
-    CK(cudaMemcpyAsync(&fin, cstate, sizeof(fin), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    *live_nodes = fin.tail; *tree_height = (int)fin.depth; *root_ref = 0;
+    if (n) {
+        uint64_t* keys = (uint64_t*)(base + o_keys); uint64_t* keys_s = (uint64_t*)(base + o_keys_s);
+        uint32_t* vals = (uint32_t*)(base + o_vals); uint32_t* vals_s = (uint32_t*)(base + o_vals_s);
+        float4* leaf_lo = (float4*)(base + o_leaf_lo); float4* leaf_hi = (float4*)(base + o_leaf_hi);
+        float4* node_lo = (float4*)(base + o_node_lo); float4* node_hi = (float4*)(base + o_node_hi);
+        int2* children = (int2*)(base + o_children); int2* range = (int2*)(base + o_range);
+        int* parent_int = (int*)(base + o_parent_int); int* parent_leaf = (int*)(base + o_parent_leaf);
+        int* flags = (int*)(base + o_flags); int* height = (int*)(base + o_height);
+        uint32_t* queue = (uint32_t*)(base + o_queue); CollapseState* cstate = (CollapseState*)(base + o_cstate);
+        void* tmp = base + o_tmp;
+        k_prepare<<<g, Bk, 0, st>>>(d_raw, n, bp, d_normals, keys, vals);
+        CK(cudaGetLastError());
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, vals_s, (int)n, 0, 63, st));
+        k_emit_tris<<<g, Bk, 0, st>>>(d_raw, vals_s, n, bp, d_tris, leaf_lo, leaf_hi);
+        CK(cudaGetLastError());
+        if (!one_leaf) {
+            CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
+            k_karras<<<(ni + Bk - 1) / Bk, Bk, 0, st>>>(keys_s, (int)n, children, range, parent_int, parent_leaf);
+            CK(cudaGetLastError());
+            // SAH pass: tree rotations during the refit; only with one-triangle leaves (a rotated subtree no longer covers a
+            // contiguous run of the Morton order, which multi-triangle leaves rely on).  RBRT_SAH_PASSES: tuning knob.
+            static const int sah_passes_env = getenv("RBRT_SAH_PASSES") ? atoi(getenv("RBRT_SAH_PASSES")) : 1;
+            const int passes = (sah && leaf_size == 1) ? sah_passes_env : 0;
+            if (passes <= 0) k_refit<false><<<g, Bk, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+            for (int pass = 0; pass < passes; ++pass) {
+                if (pass) CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
+                k_refit<true><<<g, Bk, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+            }
+            CK(cudaGetLastError());
+            k_collapse_init<<<1, 32, 0, st>>>(cstate, queue);
+            uint32_t gcol = (ni + Bk - 1) / Bk; if (gcol > 148u * 8u) gcol = 148u * 8u;
+            // level-synchronous collapse, a FIXED number of launches (the depth is only known on the device): a level of a finished
+            // tree returns at once (~2 us each)
+            for (int level = 0; level < COLLAPSE_LEVELS; ++level)
+                k_collapse4<<<gcol, Bk, 0, st>>>((uint32_t)level, leaf_size, bp, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate,
+                                                reinterpret_cast<uint4*>(d_nodes));
+            CK(cudaGetLastError());
+            k_build_finish<<<1, 32, 0, st>>>(cstate, COLLAPSE_LEVELS, d_mesh, d_res);
+        } else k_build_finish<<<1, 32, 0, st>>>(nullptr, 0, d_mesh, d_res);
+    } else k_build_finish<<<1, 32, 0, st>>>(nullptr, 0, d_mesh, d_res);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(S.busy, st));
     return cudaSuccess;
 }
 

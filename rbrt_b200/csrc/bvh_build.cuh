@@ -1,22 +1,29 @@
-// bvh_build.cuh — entry point of the GPU LBVH builder (bvh_build.cu).
+// bvh_build.cuh — the GPU LBVH builder (bvh_build.cu): fully ASYNCHRONOUS.  A scene's meshes are uploaded on a copy stream
+// and built on a build stream of the device; nothing is read back to the host on the way (the exact mesh AABB, the node
+// grid and the MeshDev record are produced and consumed on the device), so rbrt_gpu_scene_create returns as soon as the
+// triangle soup has left the caller's arrays, while renders of earlier frames keep the SMs busy.
 #pragma once
 #include "common.cuh"
 
 namespace rbrt {
 
-// upload_mesh copies a mesh's n_all x 9 floats (HOST pointer, world space, original order) into the process-wide build
-// scratch and returns the exact AABB over ALL of them (aabbox.rs:62-88, computed on the device); build_mesh_bvh must
-// follow it directly with d_raw = the pointer it returned and n = the triangles the reference actually tests.
-cudaError_t upload_mesh(const float* h_tris, uint64_t n_all, float lo[3], float hi[3], const float** d_raw_out, cudaStream_t st);
-void release_build_scratch();
+struct BuildResult { uint32_t live_nodes, depth, error, pad; };      // per mesh, written on the device when its tree is complete
 
-// d_raw: n triangles x 9 floats on the device (world space, original order).
-// Writes n triangle records (3 float4 each) in Morton order to d_tris, n unit normals in ORIGINAL
-// order to d_normals and up to n-1 64-byte 4-wide nodes to d_nodes (tree_height = depth of the wide tree); qorg/qstep = the 16-bit grid the node boxes are
-// quantised on.  lo/hi = exact mesh AABB.
-// sah: run the tree-rotation pass during the refit (one-triangle leaves only).
-cudaError_t build_mesh_bvh(const float* d_raw, uint32_t n, const float lo[3], const float hi[3], float pad, uint32_t leaf_size, bool sah,
-                           float4* d_tris, float4* d_normals, float4* d_nodes, int32_t* root_ref, uint64_t* live_nodes,
-                           int* tree_height, float qorg[3], float qstep[3], cudaStream_t st);
+struct BuildCtx {
+    int device = 0, slot = 0;
+    cudaStream_t copy = nullptr, build = nullptr;    // per-device streams (non-blocking): H2D uploads / build kernels
+};
+
+// Picks one of the device's two scratch slots (a create can upload while the previous scene's build is still running).
+cudaError_t build_begin(int device, BuildCtx* ctx);
+// One mesh: H2D of its n_all x 9 floats (HOST pointer, world space, original order) on ctx.copy, then on ctx.build the exact
+// AABB over ALL of them (aabbox.rs:62-88), the MeshDev record (*d_mesh = proto + box + node grid), n_eff triangle records
+// (Morton order), unit normals (ORIGINAL order), up to n_eff - 1 64-byte 4-wide nodes, and *d_res.
+// sah: tree rotations during the refit (one-triangle leaves only).
+cudaError_t build_mesh(BuildCtx& ctx, const float* h_tris, uint64_t n_all, uint32_t n_eff, float pad_rel, uint32_t leaf_size, bool sah,
+                       const MeshDev& proto, MeshDev* d_mesh, float4* d_tris, float4* d_normals, float4* d_nodes, BuildResult* d_res);
+// Event recorded on ctx.copy after the last upload: once it has completed the caller's arrays are no longer read.
+cudaError_t build_uploads_done(BuildCtx& ctx, cudaEvent_t ev);
+void release_build_scratch();
 
 }  // namespace rbrt

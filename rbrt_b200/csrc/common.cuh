@@ -95,6 +95,8 @@ struct SceneDev {
     uint32_t n_etris;
 };
 
+#define RBRT_STACK 192            // traversal stack entries per lane: <= 3 per level of the 4-wide tree + sentinel (checked by the builder)
+
 // leaf reference encoding: ~((first << 3) | (count - 1)), count in 1..8
 __host__ __device__ __forceinline__ int32_t make_leaf_ref(uint32_t first, uint32_t count) { return ~(int32_t)((first << 3) | (count - 1)); }
 

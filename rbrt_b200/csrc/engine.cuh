@@ -45,8 +45,9 @@ struct WaveBuffers {
 
 // A scene's device data is ONE allocation ("arena"); every array sits at a fixed offset, so a replica on another GPU is
 // the same bytes at another base address (multi.cu broadcasts the arena instead of rebuilding the LBVH on every GPU).
-struct ArenaLayout { size_t nodes = 0, tris = 0, nrm = 0, sph = 0, mat = 0, kind = 0, mesh = 0, etris = 0, ekind = 0, total = 0; };
-struct Replica { int device = 0; char* arena = nullptr; size_t arena_bytes = 0; SceneDev dev{}; int sm_count = 148; };
+struct ArenaLayout { size_t nodes = 0, tris = 0, nrm = 0, sph = 0, mat = 0, kind = 0, mesh = 0, etris = 0, ekind = 0, result = 0, total = 0; };
+struct Replica { int device = 0; char* arena = nullptr; size_t arena_bytes = 0; SceneDev dev{}; int sm_count = 148;
+                 cudaEvent_t ready = nullptr; };   // recorded when this replica's data is complete (build / replication are asynchronous): every reader's stream waits for it
 struct SceneUse { int device; cudaStream_t stream; cudaEvent_t ev; };   // last work enqueued on a stream that reads the scene
 
 struct Scene {
@@ -60,7 +61,15 @@ struct Scene {
     int sm_count = 148;
     bool collective = false;     // created under a communicator: renders with shard_count == 0 are sharded over its ranks
     mutable std::vector<SceneUse> uses;
+    // scene_create does not wait for the build: per-mesh results (live nodes, depth, error) arrive in pinned host memory behind info_ev
+    void* res_h = nullptr;       // BuildResult[n_meshes]
+    cudaEvent_t info_ev = nullptr, t_up0 = nullptr, t_up1 = nullptr, t_b0 = nullptr, t_b1 = nullptr;
+    mutable bool info_resolved = false;
+    mutable int build_error = 0; // mesh index + 1 whose tree was refused (deeper than the traversal stack), 0 = none
+    double ms_host_create = 0;
 };
+int resolve_scene_info(const Scene& sc, bool wait);   // api.cu: fills info from the build results once they are there (wait: block for them); returns RBRT_E_* if the build refused a mesh
+void wait_scene_ready(const Scene& sc, int li, cudaStream_t st);   // makes `st` wait for replica li's data
 
 // Everything a wavefront kernel needs, passed by value (kernel parameter space).
 struct WaveParams {
@@ -78,6 +87,7 @@ struct WaveParams {
     uint32_t max_depth;      // 50 (lib.rs:99)
     uint32_t fetch_thr;      // k_trace re-fills a warp from the queue when fewer lanes than this still traverse
     uint32_t tail_thr;       // the same for k_tail, whose "re-fill" also shades the lanes' pending hits
+    uint32_t use_cull;       // k_generate skips provably missed elements of camera rays (render.cu cone_of_sphere)
     uint4* rec;
     uint32_t* candq; uint32_t* matq[2][3];
     float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;

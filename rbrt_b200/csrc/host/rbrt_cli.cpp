@@ -295,6 +295,8 @@ void usage() {
            "  -s, --samples <samples>          number of rays per pixel [default: 5]\n"
            "      --seed <seed>                (extension) Philox seed; the reference is unseeded [default: 0]\n"
            "      --device <device>            (extension) CUDA device [default: 0]\n"
+           "      --gpus <n>                   (extension) render on the first n GPUs of this box: tile-sharded inside the library [default: 1]\n"
+           "      --transport <auto|nccl|peer> (extension) how the GPUs exchange the scene and the image [default: auto]\n"
            "      --check                      (extension) parse the scene, print a summary and exit without rendering\n"
            "  -h, --help                       Print help\n  -V, --version                    Print version\n");
 }
@@ -312,6 +314,7 @@ int main(int argc, char** argv) {
     std::string target = "dbg_out.png", config = "scenes/example_scene.yaml";      // main.rs:14-50
     uint32_t height = 600, width = 800, samples = 5;
     uint64_t seed = 0; int device = 0; bool check_only = false;
+    uint32_t gpus = 1; int transport = RBRT_TRANSPORT_AUTO;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto value = [&](const char* name) -> const char* {
@@ -328,6 +331,12 @@ int main(int argc, char** argv) {
         else if (key == "-s" || key == "--samples") samples = parse_u32(value("--samples"), "--samples");
         else if (key == "--seed") seed = strtoull(value("--seed"), nullptr, 0);
         else if (key == "--device") device = (int)parse_u32(value("--device"), "--device");
+        else if (key == "--gpus") gpus = parse_u32(value("--gpus"), "--gpus");
+        else if (key == "--transport") {
+            std::string t = value("--transport");
+            if (t == "auto") transport = RBRT_TRANSPORT_AUTO; else if (t == "nccl") transport = RBRT_TRANSPORT_NCCL; else if (t == "peer") transport = RBRT_TRANSPORT_PEER;
+            else die("error: invalid value '" + t + "' for '--transport' [possible values: auto, nccl, peer]");
+        }
         else if (key == "--check") check_only = true;
         else if (key == "-h" || key == "--help") { usage(); return 0; }
         else if (key == "-V" || key == "--version") { printf("rbrt 0.1 (%s)\n", rbrt_gpu_version()); return 0; }
@@ -361,7 +370,13 @@ int main(int argc, char** argv) {
         return 0;
     }
 
-    if (rbrt_gpu_init(device) != RBRT_OK) die(std::string("rbrt_gpu: ") + rbrt_last_error());
+    // The reference's render_scene spreads over every core of the host (rayon, lib.rs:84-86); here --gpus spreads it over the
+    // GPUs of the box: ONE process, the library replicates the scene and shards the image (csrc/multi.cu).
+    if (gpus > 1) {
+        std::vector<int> devs(gpus);
+        for (uint32_t i = 0; i < gpus; ++i) devs[i] = device + (int)i;
+        if (rbrt_gpu_init_multi(devs.data(), (int)gpus, transport) != RBRT_OK) die(std::string("rbrt_gpu: ") + rbrt_last_error());
+    } else if (rbrt_gpu_init(device) != RBRT_OK) die(std::string("rbrt_gpu: ") + rbrt_last_error());
     rbrt_scene* scene = nullptr;
     if (rbrt_gpu_scene_create(spheres.data(), (uint32_t)spheres.size(), meshes.data(), (uint32_t)meshes.size(), nullptr, &scene) != RBRT_OK)
         die(std::string("rbrt_gpu: ") + rbrt_last_error());
@@ -374,7 +389,7 @@ int main(int argc, char** argv) {
     rbrt_gpu_scene_destroy(scene);
     printf("Saving rendered image to %s\n", target.c_str());                        // main.rs:84
     if (!save_image(target, rgb, width, height)) die("Unable to save target img to " + target + "! Maybe the directory does not exist?");   // main.rs:86-91
-    fprintf(stderr, "[rbrt_b200] %llu rays, %llu samples in %.1f ms on the device (%.1f Mrays/s)\n", (unsigned long long)st.rays,
-            (unsigned long long)st.paths, st.ms_device, st.ms_device > 0 ? st.rays / st.ms_device / 1e3 : 0.0);
+    fprintf(stderr, "[rbrt_b200] %llu rays, %llu samples in %.1f ms on %u GPU%s (%.1f Mrays/s)\n", (unsigned long long)st.rays,
+            (unsigned long long)st.paths, st.ms_device, gpus, gpus > 1 ? "s" : "", st.ms_device > 0 ? st.rays / st.ms_device / 1e3 : 0.0);
     return 0;
 }

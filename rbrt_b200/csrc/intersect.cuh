@@ -12,7 +12,6 @@ namespace rbrt {
 #define RBRT_MIN_DIST 0.001f       // lib.rs:44
 #define RBRT_MAX_DIST 2000.0f      // lib.rs:45
 #define RBRT_T_CAP 999.99994f      // 1.0f / 0.001f as f32 (triangle.rs:146): triangle t must be < this
-#define RBRT_STACK 192            // traversal stack entries per lane: <= 3 per level of the 4-wide tree + sentinel (checked at build)
 
 struct Hit {
     int kind;            // -1 none, 0 sphere, 1 mesh, -2 NaN (reference panics, sphere.rs:33)
@@ -208,7 +207,13 @@ __device__ __forceinline__ RaySlabs ray_slabs(const MeshDev& M, f3 o, f3 d) {
     return r;
 }
 
-__device__ __forceinline__ float q16(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+// (PTX prmt directly: __byte_perm masks its selector with 0x7777 first, and because the selectors are deliberately opaque to the
+// compiler that mask was re-applied at every node visit — six LOP3 per visit on the pipe that binds the kernel)
+__device__ __forceinline__ float q16(uint32_t w, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
+    return __uint_as_float(r);
+}
 
 // One node visit: returns the next reference to process (nearest hit child, or the popped stack top); the other
 // hit children are pushed far-to-near.

@@ -16,7 +16,10 @@
 // NCCL is loaded at run time (dlopen), so a one-GPU host does not need it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
+#include "bvh_build.cuh"
 #include "multi.cuh"
 #include "shade.cuh"
 
@@ -161,48 +164,46 @@ __global__ void __launch_bounds__(256) k_sum_peers(float4* __restrict__ dst, Pee
 }
 
 // ------------------------------------------------------------------ scene replication
-int replicate_scene(Scene* sc, uint64_t nodes_end) {
+int replicate_scene(Scene* sc, cudaStream_t bs) {
+    // Enqueued, not waited for: the build on rank 0's build stream `bs` is followed by the copy of the WHOLE block (its size is
+    // known to every rank from the scene description alone; how many LBVH node slots are live is only known on the device),
+    // and every replica's `ready` event is recorded behind its copy.
     Comm& C = g_comm;
-    const ArenaLayout& L = sc->lay;
-    uint64_t hdr[4] = {nodes_end, sc->info.num_bvh_nodes, 0, 0};
+    const size_t bytes = sc->lay.total;
     if (C.multi_process) {
-        // two broadcasts: 32 bytes (how many LBVH nodes are live), then the block up to the last live node
-        static uint64_t* d_hdr[64] = {nullptr};
-        const int dev = C.devices[0];
-        CKM(cudaSetDevice(dev));
-        if (!d_hdr[dev & 63]) CKM(cudaMalloc(&d_hdr[dev & 63], 32));
-        if (C.rank == 0) CKM(cudaMemcpyAsync(d_hdr[dev & 63], hdr, 32, cudaMemcpyHostToDevice, 0));
-        CKN(g_nccl.Broadcast(d_hdr[dev & 63], d_hdr[dev & 63], 32, ncclChar, 0, (ncclComm_t)C.nccl[0], 0));
-        CKM(cudaMemcpyAsync(hdr, d_hdr[dev & 63], 32, cudaMemcpyDeviceToHost, 0));
-        CKM(cudaStreamSynchronize(0));
-        const size_t bytes = L.nodes + 64ull * hdr[0];
-        CKN(g_nccl.Broadcast(sc->rep[0].arena, sc->rep[0].arena, bytes, ncclChar, 0, (ncclComm_t)C.nccl[0], 0));
-        if (C.rank != 0) {
-            if (sc->n_meshes) CKM(cudaMemcpyAsync(sc->meshes_h.data(), sc->rep[0].arena + L.mesh, sizeof(MeshDev) * sc->n_meshes, cudaMemcpyDeviceToHost, 0));
-            sc->info.num_bvh_nodes = hdr[1];
-        }
-        CKM(cudaStreamSynchronize(0));
-        if (C.rank != 0)
-            for (const MeshDev& m : sc->meshes_h)                          // same check the builder made on rank 0 (api.cu); a failed build there aborts before this
-                if (m.n_tris > (1u << 28)) { set_error("replicated scene is corrupt"); return RBRT_E_CUDA; }
+        CKM(cudaSetDevice(C.devices[0]));
+        CKN(g_nccl.Broadcast(sc->rep[0].arena, sc->rep[0].arena, bytes, ncclChar, 0, (ncclComm_t)C.nccl[0], bs));
+        CKM(cudaEventRecord(sc->rep[0].ready, bs));
         return RBRT_OK;
     }
-    const size_t bytes = L.nodes + 64ull * nodes_end;
+    std::vector<cudaStream_t> s_of(C.local_n, bs);
+    for (int li = 1; li < C.local_n; ++li) {
+        if (C.devices[li] == C.devices[0]) continue;
+        CKM(cudaSetDevice(C.devices[li]));
+        BuildCtx other; cudaError_t e = build_begin(C.devices[li], &other);
+        if (e != cudaSuccess) return cuda_fail(e, "build_begin");
+        s_of[li] = other.build;
+    }
+    CKM(cudaSetDevice(C.devices[0]));
     if (C.transport == RBRT_TRANSPORT_NCCL) {
         CKN(g_nccl.GroupStart());
-        for (int li = 0; li < C.local_n; ++li) {
-            CKM(cudaSetDevice(C.devices[li]));
-            CKN(g_nccl.Broadcast(sc->rep[li].arena, sc->rep[li].arena, bytes, ncclChar, 0, (ncclComm_t)C.nccl[li], 0));
-        }
+        for (int li = 0; li < C.local_n; ++li)
+            CKN(g_nccl.Broadcast(sc->rep[li].arena, sc->rep[li].arena, bytes, ncclChar, 0, (ncclComm_t)C.nccl[li], s_of[li]));
         CKN(g_nccl.GroupEnd());
+        for (int li = 0; li < C.local_n; ++li) { CKM(cudaSetDevice(C.devices[li])); CKM(cudaEventRecord(sc->rep[li].ready, s_of[li])); }
     } else {
-        CKM(cudaSetDevice(C.devices[0]));
         for (int li = 1; li < C.local_n; ++li) {
-            if (C.devices[li] == C.devices[0]) CKM(cudaMemcpyAsync(sc->rep[li].arena, sc->rep[0].arena, bytes, cudaMemcpyDeviceToDevice, 0));
-            else CKM(cudaMemcpyPeerAsync(sc->rep[li].arena, C.devices[li], sc->rep[0].arena, C.devices[0], bytes, 0));
+            if (C.devices[li] == C.devices[0]) CKM(cudaMemcpyAsync(sc->rep[li].arena, sc->rep[0].arena, bytes, cudaMemcpyDeviceToDevice, bs));
+            else CKM(cudaMemcpyPeerAsync(sc->rep[li].arena, C.devices[li], sc->rep[0].arena, C.devices[0], bytes, bs));
+        }
+        CKM(cudaEventRecord(sc->rep[0].ready, bs));                        // behind the build AND the copies
+        for (int li = 1; li < C.local_n; ++li) {
+            if (C.devices[li] == C.devices[0]) { CKM(cudaEventRecord(sc->rep[li].ready, bs)); continue; }
+            CKM(cudaSetDevice(C.devices[li]));                             // an event is recorded on a stream of ITS device: hop over
+            CKM(cudaStreamWaitEvent(s_of[li], sc->rep[0].ready, 0));
+            CKM(cudaEventRecord(sc->rep[li].ready, s_of[li]));
         }
     }
-    for (int li = 0; li < C.local_n; ++li) { CKM(cudaSetDevice(C.devices[li])); CKM(cudaStreamSynchronize(0)); }
     CKM(cudaSetDevice(C.devices[0]));
     return RBRT_OK;
 }
@@ -235,6 +236,7 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
     const uint32_t W = cams[0].img_width_pix, H = cams[0].img_height_pix;
     const size_t n_px = (size_t)W * H;
     if (!n_px || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
+    { int rc0 = resolve_scene_info(sc, false); if (rc0) return rc0; }     // a mesh the (asynchronous) build refused, if that is known by now
     const int pool = (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT);
     Comm& C = g_comm;
     const bool sharded = sc.collective && o.shard_count == 0 && C.active && C.world > 1;
@@ -250,7 +252,7 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
             rc = finalize(D.accum[f], W, H, spp, d_rgb ? d_rgb[f] : nullptr, d_hdr ? d_hdr[f] : nullptr, st);
             if (rc) return rc;
         }
-        if (stats) stats->launches += n_frames;
+        if (stats) { stats->launches += n_frames; return resolve_scene_info(sc, true); }
         return RBRT_OK;
     }
 
@@ -272,6 +274,9 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
     const size_t gather_total = 3ull * gm.off_px[world] * esize;
     const size_t hdr_base = d_rgb ? 3ull * gm.off_px[world] : 0;          // byte offset of the f32 part of the gather buffer (16-byte aligned: off_px are multiples of 32)
 
+    const bool dbg = getenv("RBRT_DEBUG_MULTI") != nullptr;
+    const auto t_dbg0 = std::chrono::steady_clock::now();
+    auto dbg_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_dbg0).count(); };
     std::vector<RenderJob> jobs(stats ? C.local_n : 0);
     rbrt_stats total; memset(&total, 0, sizeof(total));
     CKM(cudaSetDevice(C.devices[0]));
@@ -305,7 +310,9 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
         if (rc) return rc;
         rc = render_accum(sc, li, cams, seeds, n_frames, spp, &ol, D.accum, s, nullptr, stats ? &jobs[li] : nullptr);
         if (rc) return rc;
-        if (stats && same_dev && C.local_n > 1) {                         // one-GPU emulation of N ranks: the ranks share the device's wavefront pool,
+        bool shared_dev = false;                                          // does another local rank use this GPU (one-GPU emulation of N ranks)?
+        for (int lj = 0; lj < C.local_n; ++lj) if (lj != li && C.devices[lj] == dev) shared_dev = true;
+        if (stats && shared_dev) {                                        // the ranks share the device's wavefront pool,
             rbrt_stats one; memset(&one, 0, sizeof(one));                 // so this rank's counters are read before the next rank resets them
             rc = collect_stats(jobs[li], &one); if (rc) return rc;
             add_stats(&total, one); jobs[li].wb = nullptr;
@@ -322,6 +329,7 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
             }
         }
         if (s != st) CKM(cudaEventRecord(D.ev_done, s));
+        if (dbg) fprintf(stderr, "[multi] rank %u enqueued at %.3f ms\n", r, dbg_ms());
     }
     if (!samples) {
         if (!peer) {
@@ -380,6 +388,7 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
             }
         }
     }
+    if (dbg) fprintf(stderr, "[multi] collectives enqueued at %.3f ms\n", dbg_ms());
     if (stats) {
         for (int li = 0; li < C.local_n; ++li) {
             if (!jobs[li].wb) continue;
@@ -387,10 +396,12 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
             rbrt_stats one; memset(&one, 0, sizeof(one));
             int rc = collect_stats(jobs[li], &one); if (rc) return rc;
             add_stats(&total, one);
+            if (dbg) fprintf(stderr, "[multi] local rank %d done at %.3f ms (device time %.3f ms)\n", li, dbg_ms(), one.ms_device);
         }
         CKM(cudaSetDevice(C.devices[0]));
         CKM(cudaStreamSynchronize(st));                                   // stats != NULL: the call waits for the frame (gather included)
         *stats = total;
+        int rc1 = resolve_scene_info(sc, true); if (rc1) return rc1;
     }
     CKM(cudaSetDevice(C.devices[0]));
     return RBRT_OK;

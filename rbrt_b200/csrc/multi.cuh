@@ -23,9 +23,9 @@ int arena_alloc(int device, size_t bytes, char** base, size_t* got_bytes);
 void destroy_scene(Scene* sc);
 
 // multi.cu
-// Copies replica 0's block (everything up to the last live LBVH node) to the scene's other replicas / ranks and, on
-// ranks that did not build, fills Scene::meshes_h and info from it.
-int replicate_scene(Scene* sc, uint64_t nodes_end);
+// Enqueues, behind the build on `build_stream`, the copy of replica 0's block to the scene's other replicas / ranks and records
+// every replica's `ready` event.
+int replicate_scene(Scene* sc, cudaStream_t build_stream);
 // The collective render (or, without a communicator, render + finalise on one GPU) with device outputs on rank 0.
 int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seeds, uint32_t n_frames, uint32_t spp,
                   const rbrt_render_opts* opts, uint8_t* const* d_rgb, float* const* d_hdr, cudaStream_t st, rbrt_stats* stats);
