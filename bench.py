@@ -93,9 +93,9 @@ def build_workload(name, pinned=False):
     raise SystemExit(f"unknown workload {name}")
 
 
-def make_scene(spheres, meshes, pinned_cache=None):
+def make_scene(spheres, meshes, pinned_cache=None, broadcast=False):
     import rbrt_b200 as R
-    sc = R.Scene()
+    sc = R.Scene(broadcast=broadcast)
     sc.elements += [R.Sphere(c, r, m) for c, r, m in spheres]
     for i, (tris, mat) in enumerate(meshes):
         if pinned_cache is not None:
@@ -402,8 +402,21 @@ def run_gpu(args):
         barrier()
         single_ms.append(e0.elapsed_time(e1))
         stats.append(st.as_dict())
-    ms_single = statistics.median(single_ms)
+    ms_single_one_lane = statistics.median(single_ms)
     rgb_ref = rgb.clone() if rank == 0 else None
+    # the lone frame as rbrt_gpu_render issues it: its sample batches on two lanes (RBRT_OPT_SPLIT_BATCHES), so that the sparse end of
+    # one batch runs under the dense start of the next
+    single_ms = []
+    for k in range(3 + n_single):
+        e0.record(stream)
+        step_single(dict(split=True), _abi.StatsC())
+        e1.record(stream)
+        barrier()
+        if k >= 3:
+            single_ms.append(e0.elapsed_time(e1))
+    ms_single = statistics.median(single_ms)
+    if rank == 0:
+        assert torch.equal(rgb, rgb_ref), "two-lane frame differs from the one-lane frame"
     frame = stats[-1]
     assert all(s_["rays"] == frame["rays"] and s_["paths"] == frame["paths"] for s_ in stats), "frames of one seed differ"
 
@@ -451,7 +464,7 @@ def run_gpu(args):
         regions1, last1 = timed_pipeline(1, 0.4)
         if rank == 0:
             assert torch.equal(last1, rgb_ref), "pipelined frame (1 per batch) differs from the single-frame render"
-    t = torch.tensor([ms, ms_single, statistics.median(regions1) if regions1 else 0.0, min(regions), max(regions)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, ms_single, statistics.median(regions1) if regions1 else 0.0, min(regions), max(regions), ms_single_one_lane], dtype=torch.float64, device="cuda")
     agg = torch.tensor([frame["rays"] * args.steps, frame["paths"] * args.steps, (frame["launches"]) * args.steps,
                         counts["node_visits"] - counts["tail_node_visits"], counts["tri_tests"] - counts["tail_tri_tests"], counts["rays"],
                         counts["traversed_rays"] - counts["tail_traversed_rays"]], dtype=torch.float64, device="cuda")
@@ -460,7 +473,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         dist.all_reduce(trace_ms, op=dist.ReduceOp.MAX)
-    ms, ms_single, ms_fpb1, ms_min, ms_max = (float(x) for x in t.tolist())
+    ms, ms_single, ms_fpb1, ms_min, ms_max, ms_single_one_lane = (float(x) for x in t.tolist())
     rays, paths, launches, V, T, Rc, Cc = (float(x) for x in agg.tolist())
     trace_ms = float(trace_ms.item())
     clocks = clk.summary()
@@ -479,10 +492,12 @@ def run_gpu(args):
             old_scene.close()
             e2e_last[0] = img
 
+    e2e_broadcast = [False]
+
     def step_e2e():
         t_a = time.perf_counter()
-        sc = make_scene(spheres, meshes, pinned)
-        sc.handle()                                           # rbrt_gpu_scene_create: rank 0 H2D of the triangle soup + LBVH build, NCCL broadcast of the block
+        sc = make_scene(spheres, meshes, pinned, broadcast=e2e_broadcast[0])
+        sc.handle()                                           # rbrt_gpu_scene_create: H2D of the triangle soup + LBVH build, enqueued (every rank its own; or rank 0 + NCCL broadcast)
         t_b = time.perf_counter()
         # render -> finalise -> [gather] -> RGB8 image to pinned host memory, enqueued on the frame's stream; the image of
         # the frame submitted `frames_in_flight` steps ago is collected (host buffer ready) and its scene destroyed
@@ -491,41 +506,52 @@ def run_gpu(args):
         t_c = time.perf_counter()
         return (t_b - t_a) * 1e3, (t_c - t_b) * 1e3
 
-    for _ in range(max(2, args.frames_in_flight + 1)):
-        step_e2e()
-    for fin in pipe_e.drain():
-        retire(fin)
-    barrier()
     e_steps = max(2, min(args.steps, 5))
-    e_regions = []
-    t_all = time.perf_counter()
-    while True:
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(e_steps):
-            ms_create, ms_render = step_e2e()
-        for fin in pipe_e.drain():                            # every image of the timed steps is on the host when the clock stops
+
+    def timed_e2e(budget_s):
+        for _ in range(max(2, args.frames_in_flight + 1)):
+            step_e2e()
+        for fin in pipe_e.drain():
             retire(fin)
-        e1.record(stream)
         barrier()
-        e_regions.append(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))   # host-side work (malloc, sync copies) counts too
-        go = torch.tensor([1.0 if (time.perf_counter() - t_all < 0.6 and len(e_regions) < 30) else 0.0], device="cuda")
-        if world > 1:
-            dist.broadcast(go, src=0)
-        if go.item() == 0.0:
-            break
-    print(f"[e2e rank {rank}] last step: scene_create {ms_create:.1f} ms, submit (+ wait for the frame {args.frames_in_flight} steps back) {ms_render:.1f} ms; "
-          f"{len(e_regions)} regions of {e_steps} steps", file=sys.stderr)
+        regs = []
+        t_all = time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(e_steps):
+                ms_create, ms_render = step_e2e()
+            for fin in pipe_e.drain():                        # every image of the timed steps is on the host when the clock stops
+                retire(fin)
+            e1.record(stream)
+            barrier()
+            regs.append(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))   # host-side work (malloc, sync copies) counts too
+            go = torch.tensor([1.0 if (time.perf_counter() - t_all < budget_s and len(regs) < 30) else 0.0], device="cuda")
+            if world > 1:
+                dist.broadcast(go, src=0)
+            if go.item() == 0.0:
+                break
+        print(f"[e2e rank {rank}] broadcast={e2e_broadcast[0]} last step: scene_create {ms_create:.1f} ms, submit (+ wait for the frame {args.frames_in_flight} steps back) "
+              f"{ms_render:.1f} ms; {len(regs)} regions of {e_steps} steps", file=sys.stderr)
+        return regs
+
+    e_regions = timed_e2e(0.6)
     e_ms = statistics.median(e_regions)
+    e_ms_bcast = None
+    if world > 1:                                             # for the record: rank 0 alone uploads + builds, NCCL broadcast of the scene block
+        e2e_broadcast[0] = True
+        e_ms_bcast = statistics.median(timed_e2e(0.4))
+        e2e_broadcast[0] = False
     if rank == 0:
         assert np.array_equal(e2e_last[0].pixels.reshape(-1), rgb_ref.cpu().numpy()), "e2e image differs from the single-frame render"
     e_rays = frame["rays"] * e_steps
-    te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+    te = torch.tensor([e_ms, e_ms_bcast or 0.0], dtype=torch.float64, device="cuda")
     re = torch.tensor([float(e_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(re, op=dist.ReduceOp.SUM)
-    e_val = float(re.item()) / (float(te.item()) / 1e3) / 1e6
+    e_ms_max, e_ms_bcast_max = (float(x) for x in te.tolist())
+    e_val = float(re.item()) / (e_ms_max / 1e3) / 1e6
 
     # ---- image check at EVERY N: rank 0 renders a pixel lattice of the same frame with the CPU oracle; all ranks render that
     #      frame collectively at the same seed and sample count; the lattice pixels must agree bit for bit.  At N = 1 the oracle
@@ -593,14 +619,19 @@ def run_gpu(args):
         "timed_region": {"repeats": len(regions), "steps_per_repeat": args.steps, "ms_median": ms, "ms_min": ms_min, "ms_max": ms_max,
                          "note": "the K-step region (barrier + synchronize on both sides, CUDA events, max over ranks) is repeated; value uses the median region"},
         "single_frame": {"ms_per_step": ms_single, "value": rays / args.steps / (ms_single / 1e3) / 1e6, "unit": "Mrays/s",
-                         "note": "one frame at a time, host waits for each (latency of a lone render_scene call, gather on rank 0 included); `value` keeps "
-                                 "`frames_in_flight` groups of `frames_per_batch` frames in flight on separate streams"},
+                         "ms_per_step_one_lane": ms_single_one_lane,
+                         "note": "one frame at a time, host waits for each (latency of a lone render_scene call, gather on rank 0 included), the frame's "
+                                 "sample batches on two lanes as rbrt_gpu_render issues them (RBRT_OPT_SPLIT_BATCHES; one lane: ms_per_step_one_lane); `value` "
+                                 "keeps `frames_in_flight` groups of `frames_per_batch` frames in flight on separate streams"},
         "frames_per_batch_1": ({"ms_per_step": ms_fpb1 / args.steps, "value": rays / (ms_fpb1 / 1e3) / 1e6, "unit": "Mrays/s"} if regions1 else None),
         "samples_per_s": paths / (ms / 1e3), "rays_per_step": rays / args.steps, "rays_per_sample": rays / max(paths, 1),
         "clocks": clocks,
         "e2e": {"value": e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps, "repeats": len(e_regions),
-                "ms_per_step": float(te.item()) / e_steps, "includes": "scene upload from pinned host memory + LBVH build (rank 0) [+ NCCL broadcast of the scene block] + render + "
-                            "RGB8 image to pinned host memory, per step; frames_in_flight frames overlap (FramePipeline), all images on the host when the clock stops"},
+                "ms_per_step": e_ms_max / e_steps,
+                "ms_per_step_scene_broadcast": (e_ms_bcast_max / e_steps) if e_ms_bcast else None,
+                "includes": "scene upload from pinned host memory + LBVH build (every rank its own replica, the library's default with one process per GPU; "
+                            "ms_per_step_scene_broadcast: rank 0 alone + ncclBroadcast of the 168 MB block) + render + RGB8 image to pinned host memory, per step; "
+                            "frames_in_flight frames overlap (FramePipeline), all images on the host when the clock stops"},
         "gpu_launches": int(launches),
         "multi_gpu": {"inside_library": True, "transport": {0: "none", 1: "nccl", 2: "peer"}.get(comm["transport"], "?"), "nccl_version": comm["nccl_version"]},
         "roofline": {"bound": "hbm", "limiter": "issue / ALU pipe under partial lane occupancy, NOT memory (see `ncu`): the kernel's requested bytes are served by L1/L2",
@@ -611,7 +642,7 @@ def run_gpu(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_traversed_ray": bytes_step / max(Cc, 1),
                      "traversed_rays_per_step": Cc, "traversed_share_of_rays": Cc / max(Rc, 1),
                      "node_visits_per_traversed_ray": V / max(Cc, 1), "tri_tests_per_traversed_ray": T / max(Cc, 1),
-                     "trace_ms_per_step": trace_ms_step, "trace_share_of_step": trace_ms_step / ms_single,
+                     "trace_ms_per_step": trace_ms_step, "trace_share_of_step": trace_ms_step / ms_single_one_lane,
                      "fp32_achieved_tflops": flops_step / max(world, 1) / (trace_ms_step / 1e3) / 1e12 if trace_ms_step > 0 else None,
                      "fp32_peak_tflops": 37.2, "fp32_frac": (flops_step / max(world, 1) / (trace_ms_step / 1e3) / 1e12 / 37.2) if trace_ms_step > 0 else None,
                      "fp32_note": "secondary bound of SURVEY.md 8(d): 148 SMs x 128 lanes x 1.965 GHz = 37.2 T lane-ops/s without FMA contraction (parity forbids it)",

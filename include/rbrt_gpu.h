@@ -19,8 +19,9 @@
  *   - one process, N GPUs:     rbrt_gpu_init_multi(devices, N, transport)
  *   - one process per GPU:     rbrt_gpu_init(device); rank 0: rbrt_gpu_comm_unique_id(id); every rank:
  *                              rbrt_gpu_comm_init_rank(id, rank, world)   (id travels over any side channel)
- * Under a communicator rbrt_gpu_scene_create uploads and builds the LBVH ONCE (rank 0) and replicates the scene's
- * device block to the other GPUs over NVLink (NCCL broadcast / peer copies); rbrt_gpu_render shards the image by
+ * Under a communicator rbrt_gpu_scene_create makes one replica of the scene per GPU — one process: built once, copied
+ * device to device over NVLink (NCCL broadcast / peer copies); process per GPU: built by every rank from its own arrays,
+ * or by rank 0 alone + ncclBroadcast (RBRT_SCENE_BROADCAST) — and rbrt_gpu_render shards the image by
  * interleaved 8x4-pixel tiles (or by sample range), every GPU finalises its own pixels and rank 0 gathers them.
  * The explicit building blocks (rbrt_render_opts.shard_*, rbrt_gpu_render_accum_device) remain for hosts that
  * place shards themselves.
@@ -124,12 +125,19 @@ enum {
                                     up to four renders can be in flight on four streams (rbrt_gpu_render_accum_device with
                                     stats = NULL returns without synchronising): the sparse last bounces of one frame then
                                     overlap the dense first bounces of the next */
-    RBRT_OPT_POOL_MASK = 24
+    RBRT_OPT_POOL_MASK = 24,
+    RBRT_OPT_SPLIT_BATCHES = 32  /* render the frame's samples as (at least) two batches on two internal lanes, so that the sparse, latency-bound
+                                    end of one batch runs under the dense start of the next: shortens a LONE frame (rbrt_gpu_render and
+                                    rbrt_gpu_render_hdr set it themselves).  Leave it off when several frames are in flight anyway. */
 };
 
 enum {
     RBRT_SCENE_LOCAL = 1,     /* under a communicator: build on THIS rank only, no replication (renders of it are not auto-sharded) */
-    RBRT_SCENE_NO_SAH = 2     /* skip the SAH pass over the LBVH (tree rotations during the refit): the plain Morton-order tree */
+    RBRT_SCENE_NO_SAH = 2,    /* skip the SAH pass over the LBVH (tree rotations during the refit): the plain Morton-order tree */
+    RBRT_SCENE_BROADCAST = 4  /* one process per GPU only: rank 0 alone uploads and builds, the other ranks receive the scene's device block by
+                                 ncclBroadcast (they may pass tri_vertices = NULL).  Default there: EVERY rank uploads and builds from its own
+                                 (identical) arrays — no rank waits for another, measured faster.  One process driving
+                                 several GPUs always builds once and copies device to device. */
 };
 typedef struct rbrt_scene_opts {
     uint32_t simd_lanes;     /* RBRT_LANES_*; 0 = 8 */

@@ -42,11 +42,13 @@ pub const RBRT_TRANSPORT_NCCL: c_int = 1;
 pub const RBRT_TRANSPORT_PEER: c_int = 2;
 pub const RBRT_SCENE_LOCAL: u32 = 1;
 pub const RBRT_SCENE_NO_SAH: u32 = 2;
+pub const RBRT_SCENE_BROADCAST: u32 = 4;
 pub const RBRT_OPT_COUNT_VISITS: u32 = 1;
 pub const RBRT_OPT_TIME_KERNELS: u32 = 2;
 pub const RBRT_OPT_NO_TAIL_KERNEL: u32 = 4;
 pub const RBRT_OPT_POOL_SHIFT: u32 = 3;    // flags |= slot << RBRT_OPT_POOL_SHIFT, slot in 0..4: the wavefront pool of a frame in flight
 pub const RBRT_OPT_POOL_MASK: u32 = 24;
+pub const RBRT_OPT_SPLIT_BATCHES: u32 = 32;
 
 extern "C" {
     pub fn rbrt_camera_new(position: RbrtVec3, look_at: RbrtVec3, up: RbrtVec3, img_height_pix: u32, img_width_pix: u32,

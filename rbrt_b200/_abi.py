@@ -108,10 +108,10 @@ HIT_DTYPE = [("kind", "<i4"), ("elem_idx", "<u4"), ("tri_idx", "<u4"), ("t", "<f
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 SHARD_NONE, SHARD_TILES, SHARD_SAMPLES = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE, TRACE_WAVEFRONT = 0, 1, 2
-SCENE_LOCAL, SCENE_NO_SAH = 1, 2
+SCENE_LOCAL, SCENE_NO_SAH, SCENE_BROADCAST = 1, 2, 4
 TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_PEER = 0, 1, 2
 COMM_ID_BYTES = 128
-OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL, OPT_POOL_SHIFT = 1, 2, 4, 3
+OPT_COUNT_VISITS, OPT_TIME_KERNELS, OPT_NO_TAIL_KERNEL, OPT_POOL_SHIFT, OPT_SPLIT_BATCHES = 1, 2, 4, 3, 32
 MAX_FRAMES = 4          # frames one wavefront batch can hold (rbrt_gpu_render_accum_device_frames)
 HIT_NONE, HIT_SPHERE, HIT_MESH, HIT_TRIANGLE = -1, 0, 1, 2
 ELEM_SPHERE, ELEM_TRIANGLE = 0, 1

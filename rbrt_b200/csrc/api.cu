@@ -127,8 +127,10 @@ int resolve_scene_info(const Scene& sc, bool wait) {
         m.info.num_bvh_nodes = live;
         float up = 0, bu = 0;
         if (m.t_up0 && cudaEventElapsedTime(&up, m.t_up0, m.t_up1) != cudaSuccess) { cudaGetLastError(); up = 0; }
-        if (m.t_b0 && cudaEventElapsedTime(&bu, m.t_b0, m.t_b1) != cudaSuccess) { cudaGetLastError(); bu = 0; }
-        m.info.ms_upload = up; m.info.ms_build = bu;                       // device times: H2D of the triangle soup / build kernels (+ replication)
+        // build = from the end of the uploads (the build stream waits for them) to the end of the build kernels
+        if (m.t_b0 && cudaEventElapsedTime(&bu, m.t_up1, m.t_b1) != cudaSuccess) { cudaGetLastError(); bu = 0; }
+        if (bu < 0) bu = 0;
+        m.info.ms_upload = up; m.info.ms_build = bu;                       // device times: H2D of the triangle soup / build kernels
         m.info_resolved = true;
     }
     if (m.build_error) { set_error("mesh %d: BVH deeper than the traversal stack allows (the mesh was left out of the scene)", m.build_error - 1); return RBRT_E_INVALID; }
@@ -235,7 +237,10 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
     int rc = ensure_device();
     if (rc) return rc;
     const bool collective = comm().active && comm().world > 1 && !(sflags & RBRT_SCENE_LOCAL);
-    const bool is_root = !collective || comm().rank == 0;                 // this process uploads and builds
+    // replicas: one process -> built once, copied device to device; process per GPU -> every rank builds its own (default) or
+    // rank 0 builds and broadcasts (RBRT_SCENE_BROADCAST)
+    const bool replicate = collective && (!comm().multi_process || (sflags & RBRT_SCENE_BROADCAST));
+    const bool is_root = !replicate || comm().rank == 0;                  // this process uploads and builds
     uint64_t total_tris = 0, total_eff = 0;
     for (uint32_t i = 0; i < nm; ++i) {
         if (meshes[i].material.kind > 2) { set_error("mesh %u: unknown material kind", i); return RBRT_E_INVALID; }
@@ -362,7 +367,7 @@ int rbrt_gpu_scene_create_elements(const rbrt_element_ref* order, uint32_t ne, c
         CKSC(cudaEventRecord(sc->t_up1, ctx.copy));
         CKSC(cudaEventRecord(sc->t_b1, ctx.build));
     }
-    if (collective) CKS(replicate_scene(sc, ctx.build));                  // replicas on the other GPUs (multi.cu): NCCL broadcast / peer copies, enqueued behind the build
+    if (replicate) CKS(replicate_scene(sc, ctx.build));                   // replicas on the other GPUs (multi.cu): NCCL broadcast / peer copies, enqueued behind the build
     else CKSC(cudaEventRecord(sc->rep[0].ready, ctx.build));
     // the per-mesh results: device -> pinned host, behind everything else on the build stream
     if (nm) CKSC(cudaMemcpyAsync(sc->res_h, base + sc->lay.result, sizeof(BuildResult) * nm, cudaMemcpyDeviceToHost, ctx.build));
@@ -464,21 +469,27 @@ static int render_host(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t
     LOCK;
     if (!scene || !cam) { set_error("null argument"); return RBRT_E_INVALID; }
     const Scene& sc = *reinterpret_cast<const Scene*>(scene);
-    const bool sharded = sc.collective && (!opts || opts->shard_count == 0);
+    rbrt_render_opts ro{}; if (opts) ro = *opts;
+    opts = &ro;
+    const bool sharded = sc.collective && opts->shard_count == 0;
+    {   // a lone, blocking frame with enough paths per GPU (measured: pays from ~2^26 on, costs a few % below): two lanes (render.cu)
+        const uint64_t share = (uint64_t)cam->img_width_pix * cam->img_height_pix * spp / (uint64_t)(sharded ? comm().world : (ro.shard_count > 1 ? ro.shard_count : 1));
+        if (!(ro.flags & RBRT_OPT_TIME_KERNELS) && share >= (1ull << 26)) ro.flags |= RBRT_OPT_SPLIT_BATCHES;
+    }
     const bool root = !sharded || comm().rank == 0;
     if (root && !rgb_out && !hdr_out) { set_error("null output"); return RBRT_E_INVALID; }
     CKA(cudaSetDevice(sc.device));
     double t0 = now_ms();
     size_t n = (size_t)cam->img_width_pix * cam->img_height_pix;
     if (!n || !spp) { set_error("empty image or zero samples"); return RBRT_E_INVALID; }
-    WaveBuffers& wb = device_wave_buffers(sc.device, opts ? (int)((opts->flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT) : 0);
+    WaveBuffers& wb = device_wave_buffers(sc.device, (int)((opts->flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT));
     if (wb.out_px < n) {
         cudaFree(wb.rgb); cudaFree(wb.hdr); wb.rgb = nullptr; wb.hdr = nullptr; wb.out_px = 0;
         CKA(cudaMalloc(&wb.rgb, 3 * n)); CKA(cudaMalloc(&wb.hdr, 12 * n)); wb.out_px = n;
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     rbrt_stats local; memset(&local, 0, sizeof(local));
-    const uint64_t seed = opts ? opts->seed : 0;
+    const uint64_t seed = opts->seed;
     uint8_t* rgb1[1] = {wb.rgb}; float* hdr1[1] = {wb.hdr};
     const bool want_rgb = rgb_out || (!root && !hdr_out), want_hdr = hdr_out != nullptr;    // every rank must make the same choice: see below
     int rc = render_frames(sc, cam, &seed, 1, spp, opts, want_rgb ? rgb1 : nullptr, want_hdr ? hdr1 : nullptr, 0, &local);

@@ -104,7 +104,7 @@ SceneDev make_scene_dev(char* base, const ArenaLayout& lay, uint32_t n_elems, ui
 // What a render left behind for its statistics (device counters, events); collect_stats() waits for the frame and reads them.
 struct RenderJob {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    WaveBuffers* wb = nullptr;
+    WaveBuffers* wb = nullptr, *wb2 = nullptr;   // wb2: the second lane's pool (RBRT_OPT_SPLIT_BATCHES)
     ShardDev sh{};
     uint32_t P = 0, n_frames = 0, W = 0, H = 0, launches = 0, iterations = 0, batch_iters = 0, flags = 0, max_depth = 0;
     bool rendered = false;

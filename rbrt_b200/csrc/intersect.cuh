@@ -241,14 +241,26 @@ __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
-template <class STK>
-__device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const RaySlabs& R, float t_prune, const STK& stack, int& sp) {
+// PF (experiment, off: -DRBRT_TAIL_PREFETCH turns it on in the tail kernel): as soon as the child references are there, the lines of ALL
+// internal children and of the first triangle of leaf children are prefetched, before the slab tests decide which one is visited next.
+// Measured SLOWER (tail kernel 1.3 -> 2.3 ms on a 1/8 shard of C3), see render.cu.
+template <bool PF, class STK>
+__device__ __forceinline__ int32_t bvh4_step(const uint4* __restrict__ nd, const uint4* __restrict__ nodes, const float4* __restrict__ tris_m,
+                                             const RaySlabs& R, float t_prune, const STK& stack, int& sp) {
 #ifndef RBRT_LDG128
     uint4 w0, w1, w2, w3;
     ldg256(nd, w0, w1); ldg256(nd + 2, w2, w3);
 #else
     const uint4 w0 = __ldg(nd), w1 = __ldg(nd + 1), w2 = __ldg(nd + 2), w3 = __ldg(nd + 3);
 #endif
+    if (PF) {
+        const int32_t cr[4] = {(int32_t)w3.x, (int32_t)w3.y, (int32_t)w3.z, (int32_t)w3.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const void* a = cr[k] >= 0 ? (const void*)(nodes + 4 * (size_t)cr[k]) : (const void*)(tris_m + 3 * (size_t)(((uint32_t)~cr[k]) >> 3));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
+        }
+    }
     const uint32_t fx = R.fx, fy = R.fy, fz = R.fz;
     float t[4]; int32_t r[4];
 #define RBRT_CHILD(k, X, Y, Z) { \
@@ -320,7 +332,7 @@ __device__ __forceinline__ void leaf_step_one(const float4* __restrict__ tris, u
 #define RBRT_VOTE_N 1      // node step iff  lanes at nodes * RBRT_VOTE_N >= lanes at leaves * RBRT_VOTE_L
 #define RBRT_VOTE_L 1
 #endif
-template <bool COUNT, class STK>
+template <bool COUNT, bool PF, class STK>
 __device__ __forceinline__ void traverse_voted(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t tri_base,
                                                const RaySlabs& R, f3 o, f3 d, float t_limit, const STK& stack, int& sp, int32_t& cur,
                                                float& best_t, uint32_t& best_idx, float& t_prune, int threshold,
@@ -331,7 +343,7 @@ __device__ __forceinline__ void traverse_voted(const uint4* __restrict__ nodes, 
         const int nn = __popc(__ballot_sync(0xFFFFFFFFu, at_node)), nl = __popc(__ballot_sync(0xFFFFFFFFu, at_leaf));
         if (nn + nl < threshold) break;
         if (nn * RBRT_VOTE_N >= nl * RBRT_VOTE_L) {
-            if (at_node) { cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp); if (COUNT) ++n_nodes; }
+            if (at_node) { cur = bvh4_step<PF>(nodes + 4 * (size_t)cur, nodes, tris + 3 * (size_t)tri_base, R, t_prune, stack, sp); if (COUNT) ++n_nodes; }
         } else if (at_leaf) {
             leaf_step_one(tris, tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, stack, sp);
             if (COUNT) ++n_tris;
@@ -354,7 +366,7 @@ __device__ __forceinline__ bool mesh_closest_bvh(const SceneDev& S, const MeshDe
     stack.put(sp++, RBRT_SENTINEL);
     uint32_t n_nodes = 0, n_tris = 0;
     while (cur != RBRT_SENTINEL) {
-        if (cur >= 0) { cur = bvh4_step(nodes + 4 * (size_t)cur, R, t_prune, stack, sp); ++n_nodes; }
+        if (cur >= 0) { cur = bvh4_step<false>(nodes + 4 * (size_t)cur, nodes, S.tris, R, t_prune, stack, sp); ++n_nodes; }
         else { leaf_step(S.tris, M.tri_base, cur, o, d, t_limit, best_t, best_idx, t_prune, n_tris); cur = stack.get(--sp); }
     }
     if (cnt) { cnt->nodes += n_nodes; cnt->tris += n_tris; }

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
         if (active == 0) { if (exhausted) break; continue; }
         const int threshold = exhausted ? 1 : min((int)P.fetch_thr, (int)quota);
         // ---- warp-voted traversal: one node visit or one triangle test per step, whichever more lanes wait for (intersect.cuh)
-        traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
+        traverse_voted<COUNT, false>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
     }
     if (COUNT) {
         for (int off = 16; off; off >>= 1) { n_nodes += __shfl_down_sync(FULL_MASK, n_nodes, off); n_tris += __shfl_down_sync(FULL_MASK, n_tris, off); }
@@ -694,7 +694,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         if (active == 0) { if (exhausted) break; continue; }
         const int threshold = exhausted ? 1 : min((int)P.tail_thr, (int)quota);
         // ---- (4) traversal, as k_trace
-        traverse_voted<COUNT>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
+#ifndef RBRT_TAIL_PREFETCH      // measured (profiles/r2_summary.md): prefetching the four children of every visited node into L1 makes the tail kernel SLOWER
+                                // (1/8 shard of C3: 1.3 -> 2.3 ms, full frame 2.9 -> 4.0 ms): it is not a pure latency chain, the extra L1TEX requests cost more
+        traverse_voted<COUNT, false>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
+#else
+        traverse_voted<COUNT, true>(nodes, P.S.tris, tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, threshold, n_nodes, n_tris);
+#endif
     }
     for (int off = 16; off; off >>= 1) { rays += __shfl_down_sync(FULL_MASK, rays, off); nan_count += __shfl_down_sync(FULL_MASK, nan_count, off); }
     if (lane == 0) {
@@ -874,12 +879,31 @@ static CamDev make_cam(const rbrt_camera& c) {
     return d;
 }
 
-static WaveBuffers g_wave[4][64];                                       // [pool][device]; pools 1..3 = RBRT_OPT_POOL_* (more frames in flight)
-WaveBuffers& device_wave_buffers(int device, int pool) { return g_wave[pool & 3][(device >= 0 && device < 64) ? device : 0]; }
+static WaveBuffers g_wave[8][64];                                       // [pool][device]; pools 1..3 = RBRT_OPT_POOL_* (more frames in flight);
+                                                                        // 4..7 = the second lane of pools 0..3 (RBRT_OPT_SPLIT_BATCHES)
+WaveBuffers& device_wave_buffers(int device, int pool) { return g_wave[pool & 7][(device >= 0 && device < 64) ? device : 0]; }
+// Second lane of a pool: its own stream and the events that order the two lanes of one frame
+struct SplitLane { cudaStream_t aux = nullptr; cudaEvent_t fork = nullptr, acc[2] = {nullptr, nullptr}, join = nullptr; };
+static SplitLane g_lane[4][64];
+static int ensure_lane(SplitLane& L) {
+    if (L.aux) return RBRT_OK;
+    cudaError_t e = cudaStreamCreateWithFlags(&L.aux, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&L.fork, &L.acc[0], &L.acc[1], &L.join}) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_fail(e, "split lane");
+    return RBRT_OK;
+}
 void release_device_wave_buffers() {
     int cur = 0; cudaGetDevice(&cur);
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 8; ++p)
         for (int d = 0; d < 64; ++d) if (g_wave[p][d].cap || g_wave[p][d].accum || g_wave[p][d].rgb) { cudaSetDevice(d); free_wave_buffers(g_wave[p][d]); }
+    for (int p = 0; p < 4; ++p)
+        for (int d = 0; d < 64; ++d) {
+            SplitLane& L = g_lane[p][d];
+            if (!L.aux) continue;
+            cudaSetDevice(d); cudaStreamSynchronize(L.aux); cudaStreamDestroy(L.aux);
+            for (cudaEvent_t ev : {L.fork, L.acc[0], L.acc[1], L.join}) if (ev) cudaEventDestroy(ev);
+            L = SplitLane();
+        }
     cudaSetDevice(cur);
 }
 
@@ -971,7 +995,19 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
     wait_scene_ready(sc, li, st);                                         // the scene's build / replication is asynchronous
     for (uint32_t f = 0; f < n_frames; ++f) CKR(cudaMemsetAsync(d_accum[f], 0, 16ull * W * H, st));
     uint32_t launches = 0, iterations = 0, batch_iters = 0;
-    WaveBuffers& wb = device_wave_buffers(rp.device, (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT));
+    const int pool = (int)((o.flags & RBRT_OPT_POOL_MASK) >> RBRT_OPT_POOL_SHIFT);
+    // TWO LANES (RBRT_OPT_SPLIT_BATCHES).  A batch ends sparsely: its last bounce iterations and the tail kernel are latency chains
+    // that leave most SMs idle (1/8 shard of C3: ~2.3 of 6.3 ms), and for a LONE frame no other frame is there to fill them.  So the
+    // frame's samples are cut into at least two batches that alternate between two lanes — the caller's stream with pool p, an
+    // internal stream with pool 4 + p — and the dense start of one batch runs under the sparse end of the previous one.  The
+    // per-pixel sums keep their sample order: a batch's k_accumulate waits (event) for the previous batch's.
+    const bool split = (o.flags & RBRT_OPT_SPLIT_BATCHES) && !(o.flags & RBRT_OPT_TIME_KERNELS) && sh.s1 - sh.s0 >= 2;
+    WaveBuffers* wbs[2] = {&device_wave_buffers(rp.device, pool), split ? &device_wave_buffers(rp.device, 4 + pool) : nullptr};
+    WaveBuffers& wb = *wbs[0];
+    SplitLane& SL = g_lane[pool][rp.device & 63];
+    if (split) { int rc_l = ensure_lane(SL); if (rc_l) return rc_l; }
+    cudaStream_t lane_st[2] = {st, split ? SL.aux : st};
+    uint32_t lane_iters[2] = {0, 0};
     CKR(cudaEventRecord(ev0, st));
     if (P && sh.s1 > sh.s0) {
         // Paths in flight per batch.  Every bounce iteration is one trace + one shade launch whose duration is
@@ -983,45 +1019,56 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
         if (PF > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
         const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
         const uint64_t limit_paths = pool_limit_bytes() ? std::max<uint64_t>(pool_limit_bytes() / per_path, 1) : ~0ull;   // rbrt_gpu_set_pool_limit
+        const uint32_t S_all = sh.s1 - sh.s0, S_half = (S_all + 1) / 2;
         if (!target) {
-            const uint64_t want = std::min<uint64_t>(std::min<uint64_t>((uint64_t)(sh.s1 - sh.s0) * PF, 1ull << 27), limit_paths);
+            const uint64_t want = std::min<uint64_t>(std::min<uint64_t>((uint64_t)(split ? S_half : S_all) * PF, 1ull << 27), limit_paths);
             const uint64_t want_sb = std::max<uint64_t>(want / PF, 1);                      // whole samples per batch
-            if (wb.cap >= want_sb * PF && wb.depth_cap >= max_depth) target = (uint32_t)want;  // the pool already holds it: no driver query
-                                                                                            // (cudaMemGetInfo takes tens of ms at times)
+            bool have = true;
+            for (int l = 0; l < (split ? 2 : 1); ++l) have = have && wbs[l]->cap >= want_sb * PF && wbs[l]->depth_cap >= max_depth;
+            if (have) target = (uint32_t)want;                            // the pools already hold it: no driver query (cudaMemGetInfo takes tens of ms at times)
             else {
                 size_t free_b = 0, total_b = 0;
                 CKR(cudaMemGetInfo(&free_b, &total_b));
-                free_b += wb.bytes;                                       // what a re-allocation would release first
-                uint64_t fit = (free_b / 2) / per_path;
+                free_b += wb.bytes + (split ? wbs[1]->bytes : 0);         // what a re-allocation would release first
+                uint64_t fit = (free_b / 2) / per_path / (split ? 2 : 1);
                 target = (uint32_t)(fit < (1ull << 21) ? (1ull << 21) : (fit > (1ull << 27) ? (1ull << 27) : fit));
             }
         }
         if ((uint64_t)target > limit_paths) target = (uint32_t)limit_paths;
-        uint64_t S_b64 = (uint64_t)target / PF; if (S_b64 < 1) S_b64 = 1; if (S_b64 > sh.s1 - sh.s0) S_b64 = sh.s1 - sh.s0;
+        uint64_t S_b64 = (uint64_t)target / PF; if (S_b64 < 1) S_b64 = 1; if (S_b64 > S_all) S_b64 = S_all;
+        if (split && S_b64 > S_half) S_b64 = S_half;                      // at least two batches, one per lane
         if (S_b64 * PF > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
         const uint32_t S_b = (uint32_t)S_b64;
         const uint32_t cap = (uint32_t)(S_b64 * PF);
-        int rc = ensure_wave_buffers(wb, cap, max_depth);
-        if (rc) return rc;
-        CKR(cudaMemsetAsync(wb.stats, 0, 8 * ST_COUNT, st));
-        WaveParams wp;
-        wp.S = rp.dev; wp.sh = sh; wp.n_frames = n_frames;
-        for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) {
-            const uint32_t g = f < n_frames ? f : 0;
-            const uint64_t seed = seeds ? seeds[g] : o.seed;
-            wp.cam[f] = make_cam(cams[g]); wp.key0[f] = (uint32_t)seed; wp.key1[f] = (uint32_t)(seed >> 32);
+        WaveParams wps[2];
+        for (int l = 0; l < (split ? 2 : 1); ++l) {
+            WaveBuffers& w = *wbs[l];
+            int rc = ensure_wave_buffers(w, cap, max_depth);
+            if (rc) return rc;
+            WaveParams& wp = wps[l];
+            wp.S = rp.dev; wp.sh = sh; wp.n_frames = n_frames;
+            for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) {
+                const uint32_t g = f < n_frames ? f : 0;
+                const uint64_t seed = seeds ? seeds[g] : o.seed;
+                wp.cam[f] = make_cam(cams[g]); wp.key0[f] = (uint32_t)seed; wp.key1[f] = (uint32_t)(seed >> 32);
+            }
+            wp.cap = w.cap; wp.paths_px = P; wp.fd_paths_px = make_fastdiv(P); wp.max_depth = max_depth;
+            static const bool no_cull_env = getenv("RBRT_NO_PRIMARY_CULL") != nullptr;      // tuning / A-B knob
+            wp.use_cull = no_cull_env ? 0u : 1u;
+            const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
+            wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
+            const char* tthr_env = getenv("RBRT_TAIL_FETCH_THRESHOLD");
+            wp.tail_thr = tthr_env ? (uint32_t)std::min(32, std::max(1, atoi(tthr_env))) : TAIL_FETCH_THRESHOLD;
+            wp.rec = w.rec; wp.candq = w.candq;
+            for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = w.matq[i / 3][i % 3];
+            wp.out = w.out; wp.hist = w.hist; wp.ctr = w.ctr; wp.stats = w.stats;
         }
         AccumPtrs ap; for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) ap.p[f] = d_accum[f < n_frames ? f : 0];
-        wp.cap = wb.cap; wp.paths_px = P; wp.fd_paths_px = make_fastdiv(P); wp.max_depth = max_depth;
-        static const bool no_cull_env = getenv("RBRT_NO_PRIMARY_CULL") != nullptr;      // tuning / A-B knob
-        wp.use_cull = no_cull_env ? 0u : 1u;
-        const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
-        wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
-        const char* tthr_env = getenv("RBRT_TAIL_FETCH_THRESHOLD");
-        wp.tail_thr = tthr_env ? (uint32_t)std::min(32, std::max(1, atoi(tthr_env))) : TAIL_FETCH_THRESHOLD;
-        wp.rec = wb.rec; wp.candq = wb.candq;
-        for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
-        wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
+        if (split) {                                                      // fork: the second lane starts behind the caller's stream (scene ready, accumulators cleared)
+            CKR(cudaEventRecord(SL.fork, st));
+            CKR(cudaStreamWaitEvent(SL.aux, SL.fork, 0));
+        }
+        for (int l = 0; l < (split ? 2 : 1); ++l) CKR(cudaMemsetAsync(wbs[l]->stats, 0, 8 * ST_COUNT, lane_st[l]));
         const int sm_count = rp.sm_count;
         const int grid = sm_count * 8;                                     // producers / brute: 256-thread blocks
         int per_sm = 0;                                                   // k_trace: persistent blocks, exactly one resident wave
@@ -1042,16 +1089,32 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
         const bool et = rp.dev.n_etris > 0;                               // BasicTriangle elements present: the ET kernel instantiations
         const bool count = (o.flags & RBRT_OPT_COUNT_VISITS) != 0;
         const bool time_kernels = (o.flags & RBRT_OPT_TIME_KERNELS) != 0;      // bracket every trace launch with events -> stats.ms_trace
+        // The launch sequence of a batch is fixed on the host, but how fast its rays die out is only known on the device: the hand-over
+        // to the tail kernel becomes unconditional at iteration `force_it`, where the sequence ends.  Rays roughly halve per bounce, so
+        // the threshold (2^18 rays) is expected near log2(paths / 2^18); two iterations of slack, at most TAIL_FORCE_IT.  (A 1/8 shard
+        // of C3 hands over at iteration 6; with the fixed 12 it then ran 18 launches that found the "tail done" flag and returned.)
+        uint32_t force_it = TAIL_FORCE_IT;
+        {
+            const char* fenv = getenv("RBRT_TAIL_FORCE_IT");               // tuning knob
+            uint32_t lg = 0; while (lg < 31 && ((uint64_t)cap >> lg) > (1ull << 18)) ++lg;
+            const uint32_t guess = lg + 2 < 2 ? 2 : lg + 2;
+            force_it = fenv ? (uint32_t)std::max(1, atoi(fenv)) : std::min<uint32_t>(TAIL_FORCE_IT, guess);
+            if (brute) force_it = TAIL_FORCE_IT;
+        }
         size_t ev_used = 0;
         auto next_event = [&]() -> cudaEvent_t {
             if (ev_used == wb.ev.size()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); wb.ev.push_back(e); }
             return wb.ev[ev_used++];
         };
-        for (uint32_t s_base = sh.s0; s_base < sh.s1; s_base += S_b) {
+        uint32_t batch_no = 0;
+        for (uint32_t s_base = sh.s0; s_base < sh.s1; s_base += S_b, ++batch_no) {
+            const int l = split ? (int)(batch_no & 1u) : 0;
+            WaveParams& wp = wps[l];
+            cudaStream_t bs = lane_st[l];
             wp.s_base = s_base; wp.s_count = (sh.s1 - s_base < S_b) ? sh.s1 - s_base : S_b;
             wp.fd_s_count = make_fastdiv(wp.s_count);
-            CKR(cudaMemsetAsync(wb.ctr, 0, sizeof(IterCtr) * (max_depth + 2), st));
-            if (et) k_generate<true><<<grid, 256, 0, st>>>(wp); else k_generate<false><<<grid, 256, 0, st>>>(wp);
+            CKR(cudaMemsetAsync(wbs[l]->ctr, 0, sizeof(IterCtr) * (max_depth + 2), bs));
+            if (et) k_generate<true><<<grid, 256, 0, bs>>>(wp); else k_generate<false><<<grid, 256, 0, bs>>>(wp);
             ++launches;
             batch_iters = 0;
             // A scene without mesh triangles (C1) has nothing to traverse: every closest-hit query is resolved by stage A inside the
@@ -1060,34 +1123,38 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
             const bool no_mesh = sc.info.num_triangles_tested == 0;
             for (uint32_t it = 0; it <= max_depth; ++it) {
                 if ((it >= 1 || no_mesh) && tail_rays) {                   // see k_finish / k_tail
-                    // From iteration TAIL_FORCE_IT on the hand-over is unconditional, so the launch sequence ends there:
-                    // ~40 launches per batch instead of 155 (an empty iteration still costs three launches).
-                    const bool force = it >= TAIL_FORCE_IT || no_mesh;
+                    const bool force = it >= force_it || no_mesh;
                     const uint32_t lim = force ? 0xFFFFFFFFu : tail_rays;
                     if (brute) {
-                        if (et) { if (count) k_finish<true, true, true><<<grid_fin, 256, 0, st>>>(wp, it, lim); else k_finish<true, false, true><<<grid_fin, 256, 0, st>>>(wp, it, lim); }
-                        else { if (count) k_finish<true, true, false><<<grid_fin, 256, 0, st>>>(wp, it, lim); else k_finish<true, false, false><<<grid_fin, 256, 0, st>>>(wp, it, lim); }
-                    } else if (et) { if (count) k_tail<true, true><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); else k_tail<false, true><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); }
-                    else { if (count) k_tail<true, false><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); else k_tail<false, false><<<grid_tail, TAIL_THREADS, 0, st>>>(wp, it, lim); }
+                        if (et) { if (count) k_finish<true, true, true><<<grid_fin, 256, 0, bs>>>(wp, it, lim); else k_finish<true, false, true><<<grid_fin, 256, 0, bs>>>(wp, it, lim); }
+                        else { if (count) k_finish<true, true, false><<<grid_fin, 256, 0, bs>>>(wp, it, lim); else k_finish<true, false, false><<<grid_fin, 256, 0, bs>>>(wp, it, lim); }
+                    } else if (et) { if (count) k_tail<true, true><<<grid_tail, TAIL_THREADS, 0, bs>>>(wp, it, lim); else k_tail<false, true><<<grid_tail, TAIL_THREADS, 0, bs>>>(wp, it, lim); }
+                    else { if (count) k_tail<true, false><<<grid_tail, TAIL_THREADS, 0, bs>>>(wp, it, lim); else k_tail<false, false><<<grid_tail, TAIL_THREADS, 0, bs>>>(wp, it, lim); }
                     ++launches;
                     if (force) break;
                 }
-                if (time_kernels) CKR(cudaEventRecord(next_event(), st));
-                if (brute) { if (count) k_trace_brute<true><<<grid, 256, 0, st>>>(wp, it); else k_trace_brute<false><<<grid, 256, 0, st>>>(wp, it); }
-                else if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
-                else k_trace<false><<<grid_trace, TRACE_THREADS, 0, st>>>(wp, it);
-                ++launches; ++iterations; ++batch_iters;
-                if (time_kernels) CKR(cudaEventRecord(next_event(), st));
-                if (it < max_depth) { if (et) k_shade<true><<<grid, 256, 0, st>>>(wp, it); else k_shade<false><<<grid, 256, 0, st>>>(wp, it); ++launches; }
+                if (time_kernels) CKR(cudaEventRecord(next_event(), bs));
+                if (brute) { if (count) k_trace_brute<true><<<grid, 256, 0, bs>>>(wp, it); else k_trace_brute<false><<<grid, 256, 0, bs>>>(wp, it); }
+                else if (count) k_trace<true><<<grid_trace, TRACE_THREADS, 0, bs>>>(wp, it);
+                else k_trace<false><<<grid_trace, TRACE_THREADS, 0, bs>>>(wp, it);
+                ++launches; ++iterations; ++batch_iters; ++lane_iters[l];
+                if (time_kernels) CKR(cudaEventRecord(next_event(), bs));
+                if (it < max_depth) { if (et) k_shade<true><<<grid, 256, 0, bs>>>(wp, it); else k_shade<false><<<grid, 256, 0, bs>>>(wp, it); ++launches; }
             }
-            k_accumulate<<<dim3((P + 255) / 256, n_frames), 256, 0, st>>>(wp, ap); ++launches;
-            k_sum_rays<<<1, 64, 0, st>>>(wp); ++launches;
+            if (split && batch_no > 0) CKR(cudaStreamWaitEvent(bs, SL.acc[l ^ 1], 0));   // sample order: after the previous batch's accumulate (other lane)
+            k_accumulate<<<dim3((P + 255) / 256, n_frames), 256, 0, bs>>>(wp, ap); ++launches;
+            if (split) CKR(cudaEventRecord(SL.acc[l], bs));
+            k_sum_rays<<<1, 64, 0, bs>>>(wp); ++launches;
             CKR(cudaGetLastError());
+        }
+        if (split) {                                                      // join: the caller's stream continues behind the second lane
+            CKR(cudaEventRecord(SL.join, SL.aux));
+            CKR(cudaStreamWaitEvent(st, SL.join, 0));
         }
     }
     CKR(cudaEventRecord(ev1, st));
     note_scene_use(sc, rp.device, st);
-    job.wb = &wb; job.sh = sh; job.P = P; job.n_frames = n_frames; job.W = W; job.H = H; job.launches = launches; job.iterations = iterations;
+    job.wb = &wb; job.wb2 = split ? wbs[1] : nullptr; job.sh = sh; job.P = P; job.n_frames = n_frames; job.W = W; job.H = H; job.launches = launches; job.iterations = iterations;
     job.batch_iters = batch_iters; job.flags = o.flags; job.max_depth = max_depth; job.rendered = P && sh.s1 > sh.s0;
     if (stats && !job_out) return collect_stats(job, stats);
     return RBRT_OK;
@@ -1103,6 +1170,11 @@ int collect_stats(RenderJob& job, rbrt_stats* stats) {
         float ms = 0; CKR(cudaEventElapsedTime(&ms, ev0, ev1));
         unsigned long long h[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (wb.stats && job.rendered) CKR(cudaMemcpy(h, wb.stats, sizeof(h), cudaMemcpyDeviceToHost));
+        if (job.wb2 && job.wb2->stats && job.rendered) {                  // second lane (RBRT_OPT_SPLIT_BATCHES)
+            unsigned long long h2[ST_COUNT];
+            CKR(cudaMemcpy(h2, job.wb2->stats, sizeof(h2), cudaMemcpyDeviceToHost));
+            for (int k = 0; k < ST_COUNT; ++k) h[k] += h2[k];
+        }
         stats->rays = h[ST_RAYS]; stats->nan_rays = h[ST_NAN]; stats->node_visits = h[ST_NODES]; stats->tri_tests = h[ST_TRIS] + h[ST_TAIL_TRIS]; stats->traversed_rays = h[ST_CAND] + h[ST_TAIL_CAND];
         stats->node_visits += h[ST_TAIL_NODES];
         stats->tail_node_visits = h[ST_TAIL_NODES]; stats->tail_tri_tests = h[ST_TAIL_TRIS]; stats->tail_traversed_rays = h[ST_TAIL_CAND];

@@ -102,6 +102,8 @@ class FramePipeline:
         """Enqueue one group of frames (render -> finalise -> [gather on rank 0] -> [copy to pinned host memory]) on the slot's stream."""
         torch = self._torch
         opts.setdefault("shard_mode", self.shard_mode if self.world > 1 else _abi.SHARD_NONE)
+        if self.depth == 1:
+            opts.setdefault("split", True)                    # one group at a time: let the library overlap the group's own batches (two lanes)
         o = make_opts(pool=self._n % self.depth, **opts)    # shard_count 0 (default): the library shards over its communicator
         handle = scene.handle() if hasattr(scene, "handle") else scene
         nf = len(frames)

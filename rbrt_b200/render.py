@@ -42,11 +42,12 @@ class ImageBuffer:
 
 
 def make_opts(seed=0, max_depth=0, trace_mode=_abi.TRACE_BVH, shard_mode=_abi.SHARD_NONE, shard_rank=0, shard_count=0,
-              batch_paths=0, integrator=0, count_visits=False, time_kernels=False, no_tail_kernel=False, pool=0):
+              batch_paths=0, integrator=0, count_visits=False, time_kernels=False, no_tail_kernel=False, pool=0, split=False):
     return _abi.RenderOptsC(int(seed) & 0xFFFFFFFFFFFFFFFF, max_depth, trace_mode, shard_mode, shard_rank, shard_count,
                             batch_paths, integrator,
                             (_abi.OPT_COUNT_VISITS if count_visits else 0) | (_abi.OPT_TIME_KERNELS if time_kernels else 0)
-                            | (_abi.OPT_NO_TAIL_KERNEL if no_tail_kernel else 0) | ((int(pool) & 3) << _abi.OPT_POOL_SHIFT))
+                            | (_abi.OPT_NO_TAIL_KERNEL if no_tail_kernel else 0) | ((int(pool) & 3) << _abi.OPT_POOL_SHIFT)
+                            | (_abi.OPT_SPLIT_BATCHES if split else 0))
 
 
 def render_scene(cam, num_samples, scene, stats=None, **opts):

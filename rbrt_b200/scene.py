@@ -24,12 +24,12 @@ def element_arrays(elements):
 
 
 class Scene:
-    def __init__(self, elements=None, triangle_meshes=None, lights=None, simd_lanes=8, leaf_size=0, box_pad_rel=0.0, local=False, sah=True):
+    def __init__(self, elements=None, triangle_meshes=None, lights=None, simd_lanes=8, leaf_size=0, box_pad_rel=0.0, local=False, sah=True, broadcast=False):
         self.elements = list(elements or [])
         self.triangle_meshes = list(triangle_meshes or [])
         self.lights = list(lights or [])
         self.simd_lanes, self.leaf_size, self.box_pad_rel = simd_lanes, leaf_size, box_pad_rel
-        self.local, self.sah = local, sah     # RBRT_SCENE_LOCAL (no replication under a communicator), RBRT_SCENE_NO_SAH
+        self.local, self.sah, self.broadcast = local, sah, broadcast     # RBRT_SCENE_LOCAL / RBRT_SCENE_NO_SAH / RBRT_SCENE_BROADCAST
         self._handle = None
 
     # ---- GPU handle -----------------------------------------------------------------------
@@ -40,7 +40,8 @@ class Scene:
             nm = len(self.triangle_meshes)
             meshes = (_abi.MeshDescC * max(nm, 1))(*[m.to_c() for m in self.triangle_meshes])
             opts = _abi.SceneOptsC(self.simd_lanes, self.leaf_size, self.box_pad_rel,
-                                   (_abi.SCENE_LOCAL if self.local else 0) | (0 if self.sah else _abi.SCENE_NO_SAH))
+                                   (_abi.SCENE_LOCAL if self.local else 0) | (0 if self.sah else _abi.SCENE_NO_SAH)
+                                   | (_abi.SCENE_BROADCAST if self.broadcast else 0))
             h = C.c_void_p()
             _abi.check(lib.rbrt_gpu_scene_create_elements(order, ne, spheres, ns, tris, nt, meshes, nm, opts, C.byref(h)))
             self._handle = h

@@ -33,6 +33,15 @@ for shard in (1, 8):
         if rep >= 2:
             ms.append(st["ms_device"]); trc.append(st["ms_trace"])
     out[f"ms_frame_{shard}"] = round(float(np.mean(ms)), 3); out[f"ms_trace_{shard}"] = round(float(np.mean(trc)), 3)
+    ms = []
+    for rep in range(5):                                       # the same frame on two lanes (RBRT_OPT_SPLIT_BATCHES, what rbrt_gpu_render does)
+        st = {}
+        img = R.render_scene_hdr(cam, spp, scene, stats=st, seed=1, **kw)
+        if rep >= 2:
+            ms.append(st["ms_device"])
+    out[f"ms_split_{shard}"] = round(float(np.mean(ms)), 3)
+    if shard == 1:
+        out["split_identical"] = bool(np.array_equal(img.view(np.uint32), img0.view(np.uint32)))
 out["launches"] = st["launches"]
 out["checksum"] = int(np.ascontiguousarray(img0).view(np.uint32).astype(np.uint64).sum())
 print(json.dumps(out))

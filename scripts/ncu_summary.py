@@ -27,7 +27,7 @@ def load(path):
     launches = {}
     for r in rows:
         k = int(r["ID"])
-        d = launches.setdefault(k, {"kernel": r["Kernel Name"]})
+        d = launches.setdefault(k, {"kernel": re.sub(r"^void ", "", r["Kernel Name"])})
         d[r["Metric Name"]] = to_float(r["Metric Value"], r["Metric Unit"])
     return [launches[k] for k in sorted(launches)]
 
