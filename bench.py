@@ -406,10 +406,11 @@ def run_gpu(args):
     rgb_ref = rgb.clone() if rank == 0 else None
     # the lone frame as rbrt_gpu_render issues it: its sample batches on two lanes (RBRT_OPT_SPLIT_BATCHES), so that the sparse end of
     # one batch runs under the dense start of the next
+    use_split = (W * H * spp) // world >= (1 << 26)          # rbrt_gpu_render's own rule: two lanes from 2^26 paths per GPU
     single_ms = []
     for k in range(3 + n_single):
         e0.record(stream)
-        step_single(dict(split=True), _abi.StatsC())
+        step_single(dict(split=use_split), _abi.StatsC())
         e1.record(stream)
         barrier()
         if k >= 3:
@@ -424,7 +425,9 @@ def run_gpu(args):
     #      streams and wavefront pools, `frames_per_batch` frames per group — THE SAME at every N (a rank's launches on 8 GPUs
     #      then have about the size they have on one GPU with one frame).  The K-step region is repeated until >= ~0.6 s have been
     #      timed, each repeat bracketed by barrier + synchronize; the MEDIAN region is reported.
-    fpb = args.frames_per_batch or (1 if args.workload in SAMPLE_SHARDED else 4)
+    # 4 frames per batch at every N — unless ONE frame of the workload already fills a wavefront pool (2^27 paths: C4, C5), where
+    # batching frames only cuts each frame's samples into more, smaller batches (measured on C4: 59.1 ms with 4, 52.0 with 1)
+    fpb = args.frames_per_batch or (1 if (args.workload in SAMPLE_SHARDED or W * H * spp > (1 << 27)) else 4)
 
     def timed_pipeline(fpb_, budget_s):
         pipe = R.FramePipeline(W, H, depth=args.frames_in_flight, host_output=False, shard_mode=shard_mode, frames_per_batch=fpb_)
@@ -619,9 +622,9 @@ def run_gpu(args):
         "timed_region": {"repeats": len(regions), "steps_per_repeat": args.steps, "ms_median": ms, "ms_min": ms_min, "ms_max": ms_max,
                          "note": "the K-step region (barrier + synchronize on both sides, CUDA events, max over ranks) is repeated; value uses the median region"},
         "single_frame": {"ms_per_step": ms_single, "value": rays / args.steps / (ms_single / 1e3) / 1e6, "unit": "Mrays/s",
-                         "ms_per_step_one_lane": ms_single_one_lane,
+                         "ms_per_step_one_lane": ms_single_one_lane, "two_lanes": bool(use_split),
                          "note": "one frame at a time, host waits for each (latency of a lone render_scene call, gather on rank 0 included), the frame's "
-                                 "sample batches on two lanes as rbrt_gpu_render issues them (RBRT_OPT_SPLIT_BATCHES; one lane: ms_per_step_one_lane); `value` "
+                                 "sample batches on two lanes when it has >= 2^26 paths per GPU, as rbrt_gpu_render issues it (RBRT_OPT_SPLIT_BATCHES; one lane: ms_per_step_one_lane); `value` "
                                  "keeps `frames_in_flight` groups of `frames_per_batch` frames in flight on separate streams"},
         "frames_per_batch_1": ({"ms_per_step": ms_fpb1 / args.steps, "value": rays / (ms_fpb1 / 1e3) / 1e6, "unit": "Mrays/s"} if regions1 else None),
         "samples_per_s": paths / (ms / 1e3), "rays_per_step": rays / args.steps, "rays_per_sample": rays / max(paths, 1),

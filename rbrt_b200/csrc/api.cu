@@ -434,6 +434,7 @@ int rbrt_gpu_render_accum_device_frames(const rbrt_scene* scene, const rbrt_came
 int rbrt_gpu_release_cache(void) {
     LOCK;
     release_device_wave_buffers();
+    release_dist_buffers();
     release_build_scratch();
     arena_release_all();
     return RBRT_OK;

@@ -134,7 +134,7 @@ __device__ __forceinline__ float box_area(const BoxH& b) {
 }
 
 template <bool ROT>
-__global__ void k_refit(int n, int2* children, int* parent_int,
+__global__ void k_refit(int n, int rot_min_leaves, const int2* __restrict__ range, int2* children, int* parent_int,
                         int* parent_leaf, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                         float4* node_lo, float4* node_hi, int* __restrict__ flags, int* height) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,7 +148,9 @@ __global__ void k_refit(int n, int2* children, int* parent_int,
         __threadfence();
         int c0 = vch[2 * cur], c1 = vch[2 * cur + 1];
         BoxH b0 = load_box(c0, leaf_lo, leaf_hi, nl, nh, vh), b1 = load_box(c1, leaf_lo, leaf_hi, nl, nh, vh);
-        if (ROT) {
+        // (only where the node covers at least rot_min_leaves triangles — a node's own leaf set is invariant under rotations below it:
+        //  the bottom levels hold most of the nodes, i.e. most of the pass's cost, but few of the levels a ray descends through)
+        if (ROT && range[cur].y - range[cur].x + 1 >= rot_min_leaves) {
             float best = 0.0f; int bside = -1, bwhich = 0; BoxH bnew = b0;
 #pragma unroll
             for (int side = 0; side < 2; ++side) {                         // X = the child that is rebuilt, Y = the other child, moved down
@@ -202,64 +204,73 @@ __device__ __forceinline__ uint32_t quant_hi(float v, float org, float step) {
 // queue IS its output slot); every launch handles one BFS level [begin, end) and appends the internal children it
 // keeps to the tail.  A binary node's two children are expanded greedily — largest surface area first — until there
 // are four (subtrees of <= leaf_size triangles count as leaves and are never expanded).
-struct CollapseState { uint32_t begin[2], end[2], tail, done, depth, pad; };
+struct CollapseState { uint32_t begin[2], end[2], tail, done, depth, base_level; };
 
 __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
     float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
     return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void k_collapse4(uint32_t level, uint32_t leaf_size, const BuildParams* __restrict__ bp, const int2* __restrict__ children, const int2* __restrict__ range,
+__device__ __forceinline__ void collapse_node(uint32_t j, uint32_t leaf_size, const QGrid& g, const int2* __restrict__ children, const int2* __restrict__ range,
+                                              const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                              const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                                              uint32_t* queue, CollapseState* st, uint4* __restrict__ out) {
+    const int i = (int)queue[j];
+    int src[4]; int32_t ref[4]; int nc = 2;
+    auto effective = [&](int c, int k) {                                   // binary child -> (source of its box, traversal ref)
+        src[k] = c;
+        if (c < 0) { ref[k] = make_leaf_ref((uint32_t)(~c), 1); return; }
+        int2 r = range[c];
+        uint32_t cnt = (uint32_t)(r.y - r.x + 1);
+        ref[k] = cnt <= leaf_size ? make_leaf_ref((uint32_t)r.x, cnt) : c;
+    };
+    int2 ch = children[i];
+    effective(ch.x, 0); effective(ch.y, 1);
+    for (int round = 0; round < 2; ++round) {
+        int best = -1; float best_a = -1.0f;
+        for (int k = 0; k < nc; ++k)
+            if (ref[k] >= 0) { float a = half_area(node_lo[src[k]], node_hi[src[k]]); if (a > best_a) { best_a = a; best = k; } }
+        if (best < 0) break;
+        int2 c2 = children[src[best]];
+        effective(c2.x, best); effective(c2.y, nc); ++nc;
+    }
+    uint32_t q[4][3]; int32_t refs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nc) {
+            float4 lo, hi;
+            if (src[k] < 0) { lo = leaf_lo[~src[k]]; hi = leaf_hi[~src[k]]; } else { lo = node_lo[src[k]]; hi = node_hi[src[k]]; }
+            q[k][0] = quant_lo(lo.x, g.org[0], g.step[0]) | (quant_hi(hi.x, g.org[0], g.step[0]) << 16);
+            q[k][1] = quant_lo(lo.y, g.org[1], g.step[1]) | (quant_hi(hi.y, g.org[1], g.step[1]) << 16);
+            q[k][2] = quant_lo(lo.z, g.org[2], g.step[2]) | (quant_hi(hi.z, g.org[2], g.step[2]) << 16);
+            if (ref[k] >= 0) { uint32_t pos = atomicAdd(&st->tail, 1u); queue[pos] = (uint32_t)src[k]; refs[k] = (int32_t)pos; }
+            else refs[k] = ref[k];
+        } else {                                                           // unused slot: inverted box (lo 65535, hi 0), never hit
+            q[k][0] = q[k][1] = q[k][2] = 0x0000FFFFu;
+            refs[k] = make_leaf_ref(0, 1);
+        }
+    }
+    out[4 * (size_t)j] = make_uint4(q[0][0], q[0][1], q[0][2], q[1][0]);
+    out[4 * (size_t)j + 1] = make_uint4(q[1][1], q[1][2], q[2][0], q[2][1]);
+    out[4 * (size_t)j + 2] = make_uint4(q[2][2], q[3][0], q[3][1], q[3][2]);
+    out[4 * (size_t)j + 3] = make_uint4((uint32_t)refs[0], (uint32_t)refs[1], (uint32_t)refs[2], (uint32_t)refs[3]);
+}
+
+// One BFS level per launch, all blocks of the GPU; level index = st->base_level (how many levels the single-block kernel below has
+// already done: constant while these launches run) + launch index.
+__global__ void k_collapse4(uint32_t launch_idx, uint32_t leaf_size, const BuildParams* __restrict__ bp, const int2* __restrict__ children, const int2* __restrict__ range,
                             const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                             const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
-                            uint32_t* __restrict__ queue, CollapseState* st, uint4* __restrict__ out) {
+                            uint32_t* queue, CollapseState* st, uint4* __restrict__ out) {
+    const uint32_t level = st->base_level + launch_idx;
     const uint32_t begin = st->begin[level & 1], end = st->end[level & 1];
     if (begin == end) {                                                    // the tree is complete: the remaining launches of the fixed sequence only
         if (blockIdx.x == 0 && threadIdx.x == 0) { st->begin[(level + 1) & 1] = end; st->end[(level + 1) & 1] = end; }   // pass the empty level on
         return;
     }
     const QGrid g = bp->grid;
-    for (uint32_t j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x) {
-        const int i = (int)queue[j];
-        int src[4]; int32_t ref[4]; int nc = 2;
-        auto effective = [&](int c, int k) {                               // binary child -> (source of its box, traversal ref)
-            src[k] = c;
-            if (c < 0) { ref[k] = make_leaf_ref((uint32_t)(~c), 1); return; }
-            int2 r = range[c];
-            uint32_t cnt = (uint32_t)(r.y - r.x + 1);
-            ref[k] = cnt <= leaf_size ? make_leaf_ref((uint32_t)r.x, cnt) : c;
-        };
-        int2 ch = children[i];
-        effective(ch.x, 0); effective(ch.y, 1);
-        for (int round = 0; round < 2; ++round) {
-            int best = -1; float best_a = -1.0f;
-            for (int k = 0; k < nc; ++k)
-                if (ref[k] >= 0) { float a = half_area(node_lo[src[k]], node_hi[src[k]]); if (a > best_a) { best_a = a; best = k; } }
-            if (best < 0) break;
-            int2 c2 = children[src[best]];
-            effective(c2.x, best); effective(c2.y, nc); ++nc;
-        }
-        uint32_t q[4][3]; int32_t refs[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < nc) {
-                float4 lo, hi;
-                if (src[k] < 0) { lo = leaf_lo[~src[k]]; hi = leaf_hi[~src[k]]; } else { lo = node_lo[src[k]]; hi = node_hi[src[k]]; }
-                q[k][0] = quant_lo(lo.x, g.org[0], g.step[0]) | (quant_hi(hi.x, g.org[0], g.step[0]) << 16);
-                q[k][1] = quant_lo(lo.y, g.org[1], g.step[1]) | (quant_hi(hi.y, g.org[1], g.step[1]) << 16);
-                q[k][2] = quant_lo(lo.z, g.org[2], g.step[2]) | (quant_hi(hi.z, g.org[2], g.step[2]) << 16);
-                if (ref[k] >= 0) { uint32_t pos = atomicAdd(&st->tail, 1u); queue[pos] = (uint32_t)src[k]; refs[k] = (int32_t)pos; }
-                else refs[k] = ref[k];
-            } else {                                                       // unused slot: inverted box (lo 65535, hi 0), never hit
-                q[k][0] = q[k][1] = q[k][2] = 0x0000FFFFu;
-                refs[k] = make_leaf_ref(0, 1);
-            }
-        }
-        out[4 * (size_t)j] = make_uint4(q[0][0], q[0][1], q[0][2], q[1][0]);
-        out[4 * (size_t)j + 1] = make_uint4(q[1][1], q[1][2], q[2][0], q[2][1]);
-        out[4 * (size_t)j + 2] = make_uint4(q[2][2], q[3][0], q[3][1], q[3][2]);
-        out[4 * (size_t)j + 3] = make_uint4((uint32_t)refs[0], (uint32_t)refs[1], (uint32_t)refs[2], (uint32_t)refs[3]);
-    }
+    for (uint32_t j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < end; j += gridDim.x * blockDim.x)
+        collapse_node(j, leaf_size, g, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, st, out);
     // the last block to finish publishes the next level (in the other parity slot: blocks of THIS launch that become
     // resident late still read the current one)
     __syncthreads();
@@ -270,6 +281,31 @@ __global__ void k_collapse4(uint32_t level, uint32_t leaf_size, const BuildParam
             if (end > begin) st->depth = level + 1;
         }
     }
+}
+
+// Levels handled by ONE block, from level st->base_level + skip on: the small top levels of the tree (while a level has at most
+// max_nodes nodes; a launch per level would cost more than the level), and — after the fixed number of whole-GPU launches —
+// whatever is left of a very deep tree (max_nodes = all).  Leaves st->base_level = the next level to do.
+__global__ void __launch_bounds__(1024) k_collapse_block(uint32_t skip, uint32_t max_nodes, uint32_t leaf_size, const BuildParams* __restrict__ bp,
+                                                         const int2* __restrict__ children, const int2* __restrict__ range,
+                                                         const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                                         const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                                                         uint32_t* queue, CollapseState* st, uint4* __restrict__ out) {
+    const QGrid g = bp->grid;
+    uint32_t level = st->base_level + skip;
+    __syncthreads();                                                       // everybody has read base_level before thread 0 rewrites it
+    for (;; ++level) {
+        const uint32_t begin = st->begin[level & 1], end = st->end[level & 1];
+        if (begin == end || end - begin > max_nodes) break;
+        for (uint32_t j = begin + threadIdx.x; j < end; j += blockDim.x)
+            collapse_node(j, leaf_size, g, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, st, out);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) { st->begin[(level + 1) & 1] = end; st->end[(level + 1) & 1] = st->tail; st->depth = level + 1; }
+        __threadfence();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st->base_level = level;
 }
 
 // ------------------------------------------------------------------ exact mesh AABB (aabbox.rs:62-88) on the device
@@ -326,17 +362,17 @@ __global__ void k_mesh_setup(const int* __restrict__ mm, MeshDev proto, float pa
 
 __global__ void k_collapse_init(CollapseState* st, uint32_t* queue) {
     if (threadIdx.x || blockIdx.x) return;
-    CollapseState init; init.begin[0] = 0; init.begin[1] = 0; init.end[0] = 1; init.end[1] = 0; init.tail = 1; init.done = 0; init.depth = 0; init.pad = 0;
+    CollapseState init; init.begin[0] = 0; init.begin[1] = 0; init.end[0] = 1; init.end[1] = 0; init.tail = 1; init.done = 0; init.depth = 0; init.base_level = 0;
     *st = init; queue[0] = 0u;
 }
 
 // The tree is in place: publish its root, or — if it is deeper than the traversal stack allows (pathological input) — take the
 // mesh out of the scene (n_tris = 0: never traversed) and raise the error the host reports at its next synchronising call.
-__global__ void k_build_finish(const CollapseState* __restrict__ st, uint32_t levels_run, MeshDev* __restrict__ md, BuildResult* __restrict__ res) {
+__global__ void k_build_finish(const CollapseState* __restrict__ st, MeshDev* __restrict__ md, BuildResult* __restrict__ res) {
     if (threadIdx.x || blockIdx.x) return;
     BuildResult r; r.pad = 0;
     if (!st) { r.live_nodes = 0; r.depth = 0; r.error = 0; *res = r; return; }   // the whole mesh is one leaf (root_ref came with the proto)
-    const bool unfinished = st->begin[levels_run & 1] != st->end[levels_run & 1];
+    const bool unfinished = st->begin[st->base_level & 1] != st->end[st->base_level & 1];
     const bool bad = unfinished || 3 * st->depth + 2 > RBRT_STACK;
     r.live_nodes = bad ? 0u : st->tail; r.depth = st->depth; r.error = bad ? 1u : 0u;
     if (bad) md->n_tris = 0; else md->root_ref = 0;
@@ -372,7 +408,12 @@ cudaError_t build_begin(int device, BuildCtx* ctx) {
     DeviceBuild& B = g_build[device & 63];
     if (!B.copy) {
         CK(cudaStreamCreateWithFlags(&B.copy, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&B.build, cudaStreamNonBlocking));
+        // The build's ~80 small dependent kernels run in the gaps the render kernels of earlier frames leave; with the highest stream
+        // priority a freed SM goes to them first (RBRT_BUILD_PRIORITY=0: default priority, for A/B measurements).
+        int pr_least = 0, pr_greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+        static const bool prio = !(getenv("RBRT_BUILD_PRIORITY") && atoi(getenv("RBRT_BUILD_PRIORITY")) == 0);
+        CK(cudaStreamCreateWithPriority(&B.build, cudaStreamNonBlocking, prio ? pr_greatest : 0));
         for (auto& s : B.slot) { CK(cudaEventCreateWithFlags(&s.busy, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming)); }
     }
     ctx->device = device; ctx->slot = B.next; B.next ^= 1;
@@ -382,7 +423,6 @@ cudaError_t build_begin(int device, BuildCtx* ctx) {
 
 cudaError_t build_uploads_done(BuildCtx& ctx, cudaEvent_t ev) { return cudaEventRecord(ev, ctx.copy); }
 
-#define COLLAPSE_LEVELS 64       // launches of the level-synchronous collapse: the wide tree may be at most 63 deep (RBRT_STACK), deeper ones are refused
 
 cudaError_t build_mesh(BuildCtx& ctx, const float* h_tris, uint64_t n_all, uint32_t n, float pad_rel, uint32_t leaf_size, bool sah,
                        const MeshDev& proto, MeshDev* d_mesh, float4* d_tris, float4* d_normals, float4* d_nodes, BuildResult* d_res) {
@@ -449,23 +489,29 @@ cudaError_t build_mesh(BuildCtx& ctx, const float* h_tris, uint64_t n_all, uint3
             // contiguous run of the Morton order, which multi-triangle leaves rely on).  RBRT_SAH_PASSES: tuning knob.
             static const int sah_passes_env = getenv("RBRT_SAH_PASSES") ? atoi(getenv("RBRT_SAH_PASSES")) : 1;
             const int passes = (sah && leaf_size == 1) ? sah_passes_env : 0;
-            if (passes <= 0) k_refit<false><<<g, Bk, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+            static const int rot_min_env = getenv("RBRT_SAH_MIN_LEAVES") ? atoi(getenv("RBRT_SAH_MIN_LEAVES")) : 16;
+            if (passes <= 0) k_refit<false><<<g, Bk, 0, st>>>((int)n, 0, range, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
             for (int pass = 0; pass < passes; ++pass) {
                 if (pass) CK(cudaMemsetAsync(flags, 0, 4ull * ni, st));
-                k_refit<true><<<g, Bk, 0, st>>>((int)n, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
+                k_refit<true><<<g, Bk, 0, st>>>((int)n, rot_min_env, range, children, parent_int, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, height);
             }
             CK(cudaGetLastError());
             k_collapse_init<<<1, 32, 0, st>>>(cstate, queue);
             uint32_t gcol = (ni + Bk - 1) / Bk; if (gcol > 148u * 8u) gcol = 148u * 8u;
-            // level-synchronous collapse, a FIXED number of launches (the depth is only known on the device): a level of a finished
-            // tree returns at once (~2 us each)
-            for (int level = 0; level < COLLAPSE_LEVELS; ++level)
-                k_collapse4<<<gcol, Bk, 0, st>>>((uint32_t)level, leaf_size, bp, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate,
+            // Top-down collapse into 4-wide nodes, level-synchronous.  The depth is only known on the device, so the launch sequence
+            // is fixed: ONE block does the small top levels (up to 2048 nodes each: ~7 levels that would each cost a launch), then
+            // ceil(log2 n) + 2 whole-GPU launches, one level each (a level of a finished tree returns at once), then one block again
+            // for whatever a pathologically deep tree has left.  C3: 24 launches; the 64 of the first asynchronous version cost 0.45 ms.
+            k_collapse_block<<<1, 1024, 0, st>>>(0u, 2048u, leaf_size, bp, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate, reinterpret_cast<uint4*>(d_nodes));
+            uint32_t n_multi = 2; while ((1ull << (n_multi - 2)) < n) ++n_multi;
+            for (uint32_t k = 0; k < n_multi; ++k)
+                k_collapse4<<<gcol, Bk, 0, st>>>(k, leaf_size, bp, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate,
                                                 reinterpret_cast<uint4*>(d_nodes));
+            k_collapse_block<<<1, 1024, 0, st>>>(n_multi, 0xFFFFFFFFu, leaf_size, bp, children, range, leaf_lo, leaf_hi, node_lo, node_hi, queue, cstate, reinterpret_cast<uint4*>(d_nodes));
             CK(cudaGetLastError());
-            k_build_finish<<<1, 32, 0, st>>>(cstate, COLLAPSE_LEVELS, d_mesh, d_res);
-        } else k_build_finish<<<1, 32, 0, st>>>(nullptr, 0, d_mesh, d_res);
-    } else k_build_finish<<<1, 32, 0, st>>>(nullptr, 0, d_mesh, d_res);
+            k_build_finish<<<1, 32, 0, st>>>(cstate, d_mesh, d_res);
+        } else k_build_finish<<<1, 32, 0, st>>>(nullptr, d_mesh, d_res);
+    } else k_build_finish<<<1, 32, 0, st>>>(nullptr, d_mesh, d_res);
     CK(cudaGetLastError());
     CK(cudaEventRecord(S.busy, st));
     return cudaSuccess;

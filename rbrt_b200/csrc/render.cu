@@ -149,9 +149,11 @@ __device__ __forceinline__ float4 cone_of_sphere(f3 o, float cx, float cy, float
     const float inv = rsqrtf(d2);
     return make_float4(lx * inv, ly * inv, lz * inv, (1.0f - r2 / d2) - 1e-4f);
 }
+// d is a camera ray's direction: unit length to ~1e-7 (cam.rs:80 normalises it), which the 1e-4 margin absorbs.  u|u| < cos^2 - margin
+// covers both "points away" (u < 0) and "outside the cone"; q.w = -2 ("always test") and NaN directions compare false -> tested.
 __device__ __forceinline__ bool outside_cone(float4 q, f3 d) {
-    const float u = d.x * q.x + d.y * q.y + d.z * q.z;
-    return q.w > 0.0f && (u < 0.0f || u * u < q.w * (d.x * d.x + d.y * d.y + d.z * d.z));   // NaN direction: both compares false -> tested
+    const float u = __fmaf_rn(d.z, q.z, __fmaf_rn(d.y, q.y, d.x * q.x));
+    return u * fabsf(u) < q.w;
 }
 
 template <bool ET, bool PRIMARY = false>   // ET: Scene.elements holds BasicTriangles besides spheres (separate kernel instantiations, so the usual

@@ -15,7 +15,11 @@ spheres, meshes, camkw = bench.build_workload(wl)
 cam = R.Camera.new(camkw["position"], camkw["look_at"], camkw["up"], H, W, camkw["focal_len_mm"])
 pinned, keep = bench.pin_meshes(meshes)
 kw = dict(shard_mode=_abi.SHARD_TILES, shard_rank=0, shard_count=n) if n > 1 else {}
-pipe = R.FramePipeline(W, H, depth=2, host_output=True)
+depth = int(os.environ.get('DEPTH', '2'))
+hostout = os.environ.get('HOSTOUT', '1') == '1'
+dep = os.environ.get('DEP', '1') == '1'        # DEP=0: a scene is created per step but the render uses a resident one (cost of the build without the dependency)
+pipe = R.FramePipeline(W, H, depth=depth, host_output=hostout)
+fixed = bench.make_scene(spheres, meshes, pinned); fixed.handle()
 
 def retire(fin):
     if fin is not None:
@@ -26,7 +30,7 @@ def step():
     sc = bench.make_scene(spheres, meshes, pinned)
     sc.handle()
     t1 = time.perf_counter()
-    for fin in pipe.submit(cam, spp, sc, tag=sc, seed=1, **kw):
+    for fin in pipe.submit(cam, spp, sc if dep else fixed, tag=sc, seed=1, **kw):
         retire(fin)
     return (t1 - t0) * 1e3
 
@@ -40,4 +44,4 @@ cr = [step() for _ in range(steps)]
 for f in pipe.drain():
     retire(f)
 dt = (time.perf_counter() - t0) * 1e3 / steps
-print(f"{wl} shard 1/{n}: e2e {dt:.2f} ms/step, scene_create {sum(cr) / len(cr):.2f} ms (host view)", file=sys.stderr)
+print(f"{wl} shard 1/{n} depth {depth} hostout {hostout} dep {dep}: e2e {dt:.2f} ms/step, scene_create {sum(cr) / len(cr):.2f} ms (host view)", file=sys.stderr)

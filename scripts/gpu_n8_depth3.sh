@@ -1,0 +1,8 @@
+#!/bin/bash
+N=8
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --frames-in-flight 3 --no-cpu > gpurun_out/r2_bench_c3_n8_depth3.json 2> gpurun_out/r2_bench_c3_n8_depth3.err; echo "bench exit $?"
+python - <<PY
+import json
+b=json.load(open('gpurun_out/r2_bench_c3_n8_depth3.json'))
+print('depth3 value',round(b['value']),'ms/step',round(b['ms_per_step'],3),'fpb1',round(b['frames_per_batch_1']['ms_per_step'],3),'e2e',round(b['e2e']['value']),round(b['e2e']['ms_per_step'],3),'bcast',b['e2e']['ms_per_step_scene_broadcast'])
+PY
