@@ -416,7 +416,7 @@ def run_gpu(args):
         if k >= 3:
             single_ms.append(e0.elapsed_time(e1))
     ms_single = statistics.median(single_ms)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RBRT_DEBUG_NO_GATHER"):
         assert torch.equal(rgb, rgb_ref), "two-lane frame differs from the one-lane frame"
     frame = stats[-1]
     assert all(s_["rays"] == frame["rays"] and s_["paths"] == frame["paths"] for s_ in stats), "frames of one seed differ"
@@ -459,13 +459,14 @@ def run_gpu(args):
         clk.mark_begin()
         regions, last = timed_pipeline(fpb, 0.7)
         clk.mark_end()
-    if rank == 0:
+    check_images = not os.environ.get("RBRT_DEBUG_NO_GATHER")   # (a timing experiment of csrc/multi.cu that leaves rank 0's image incomplete)
+    if rank == 0 and check_images:
         assert torch.equal(last, rgb_ref), "pipelined frame differs from the single-frame render"
     ms = statistics.median(regions)
     regions1 = None
     if fpb != 1:                                              # the same measurement with ONE frame per batch, for the record
         regions1, last1 = timed_pipeline(1, 0.4)
-        if rank == 0:
+        if rank == 0 and check_images:
             assert torch.equal(last1, rgb_ref), "pipelined frame (1 per batch) differs from the single-frame render"
     t = torch.tensor([ms, ms_single, statistics.median(regions1) if regions1 else 0.0, min(regions), max(regions), ms_single_one_lane], dtype=torch.float64, device="cuda")
     agg = torch.tensor([frame["rays"] * args.steps, frame["paths"] * args.steps, (frame["launches"]) * args.steps,
@@ -545,7 +546,7 @@ def run_gpu(args):
         e2e_broadcast[0] = True
         e_ms_bcast = statistics.median(timed_e2e(0.4))
         e2e_broadcast[0] = False
-    if rank == 0:
+    if rank == 0 and check_images:
         assert np.array_equal(e2e_last[0].pixels.reshape(-1), rgb_ref.cpu().numpy()), "e2e image differs from the single-frame render"
     e_rays = frame["rays"] * e_steps
     te = torch.tensor([e_ms, e_ms_bcast or 0.0], dtype=torch.float64, device="cuda")

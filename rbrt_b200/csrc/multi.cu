@@ -17,8 +17,12 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
 #include "bvh_build.cuh"
 #include "multi.cuh"
 #include "shade.cuh"
@@ -208,6 +212,72 @@ int replicate_scene(Scene* sc, cudaStream_t bs) {
     return RBRT_OK;
 }
 
+// ------------------------------------------------------------------ one enqueue thread per local GPU (one process driving several GPUs)
+// Kernel launches are asynchronous but not free: a frame is 28-40 launches per GPU, ~0.13 ms of host time, and one thread feeding
+// eight GPUs in turn lets the last one start a millisecond late.  The threads only ENQUEUE (they hold no CUDA state of their own
+// beyond the current device); the caller waits for all of them before it issues the collective part on its own thread.
+struct Workers {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<int(int)> job;
+    std::vector<int> rc;
+    std::vector<std::string> msg;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+};
+static Workers* g_workers = nullptr;
+
+static void worker_main(Workers* w, int li) {
+    uint64_t seen = 0;
+    for (;;) {
+        std::function<int(int)> job;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv_go.wait(lk, [&] { return w->stop || w->gen != seen; });
+            if (w->stop) return;
+            seen = w->gen; job = w->job;
+        }
+        const int rc = job(li);
+        std::string m = rc ? rbrt_last_error() : "";
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->rc[li] = rc; w->msg[li] = m;
+        if (--w->pending == 0) w->cv_done.notify_all();
+    }
+}
+static void workers_start(int n) {
+    Workers* w = new Workers();
+    w->rc.assign(n, 0); w->msg.assign(n, "");
+    for (int li = 0; li < n; ++li) w->th.emplace_back(worker_main, w, li);
+    g_workers = w;
+}
+static void workers_stop() {
+    Workers* w = g_workers;
+    if (!w) return;
+    { std::lock_guard<std::mutex> lk(w->mu); w->stop = true; }
+    w->cv_go.notify_all();
+    for (auto& t : w->th) t.join();
+    delete w; g_workers = nullptr;
+}
+static bool workers_ready(int n) {
+    static const bool off = getenv("RBRT_NO_ENQUEUE_THREADS") != nullptr;  // A/B knob
+    return !off && g_workers && (int)g_workers->th.size() == n;
+}
+static int workers_run(int n, const std::function<int(int)>& job) {
+    Workers* w = g_workers;
+    {
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->job = job; w->pending = n; ++w->gen;
+        for (int i = 0; i < n; ++i) { w->rc[i] = 0; w->msg[i].clear(); }
+    }
+    w->cv_go.notify_all();
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv_done.wait(lk, [&] { return w->pending == 0; });
+    for (int i = 0; i < n; ++i) if (w->rc[i]) { set_error("%s", w->msg[i].c_str()); return w->rc[i]; }
+    return RBRT_OK;
+}
+
 // ------------------------------------------------------------------ the collective render
 static void add_stats(rbrt_stats* t, const rbrt_stats& s) {
     t->rays += s.rays; t->paths += s.paths; t->nan_rays += s.nan_rays; t->node_visits += s.node_visits; t->tri_tests += s.tri_tests;
@@ -291,13 +361,17 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
     if (C.local_n > 1) CKM(cudaEventRecord(g_dist[pool][0].ev_start, st));
     std::vector<cudaStream_t> s_of(C.local_n);
     std::vector<ShardDev> sh_of(C.local_n);
-    for (int li = 0; li < C.local_n; ++li) {
+    bool any_shared = false;                                              // one-GPU emulation of N ranks: several local ranks on one device
+    for (int li = 0; li < C.local_n; ++li) for (int lj = 0; lj < li; ++lj) if (C.devices[lj] == C.devices[li]) any_shared = true;
+    for (int li = 0; li < C.local_n; ++li) s_of[li] = (li == 0 || C.devices[li] == C.devices[0]) ? st : C.streams[li * 4 + pool];
+    std::mutex total_mu;
+    // Everything ONE local rank enqueues on its GPU: shard render, finalise of its own pixels (into its slab, or straight into rank 0's
+    // image through peer-mapped memory).  Runs on that GPU's enqueue thread when the local GPUs are distinct (see Workers).
+    auto enqueue_rank = [&](int li) -> int {
         const int dev = C.devices[li];
         const uint32_t r = (uint32_t)(C.rank + li);
         CKM(cudaSetDevice(dev));
-        const bool same_dev = dev == C.devices[0];
-        cudaStream_t s = (li == 0 || same_dev) ? st : C.streams[li * 4 + pool];
-        s_of[li] = s;
+        cudaStream_t s = s_of[li];
         if (s != st) CKM(cudaStreamWaitEvent(s, g_dist[pool][0].ev_start, 0));
         DistBuffers& D = g_dist[pool][li];
         const uint32_t P_r = (gm.off_px[r + 1] - gm.off_px[r]) / n_frames;
@@ -310,11 +384,12 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
         if (rc) return rc;
         rc = render_accum(sc, li, cams, seeds, n_frames, spp, &ol, D.accum, s, nullptr, stats ? &jobs[li] : nullptr);
         if (rc) return rc;
-        bool shared_dev = false;                                          // does another local rank use this GPU (one-GPU emulation of N ranks)?
+        bool shared_dev = false;                                          // does another local rank use this GPU?
         for (int lj = 0; lj < C.local_n; ++lj) if (lj != li && C.devices[lj] == dev) shared_dev = true;
         if (stats && shared_dev) {                                        // the ranks share the device's wavefront pool,
             rbrt_stats one; memset(&one, 0, sizeof(one));                 // so this rank's counters are read before the next rank resets them
             rc = collect_stats(jobs[li], &one); if (rc) return rc;
+            std::lock_guard<std::mutex> g(total_mu);
             add_stats(&total, one); jobs[li].wb = nullptr;
         }
         if (!samples) {
@@ -330,9 +405,18 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
         }
         if (s != st) CKM(cudaEventRecord(D.ev_done, s));
         if (dbg) fprintf(stderr, "[multi] rank %u enqueued at %.3f ms\n", r, dbg_ms());
+        return RBRT_OK;
+    };
+    if (C.local_n > 1 && !any_shared && workers_ready(C.local_n)) {
+        int rc = workers_run(C.local_n, enqueue_rank);                    // one enqueue thread per GPU: a frame is 28-40 launches per GPU,
+        if (rc) return rc;                                                // 0.13 ms each from one thread = 1 ms of an 8-GPU frame of 6 ms
+    } else {
+        for (int li = 0; li < C.local_n; ++li) { int rc = enqueue_rank(li); if (rc) return rc; }
     }
+    CKM(cudaSetDevice(C.devices[0]));
+    static const bool dbg_no_gather = getenv("RBRT_DEBUG_NO_GATHER") != nullptr;   // TIMING EXPERIMENT ONLY: rank 0's image then lacks the other ranks' pixels
     if (!samples) {
-        if (!peer) {
+        if (!peer && !dbg_no_gather) {
             CKN(g_nccl.GroupStart());
             for (int li = 0; li < C.local_n; ++li) {
                 const uint32_t r = (uint32_t)(C.rank + li);
@@ -359,7 +443,7 @@ int render_frames(const Scene& sc, const rbrt_camera* cams, const uint64_t* seed
                 if (d_hdr) { for (uint32_t f = 0; f < RBRT_MAX_FRAMES; ++f) op.p[f] = d_hdr[f < n_frames ? f : 0]; k_untile<float><<<grid, 256, 0, st>>>((const float*)(g_gather[pool] + hdr_base), gm, op); }
                 CKM(cudaGetLastError());
             }
-        } else {
+        } else if (peer) {
             CKM(cudaSetDevice(C.devices[0]));
             for (int li = 1; li < C.local_n; ++li) if (s_of[li] != st) CKM(cudaStreamWaitEvent(st, g_dist[pool][li].ev_done, 0));
         }
@@ -429,6 +513,7 @@ int rbrt_gpu_comm_destroy(void) {
     LOCK;
     Comm& C = g_comm;
     if (!C.active) return RBRT_OK;
+    workers_stop();
     int cur = 0; cudaGetDevice(&cur);
     for (int li = 0; li < (int)C.devices.size(); ++li) { cudaSetDevice(C.devices[li]); cudaDeviceSynchronize(); }
     for (void* c : C.nccl) if (c && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c);
@@ -498,6 +583,7 @@ int rbrt_gpu_init_multi(const int* devices, int n_devices, int transport) {
     set_current_device(devs[0]);
     N.active = true;
     C = N;
+    if (n_devices > 1 && !dup) workers_start(n_devices);                  // one enqueue thread per GPU (render_frames)
     return RBRT_OK;
 }
 

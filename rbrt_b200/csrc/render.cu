@@ -945,6 +945,8 @@ static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
 // or four frames per batch give the kernels the size they have on fewer GPUs.  Every path keeps its own (pixel,
 // sample, frame) identity, so each image is bit-identical to a lone render of that frame.
 void note_scene_use(const Scene& sc, int device, cudaStream_t st) {
+    static std::mutex mu;                                                 // the per-GPU enqueue threads of one collective render share the scene
+    std::lock_guard<std::mutex> g(mu);
     for (SceneUse& u : sc.uses)
         if (u.device == device && u.stream == st) { cudaEventRecord(u.ev, st); return; }
     SceneUse u{device, st, nullptr};
