@@ -145,7 +145,11 @@ __device__ __forceinline__ void end_path(const WaveParams& P, uint32_t pid, f3 c
 __device__ __forceinline__ float4 cone_of_sphere(f3 o, float cx, float cy, float cz, float r) {
     const float lx = cx - o.x, ly = cy - o.y, lz = cz - o.z;
     const float d2 = lx * lx + ly * ly + lz * lz, r2 = r * r;
-    if (!(d2 > 1.01f * r2) || !(d2 > 1e-20f) || !(d2 < 1e30f)) return make_float4(0.0f, 0.0f, 0.0f, -2.0f);   // inside / too close / degenerate: always test
+    // The reference's own arithmetic works on absolute coordinates: o - c and (bound - o) carry an error of ~ulp(|coordinate|), which a cone
+    // margin relative to the DISTANCE only covers while the distance is not tiny against the coordinates (camera or element far from the
+    // world origin): there, always test.
+    const float mag2 = (o.x * o.x + o.y * o.y + o.z * o.z) + (cx * cx + cy * cy + cz * cz);
+    if (!(d2 > 1.01f * r2) || !(d2 > 1e-20f) || !(d2 < 1e30f) || !(d2 > 1e-4f * mag2)) return make_float4(0.0f, 0.0f, 0.0f, -2.0f);   // inside / too close / degenerate: always test
     const float inv = rsqrtf(d2);
     return make_float4(lx * inv, ly * inv, lz * inv, (1.0f - r2 / d2) - 1e-4f);
 }

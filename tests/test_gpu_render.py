@@ -275,3 +275,36 @@ def test_basic_triangle_elements_render(gpu, oracle):
     ref = oracle.OracleScene.from_scene(scene).render_hdr(cam.to_c(), 6, _abi.RenderOptsC(seed=31))
     for kw in [{}, {"no_tail_kernel": True}, {"trace_mode": _abi.TRACE_BRUTE}]:
         assert_images_equal(R.render_scene_hdr(cam, 6, scene, seed=31, **kw), ref, f"mixed elements {kw}")
+
+
+def test_camera_ray_cone_culling_is_exact(gpu, oracle):
+    """k_generate skips the sphere / mesh-box test of an element when the camera ray misses the cone the element subtends from
+    the camera (render.cu cone_of_sphere).  Only provable misses may be skipped: adversarial set-ups — camera just outside a
+    sphere, pixel-sized spheres whose silhouettes fall between pixels, geometry and camera 1e5 units from the world origin
+    (where the reference's own f32 arithmetic is coarse), a small mesh far away — against the oracle, bit for bit."""
+    rng = np.random.default_rng(11)
+    mats = [R.Lambertian(Vec3(0.6, 0.3, 0.2)), R.Metal(Vec3(0.9, 0.9, 0.9), 0.05), R.Dielectric(1.6)]
+
+    def check(scene, cam, what, spp=2):
+        ref = oracle.OracleScene.from_scene(scene).render_hdr(cam.to_c(), spp, _abi.RenderOptsC(seed=17, max_depth=3))
+        assert_images_equal(R.render_scene_hdr(cam, spp, scene, seed=17, max_depth=3), ref, what)
+
+    for dist in (1.0051, 1.02, 1.2, 3.0):                              # camera just outside / near a unit sphere (inside 1 %: never culled)
+        sc = R.Scene()
+        sc.elements += [R.Sphere(Vec3(0, 0, 0), 1.0, mats[0]), R.Sphere(Vec3(1.5, 0.2, -0.5), 0.4, mats[1]), R.Sphere(Vec3(0, -1001, 0), 1000.0, mats[0])]
+        check(sc, R.Camera.new(Vec3(0, 0, dist), Vec3(0.1, -0.05, -1.0), Vec3(0, 1, 0), 48, 64, 12.0), f"camera at {dist} r")
+    sc = R.Scene()                                                     # 60 spheres of about one pixel, seen from 500 units
+    for k in range(60):
+        c = rng.uniform(-60, 60, size=2)
+        sc.elements.append(R.Sphere(Vec3(float(c[0]), float(c[1]), -500.0), float(rng.uniform(0.2, 0.9)), mats[k % 3]))
+    check(sc, R.Camera.new(Vec3(0, 0, 0), Vec3(0, 0, -1), Vec3(0, 1, 0), 96, 128, 60.0), "pixel-sized spheres")
+    for off in (1e3, 1e5, 3e6):                                        # everything far from the world origin
+        o = np.float32(off)
+        sc = R.Scene()
+        sc.elements += [R.Sphere(Vec3(o, o, o - 9), 1.5, mats[0]), R.Sphere(Vec3(o + 2.5, o + 0.5, o - 7), 0.8, mats[2]), R.Sphere(Vec3(o, o - 1001.5, o - 9), 1000.0, mats[1])]
+        tris = synth.displaced_icosphere(2, 1.0, (float(o) - 2.5, float(o) + 0.3, float(o) - 8.0))
+        sc.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, mats[0]))
+        check(sc, R.Camera.new(Vec3(o, o + 0.5, o), Vec3(0, -0.05, -1.0), Vec3(0, 1, 0), 48, 64, 20.0), f"offset {off:g}")
+    sc = S.spheres_scene()                                             # a small mesh far away: its box cone is a few pixels wide
+    sc.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(2, 0.5, (3.0, 6.0, -120.0)), mats[1]))
+    check(sc, S.example_camera(128, 96), "small far mesh", spp=3)
