@@ -127,8 +127,9 @@ enum {
                                     overlap the dense first bounces of the next */
     RBRT_OPT_POOL_MASK = 24,
     RBRT_OPT_SPLIT_BATCHES = 32  /* render the frame's samples as (at least) two batches on two internal lanes, so that the sparse, latency-bound
-                                    end of one batch runs under the dense start of the next: shortens a LONE frame (rbrt_gpu_render and
-                                    rbrt_gpu_render_hdr set it themselves).  Leave it off when several frames are in flight anyway. */
+                                    end of one batch runs under the dense start of the next: shortens a LONE, LARGE frame (rbrt_gpu_render and
+                                    rbrt_gpu_render_hdr set it themselves from 2^26 paths per GPU; smaller frames lose a few %).  Leave it off
+                                    when several frames are in flight anyway.  Images do not depend on it. */
 };
 
 enum {
@@ -152,7 +153,9 @@ typedef struct rbrt_render_opts {
     uint32_t trace_mode;     /* RBRT_TRACE_* */
     uint32_t shard_mode;     /* RBRT_SHARD_* */
     uint32_t shard_rank;
-    uint32_t shard_count;    /* 0 or 1 = unsharded */
+    uint32_t shard_count;    /* 0 = automatic: unsharded, or - for a scene created under a communicator - sharded over its GPUs with the
+                                gather on rank 0 inside the call; 1 = this GPU renders everything; > 1 = the host places shard_rank of
+                                shard_count itself (no collective) */
     uint32_t batch_paths;    /* paths in flight per wavefront batch; 0 = as many as fit (<= 2^27, <= half of free HBM) */
     uint32_t integrator;     /* 0 = wavefront (default); other values are rejected */
     uint32_t flags;          /* RBRT_OPT_* */

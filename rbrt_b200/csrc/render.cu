@@ -153,11 +153,20 @@ __device__ __forceinline__ float4 cone_of_sphere(f3 o, float cx, float cy, float
     const float inv = rsqrtf(d2);
     return make_float4(lx * inv, ly * inv, lz * inv, (1.0f - r2 / d2) - 1e-4f);
 }
-// d is a camera ray's direction: unit length to ~1e-7 (cam.rs:80 normalises it), which the 1e-4 margin absorbs.  u|u| < cos^2 - margin
-// covers both "points away" (u < 0) and "outside the cone"; q.w = -2 ("always test") and NaN directions compare false -> tested.
+// d is a camera ray's direction: unit length to ~1e-7 (cam.rs:80 normalises it), which the 1e-4 margin absorbs.
+// outside_cone (mesh boxes): u|u| < cos^2 - margin covers both "points away" (u < 0: the slab test rejects t_max < 0, aabbox.rs:49) and
+// "outside the cone".  outside_double_cone (spheres): u^2 < cos^2 - margin, i.e. the whole LINE misses the sphere — a sphere BEHIND the
+// origin is not a provable miss: with a discriminant of exactly 0 the reference keeps the single root even when it is negative
+// (sphere.rs:34-44: the far root is only tried when there are two) and reports a hit behind the ray.  Found by the round-2 parity runs
+// (an experiment with sphere groups for bounce rays skipped such a sphere: 1 path in 6.3 M on C4 differed), pinned in
+// tests/test_oracle_quirks.py (Q16) and tests/test_gpu_trace.py.  q.w = -2 ("always test") and NaN directions compare false -> tested.
 __device__ __forceinline__ bool outside_cone(float4 q, f3 d) {
     const float u = __fmaf_rn(d.z, q.z, __fmaf_rn(d.y, q.y, d.x * q.x));
     return u * fabsf(u) < q.w;
+}
+__device__ __forceinline__ bool outside_double_cone(float4 q, f3 d) {
+    const float u = __fmaf_rn(d.z, q.z, __fmaf_rn(d.y, q.y, d.x * q.x));
+    return u * u < q.w;
 }
 
 template <bool ET, bool PRIMARY = false>   // ET: Scene.elements holds BasicTriangles besides spheres (separate kernel instantiations, so the usual
@@ -166,7 +175,7 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
     float closest = 3.40282347e+38f;                                     // f32::MAX (scene.rs:21)
     int kind = -1; uint32_t elem = 0; float t_s = 0.0f;
     for (uint32_t i = 0; i < P.S.n_spheres; ++i) {                       // elements first, in order (scene.rs:23-31)
-        if (PRIMARY && cull && outside_cone(cull[i], d)) continue;
+        if (PRIMARY && cull && outside_double_cone(cull[i], d)) continue;
         float t, dist;
         int r = ET ? element_intersect(P.S, i, o, d, t, dist) : sphere_intersect(__ldg(P.S.spheres + i), o, d, t, dist);
         if (r < 0) { ++nan_count; end_path(P, pid, mk3(0, 0, 0)); return CLS_NONE; }   // reference panics (sphere.rs:33)

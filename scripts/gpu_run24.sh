@@ -1,0 +1,11 @@
+#!/bin/bash
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest24.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2_pytest24.log
+tail -6 gpurun_out/r2_pytest24.log
+SPP=8 timeout 600 python scripts/c4_diff.py 2>&1 | grep -E "differing|RAY|groups:|plain:" | head -12
+: > gpurun_out/r2_exp24.jsonl
+for wl in c4 c3; do timeout 300 python scripts/exp.py $wl groups2 >> gpurun_out/r2_exp24.jsonl 2>> gpurun_out/r2_exp24.err; done
+python - <<'PY'
+import json
+for l in open('gpurun_out/r2_exp24.jsonl'):
+    d=json.loads(l); print(d['wl'], 'frame', d['ms_frame_1'], 'trace', d['ms_trace_1'], 'split', d['ms_split_1'], 'frame8', d['ms_frame_8'], d['checksum'])
+PY

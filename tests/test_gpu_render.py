@@ -308,3 +308,35 @@ def test_camera_ray_cone_culling_is_exact(gpu, oracle):
     sc = S.spheres_scene()                                             # a small mesh far away: its box cone is a few pixels wide
     sc.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(2, 0.5, (3.0, 6.0, -120.0)), mats[1]))
     check(sc, S.example_camera(128, 96), "small far mesh", spp=3)
+
+
+def test_sixty_spheres_with_ties_and_overlaps(gpu, oracle):
+    """60 spheres of three materials incl. exact DUPLICATES (equal dist: the lower element index must win, scene.rs:23-31),
+    overlapping ones, a huge ground sphere and a mesh, depth 50: the render equals the oracle's, and closest hits through the
+    renderer's stage A (RBRT_TRACE_WAVEFRONT) equal the oracle's for camera rays and for rays that start inside the cluster.
+    (Written for an experiment — sphere groups for bounce rays, profiles/r2_summary.md — that was dropped; the scene stays.)"""
+    mats = [R.Lambertian(Vec3(0.6, 0.3, 0.2)), R.Metal(Vec3(0.9, 0.9, 0.9), 0.02), R.Dielectric(1.6), R.Lambertian(Vec3(0.2, 0.7, 0.3))]
+    sc = R.Scene()
+    sc.elements.append(R.Sphere(Vec3(0.0, -1000.0, -8.0), 1000.0, mats[0]))
+    r2 = np.random.default_rng(5)
+    for k in range(48):
+        c = r2.uniform(-6, 6, size=3)
+        sc.elements.append(R.Sphere(Vec3(float(c[0]), 0.5 + abs(float(c[1])) * 0.4, -8.0 + float(c[2]) * 0.6), float(r2.uniform(0.25, 0.8)), mats[k % 4]))
+    for k in (3, 7, 11, 20, 31):                                       # exact duplicates with ANOTHER material: the lower index must win the tie
+        s = sc.elements[k]
+        sc.elements.append(R.Sphere(s.center, s.radius, mats[(k + 1) % 4]))
+    for k in range(6):                                                 # a tight overlapping clump
+        sc.elements.append(R.Sphere(Vec3(0.3 * k - 0.8, 1.2, -5.0 - 0.1 * k), 0.5, mats[k % 4]))
+    sc.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(2, 1.0, (2.0, 1.0, -6.0)), mats[2]))
+    assert len(sc.elements) == 60
+    cam = S.example_camera(160, 120)
+    osc = oracle.OracleScene.from_scene(sc)
+    ref = osc.render_hdr(cam.to_c(), 3, _abi.RenderOptsC(seed=29))
+    for kw in [{}, {"no_tail_kernel": True}]:
+        assert_images_equal(R.render_scene_hdr(cam, 3, sc, seed=29, **kw), ref, f"sixty spheres {kw}")
+    rays = np.concatenate([R.primary_rays(cam, 29, 0), S.random_rays(20000, (0.0, 1.0, -8.0), 3.0, 4)], 0)
+    want = osc.hit(rays)
+    from .test_gpu_trace import assert_same
+    for mode in (_abi.TRACE_WAVEFRONT, _abi.TRACE_BVH):
+        assert_same(sc.hit(rays, mode), want, f"sixty spheres, trace mode {mode}")
+    assert (want["kind"] == 0).sum() > 10000

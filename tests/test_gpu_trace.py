@@ -246,3 +246,21 @@ def test_basic_triangle_elements(gpu, oracle):
     big = R.Scene(elements=[R.BasicTriangle.new(((-900, -900, -1500), (900, -900, -1500), (0, 900, -1500)), R.Lambertian(Vec3(1, 1, 1)))])
     h = big.hit(np.float32([[0, 0, 0, 0, 0, -1]]))
     assert h["kind"][0] == 2 and abs(h["t"][0] - 1500.0) < 1e-2                       # no upper cap on t for BasicTriangle (triangle.rs:118)
+
+
+def test_tangent_sphere_behind_the_ray_is_hit(gpu, oracle):
+    """Quirk Q16 (tests/test_oracle_quirks.py): with a discriminant of exactly 0 the reference reports a sphere BEHIND the ray.  No
+    shortcut may treat "points away from the sphere" as a miss, in any of the three trace modes, with few or many spheres."""
+    mat = R.Lambertian(Vec3(0.5, 0.5, 0.5))
+    rays = np.array([[0, 0, 0, 0, 0, -1], [0, 0, 0, 0, 0, -2.5], [0, 0, 1, 0, 0, -1], [0.5, 0, 0, 0, 0, -1]], np.float32)
+    for n_extra in (0, 30):
+        sc = R.Scene()
+        sc.elements.append(R.Sphere(Vec3(1.0, 0.0, 5.0), 1.0, mat))    # tangent to the z axis, behind the rays
+        rng = np.random.default_rng(1)
+        for k in range(n_extra):
+            c = rng.uniform(-30, 30, size=3)
+            sc.elements.append(R.Sphere(Vec3(float(c[0]) + 100.0, float(c[1]), float(c[2])), 0.7, mat))   # far off to the side
+        want = oracle.OracleScene.from_scene(sc).hit(rays)
+        assert want["kind"][0] == 0 and want["t"][0] == -5.0 and want["kind"][2] == 0 and want["kind"][3] == -1
+        for mode in MODES:
+            assert_same(sc.hit(rays, mode), want, f"{n_extra} extra spheres, mode {mode}")

@@ -98,6 +98,13 @@ def test_q9_sphere_near_root_quirk(oracle):  # sphere.rs:42-55
     assert L.rbrt_ref_kat_sphere(V(0, 0, 0), 1.0, Ray(V(0, 0, 1.0005), V(0, 0, -1)), 0.001, 2000.0, h) == 0
     # sphere behind the ray: both roots negative
     assert L.rbrt_ref_kat_sphere(V(0, 0, 5), 1.0, Ray(V(0, 0, 0), V(0, 0, -1)), 0.001, 2000.0, h) == 0
+    # Q16 (found by the round-2 GPU parity runs): a sphere BEHIND the ray whose line is exactly tangent — discriminant == 0.0 — IS hit:
+    # num_hits == 1, so the negative root is kept (the far root is only tried when there are two, sphere.rs:34-44) and only the
+    # distance window is checked: l = (-1,0,-5), b = 10, c = 25, sol = 100 - 100 = 0, t = -5, point (0,0,5), normal (-1,0,0)
+    assert L.rbrt_ref_kat_sphere(V(1, 0, 5), 1.0, Ray(V(0, 0, 0), V(0, 0, -1)), 0.001, 2000.0, h) == 1
+    assert h.t == -5.0 and h.dist == 5.0 and (h.point.x, h.point.y, h.point.z) == (0.0, 0.0, 5.0) and (h.normal.x, h.normal.y, h.normal.z) == (-1.0, 0.0, 0.0)
+    # ... while a line that cuts the same sphere (two roots, both negative) is a miss
+    assert L.rbrt_ref_kat_sphere(V(0.5, 0, 5), 1.0, Ray(V(0, 0, 0), V(0, 0, -1)), 0.001, 2000.0, h) == 0
     # max_dist is inclusive for spheres (sphere.rs:52)
     assert L.rbrt_ref_kat_sphere(V(0, 0, -2001), 1.0, Ray(V(0, 0, 0), V(0, 0, -1)), 0.001, 2000.0, h) == 1
     # NaN discriminant: the reference panics (sphere.rs:33)
