@@ -437,6 +437,8 @@ int rbrt_gpu_release_cache(void) {
     release_dist_buffers();
     release_build_scratch();
     arena_release_all();
+    for (void* p : g_pinned_free) cudaFreeHost(p);
+    g_pinned_free.clear();
     return RBRT_OK;
 }
 
