@@ -9,7 +9,7 @@
 // reference's tests): serde_yaml 0.9 -> a parser for the block-style YAML subset the scene files use (nested mappings by
 // indentation, `- ` sequences, scalars, `#` comments, `---`); tobj 4 -> `v` / `f` records, one model per `o`/`g`, position
 // indices only, faces consumed as index triples (tobj default LoadOptions: no triangulation); image 0.25 -> an 8-bit RGB
-// PNG written with zlib (lossless, so any conforming encoder stores the same pixels) or binary PPM by extension.
+// PNG written with zlib (lossless, so any conforming encoder stores the same pixels), binary PPM, 24-bit BMP or uncompressed TGA by extension.
 #include <zlib.h>
 
 #include <cctype>
@@ -279,7 +279,22 @@ bool save_image(const std::string& path, const std::vector<uint8_t>& rgb, uint32
         char hdr[64]; int n = snprintf(hdr, sizeof(hdr), "P6\n%u %u\n255\n", w, h);
         out.insert(out.end(), hdr, hdr + n);
         out.insert(out.end(), rgb.begin(), rgb.end());
-    } else return false;
+    } else if (ext == ".bmp") {                                  // 24-bit BI_RGB, bottom-up rows of BGR padded to 4 bytes
+        const uint32_t stride = (3 * w + 3) & ~3u, size = 54 + stride * h;
+        auto le32 = [&](uint32_t x) { for (int s = 0; s < 32; s += 8) out.push_back((uint8_t)(x >> s)); };
+        auto le16 = [&](uint32_t x) { out.push_back((uint8_t)x); out.push_back((uint8_t)(x >> 8)); };
+        out.push_back('B'); out.push_back('M'); le32(size); le32(0); le32(54);
+        le32(40); le32(w); le32(h); le16(1); le16(24); le32(0); le32(stride * h); le32(2835); le32(2835); le32(0); le32(0);
+        for (uint32_t y = h; y-- > 0;) {
+            for (uint32_t x = 0; x < w; ++x) { const uint8_t* p = &rgb[((size_t)y * w + x) * 3]; out.push_back(p[2]); out.push_back(p[1]); out.push_back(p[0]); }
+            for (uint32_t k = 3 * w; k < stride; ++k) out.push_back(0);
+        }
+    } else if (ext == ".tga") {                                  // uncompressed true-colour, top-left origin, BGR
+        const uint8_t hdr[18] = {0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, (uint8_t)w, (uint8_t)(w >> 8), (uint8_t)h, (uint8_t)(h >> 8), 24, 0x20};
+        if (w > 65535 || h > 65535) return false;
+        out.insert(out.end(), hdr, hdr + 18);
+        for (size_t i = 0; i < (size_t)w * h; ++i) { out.push_back(rgb[3 * i + 2]); out.push_back(rgb[3 * i + 1]); out.push_back(rgb[3 * i]); }
+    } else return false;                                         // lossy formats of the `image` crate (jpeg, ...) are not offered
     FILE* fp = fopen(path.c_str(), "wb");
     if (!fp) return false;
     bool ok = fwrite(out.data(), 1, out.size(), fp) == out.size();

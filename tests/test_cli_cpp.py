@@ -139,5 +139,22 @@ def test_cli_render_matches_python_host(cli, tmp_path, gpu):
     ppm = str(tmp_path / "out.ppm")
     assert subprocess.run([cli, "-c", y, "--height", "8", "-w", "8", "-s", "1", "-t", ppm], capture_output=True).returncode == 0
     assert open(ppm, "rb").read().startswith(b"P6\n8 8\n255\n")
+    # the other lossless formats the `image` crate picks by extension (main.rs:86): 24-bit BMP (bottom-up BGR, rows padded
+    # to 4 bytes) and uncompressed TGA (top-down BGR) hold the PNG's pixels
+    small = [cli, "-c", y, "--height", "10", "-w", "13", "-s", "2", "--seed", "5"]
+    files = {e: str(tmp_path / f"s.{e}") for e in ("png", "bmp", "tga")}
+    for f in files.values():
+        assert subprocess.run(small + ["-t", f], capture_output=True).returncode == 0
+    want = png.decode_png(open(files["png"], "rb").read())
+    bmp = open(files["bmp"], "rb").read()
+    stride = (3 * 13 + 3) & ~3
+    assert bmp[:2] == b"BM" and len(bmp) == 54 + stride * 10 and int.from_bytes(bmp[18:22], "little") == 13 and int.from_bytes(bmp[22:26], "little") == 10
+    rows = np.frombuffer(bmp[54:], np.uint8).reshape(10, stride)[::-1, :39].reshape(10, 13, 3)[:, :, ::-1]
+    assert np.array_equal(rows, want)
+    tga = open(files["tga"], "rb").read()
+    assert tga[2] == 2 and tga[12:16] == bytes([13, 0, 10, 0]) and tga[16] == 24 and tga[17] == 0x20 and len(tga) == 18 + 390
+    assert np.array_equal(np.frombuffer(tga[18:], np.uint8).reshape(10, 13, 3)[:, :, ::-1], want)
+    lossy = subprocess.run(small + ["-t", str(tmp_path / "s.jpg")], capture_output=True, text=True)
+    assert lossy.returncode == 101 and "Unable to save target img" in lossy.stderr
     bad = subprocess.run([cli, "-c", y, "--height", "8", "-w", "8", "-s", "1", "-t", str(tmp_path / "nodir" / "o.png")], capture_output=True, text=True)
     assert bad.returncode == 101 and "Unable to save target img" in bad.stderr      # main.rs:86-91
