@@ -236,8 +236,19 @@ struct StackS {
 
 // 256-bit read-only load (sm_100: LDG.E.256): a 64-byte node is two requests to L1 instead of four (the trace kernel runs
 // L1TEX at 75-80 % of its peak, mostly on these gathers).  p must be 32-byte aligned.
+// L2::evict_last: the nodes (C3: ~40 MB, every ray gathers from them) compete in L2 with the path records streaming through (4.3 GB per
+// batch) and with the triangle records; k_trace's L2 hit rate is 62 % and its warps mostly wait on these loads.  Measured on C3: trace
+// 22.65 -> 22.47 ms, frame 34.76 -> 34.51 ms.  The other hints tried made things slower or changed nothing — streaming (.cs) record loads
+// / stores, evict_last for triangles, L1::evict_last for nodes, L1::no_allocate for triangles or records (profiles/r2_exp_l2_hints.jsonl).
+#ifndef RBRT_NODE_L2_EVICT_LAST
+#define RBRT_NODE_L2_EVICT_LAST 1
+#endif
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+#if RBRT_NODE_L2_EVICT_LAST
+    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
