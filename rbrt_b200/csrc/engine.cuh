@@ -88,6 +88,7 @@ struct WaveParams {
     uint32_t fetch_thr;      // k_trace re-fills a warp from the queue when fewer lanes than this still traverse
     uint32_t tail_thr;       // the same for k_tail, whose "re-fill" also shades the lanes' pending hits
     uint32_t use_cull;       // k_generate skips provably missed elements of camera rays (render.cu cone_of_sphere)
+    uint32_t cam_rays;       // iteration-0 records hold camera rays in the one-sector layout (render.cu: path record)
     uint4* rec;
     uint32_t* candq; uint32_t* matq[2][3];
     float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;

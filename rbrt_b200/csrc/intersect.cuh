@@ -238,7 +238,7 @@ struct StackS {
 // L1TEX at 75-80 % of its peak, mostly on these gathers).  p must be 32-byte aligned.
 // L2::evict_last: the nodes (C3: ~40 MB, every ray gathers from them) compete in L2 with the path records streaming through (4.3 GB per
 // batch) and with the triangle records; k_trace's L2 hit rate is 62 % and its warps mostly wait on these loads.  Measured on C3: trace
-// 22.65 -> 22.47 ms, frame 34.76 -> 34.51 ms.  The other hints tried made things slower or changed nothing — streaming (.cs) record loads
+// 22.65 -> 22.47 ms, frame 34.76 -> 34.51 ms (the same hint on the triangle records: 22.24 -> 22.41 ms, not adopted).  The other hints tried made things slower or changed nothing — streaming (.cs) record loads
 // / stores, evict_last for triangles, L1::evict_last for nodes, L1::no_allocate for triangles or records (profiles/r2_exp_l2_hints.jsonl).
 #ifndef RBRT_NODE_L2_EVICT_LAST
 #define RBRT_NODE_L2_EVICT_LAST 1

@@ -94,8 +94,21 @@ __device__ __forceinline__ void flush(const WaveParams& P, uint32_t it, const De
 __device__ __forceinline__ uint4* rec_ptr(const WaveParams& P, uint32_t pid) { return P.rec + 4 * (size_t)pid; }
 __device__ __forceinline__ uint4 load_hit(const WaveParams& P, uint32_t pid) { return rec_ptr(P, pid)[0]; }
 __device__ __forceinline__ void store_hit(const WaveParams& P, uint32_t pid, uint4 h) { rec_ptr(P, pid)[0] = h; }
-__device__ __forceinline__ void load_ray(const WaveParams& P, uint32_t pid, f3& o, f3& d) {
+// CAMERA RAYS (iteration 0 of a render, WaveParams::cam_rays) all start at the frame's camera position, so their record is ONE sector:
+//   bytes  0..15  hit   bytes 16..27  direction.xyz   (origin = cam[frame of pid].pos; sector 1 is not touched before the first scatter)
+// k_generate writes it whole with one 256-bit store, and k_trace / k_shade of iteration 0 read 32 instead of 64 bytes per ray.  Before, the
+// 16 + 16 + 8-byte stores left sector 1 with 8 valid bytes, which L2 had to complete from DRAM before writing it back: 1.26 GB of reads
+// per 2^26 paths in a kernel that reads nothing.  The first scatter (store_hist, k = 0) then writes sector 1 whole (zero history).
+__device__ __forceinline__ uint32_t frame_of_path(const WaveParams& P, uint32_t pid) {
+    return P.n_frames > 1u ? fast_div(fast_div(pid, P.fd_paths_px), P.fd_s_count) : 0u;
+}
+__device__ __forceinline__ void load_ray(const WaveParams& P, uint32_t pid, uint32_t it, f3& o, f3& d) {
     const float4 a = reinterpret_cast<const float4*>(rec_ptr(P, pid))[1];
+    if (P.cam_rays && it == 0u) {
+        const CamDev& c = P.cam[frame_of_path(P, pid)];
+        o = mk3(c.pos[0], c.pos[1], c.pos[2]); d = mk3(a.x, a.y, a.z);
+        return;
+    }
     const float2 b = reinterpret_cast<const float2*>(rec_ptr(P, pid))[4];
     o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
 }
@@ -103,10 +116,18 @@ __device__ __forceinline__ void store_ray(const WaveParams& P, uint32_t pid, f3 
     reinterpret_cast<float4*>(rec_ptr(P, pid))[1] = make_float4(o.x, o.y, o.z, d.x);
     reinterpret_cast<float2*>(rec_ptr(P, pid))[4] = make_float2(d.y, d.z);
 }
+__device__ __forceinline__ void store_camera_record(const WaveParams& P, uint32_t pid, uint4 h, f3 d) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(rec_ptr(P, pid)), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w),
+                 "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(0u) : "memory");
+}
 __device__ __forceinline__ uint32_t load_hist(const WaveParams& P, uint32_t pid, uint32_t k) {
     return k < REC_HIST ? reinterpret_cast<const uint16_t*>(rec_ptr(P, pid))[20 + k] : P.hist[(size_t)(k - REC_HIST) * P.cap + pid];
 }
 __device__ __forceinline__ void store_hist(const WaveParams& P, uint32_t pid, uint32_t k, uint32_t elem) {
+    if (P.cam_rays && k == 0u) {                                          // first scatter of a camera ray: sector 1 whole (ray tail = 0 until stage A stores it)
+        asm volatile("st.global.v8.b32 [%0], {%1,%1,%2,%1,%1,%1,%1,%1};" :: "l"(rec_ptr(P, pid) + 2), "r"(0u), "r"(elem & 0xFFFFu) : "memory");
+        return;
+    }
     if (k < REC_HIST) reinterpret_cast<uint16_t*>(rec_ptr(P, pid))[20 + k] = (uint16_t)elem;
     else P.hist[(size_t)(k - REC_HIST) * P.cap + pid] = (uint16_t)elem;
 }
@@ -185,14 +206,16 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
         const MeshDev& M = P.S.meshes[mi];
         if (PRIMARY && cull && outside_cone(cull[P.S.n_spheres + mi], d)) continue;
         if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
-        store_ray(P, pid, o, d);
-        store_hit(P, pid, make_uint4(__float_as_uint(t_s), elem, __float_as_uint(closest), (mi << 8) | (uint32_t)(kind & 0xFF)));
+        const uint4 h = make_uint4(__float_as_uint(t_s), elem, __float_as_uint(closest), (mi << 8) | (uint32_t)(kind & 0xFF));
+        if (PRIMARY && P.cam_rays) store_camera_record(P, pid, h, d);
+        else { store_ray(P, pid, o, d); store_hit(P, pid, h); }
         return CLS_CAND;
     }
     if (kind == 0) {
         if (it < P.max_depth) {                                           // depth > 0: scatter() will run (lib.rs:54)
-            store_ray(P, pid, o, d);
-            store_hit(P, pid, make_uint4(__float_as_uint(t_s), elem, 0u, 0u));
+            const uint4 h = make_uint4(__float_as_uint(t_s), elem, 0u, 0u);
+            if (PRIMARY && P.cam_rays) store_camera_record(P, pid, h, d);
+            else { store_ray(P, pid, o, d); store_hit(P, pid, h); }
             return __ldg(P.S.mat_kind + elem);
         }
         end_path(P, pid, mk3(0, 0, 0));                                   // depth exhausted -> black (lib.rs:63-66)
@@ -371,7 +394,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
                     if (qi < n) {
                         pid = P.candq[qi];
                         uint4 h = load_hit(P, pid);
-                        load_ray(P, pid, o, d);
+                        load_ray(P, pid, it, o, d);
                         bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
                         bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
                         has_ray = true;
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
 template <bool BRUTE>
 __device__ __forceinline__ int process_candidate(const WaveParams& P, uint32_t it, uint32_t pid, TraceCounters* cnt) {
     uint4 h = load_hit(P, pid);
-    f3 o, d; load_ray(P, pid, o, d);
+    f3 o, d; load_ray(P, pid, it, o, d);
     float bt = __uint_as_float(h.x), closest = __uint_as_float(h.z);
     uint32_t belem = h.y, btri = 0; int bkind = (h.w & 0xFFu) == 0u ? 0 : -1;
     for (uint32_t mi = h.w >> 8; mi < P.S.n_meshes; ++mi) {
@@ -454,7 +477,7 @@ template <bool ET>
 __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid,
                                                uint32_t& rays, uint32_t& nan_count) {
     uint4 h = load_hit(P, pid);
-    f3 o, d; load_ray(P, pid, o, d);
+    f3 o, d; load_ray(P, pid, it, o, d);
     float t = __uint_as_float(h.x);
     uint32_t elem = h.y;
     f3 point = o + t * d;                                                 // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
@@ -645,7 +668,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
     };
     auto load_candidate = [&]() {                                         // the ray stage A queued for this path
         uint4 h = load_hit(P, pid);
-        load_ray(P, pid, o, d);
+        load_ray(P, pid, it, o, d);
         bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
         bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
         has_ray = true;
@@ -1072,6 +1095,8 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
             wp.cap = w.cap; wp.paths_px = P; wp.fd_paths_px = make_fastdiv(P); wp.max_depth = max_depth;
             static const bool no_cull_env = getenv("RBRT_NO_PRIMARY_CULL") != nullptr;      // tuning / A-B knob
             wp.use_cull = no_cull_env ? 0u : 1u;
+            static const bool two_sector_env = getenv("RBRT_TWO_SECTOR_CAMERA_RECORDS") != nullptr;   // A-B knob: camera rays in the general record layout
+            wp.cam_rays = two_sector_env ? 0u : 1u;
             const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
             wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
             const char* tthr_env = getenv("RBRT_TAIL_FETCH_THRESHOLD");
