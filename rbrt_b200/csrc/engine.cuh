@@ -26,14 +26,13 @@ enum { ST_RAYS = 0, ST_NAN = 1, ST_NODES = 2, ST_TRIS = 3, ST_CAND = 4, ST_TAIL_
 struct WaveBuffers {
     uint32_t cap = 0;            // paths per batch the buffers hold
     uint32_t depth_cap = 0;      // bounce iterations the history/counter arrays hold
-    uint4* rec = nullptr;        // [pid] ONE 64-byte record per path = two 32-byte DRAM sectors (render.cu, "path record"):
-                                 //   hit (16 B: sphere pre-result for queued candidates, final hit for queued shading work),
-                                 //   ray origin + direction (24 B), the first 12 entries of the scatter history (24 B)
+    uint4* rec = nullptr;        // [pid] ONE 32-byte record per path = one DRAM sector (render.cu, "path record"): a traversal candidate
+                                 //   {t_sphere, sphere | first mesh, origin, direction} or a pending hit {hit point, direction, element, triangle}
     uint32_t* candq = nullptr;   // pids queued for BVH traversal
     uint32_t* matq[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // pids queued for shading, by iteration parity and material kind
                                  // (k_shade(it) reads parity it&1 while it fills parity (it+1)&1)
     float4* out = nullptr;       // [pid] final radiance of the path (written exactly once, when the path ends)
-    uint16_t* hist = nullptr;    // [iteration - 12][pid]: element scattered at (attenuation product), iterations >= 12 (the first 12 live in rec)
+    uint16_t* hist = nullptr;    // [iteration][pid]: element scattered at (attenuation product when the path ends)
     IterCtr* ctr = nullptr;      // [depth_cap + 2]
     unsigned long long* stats = nullptr;   // ST_COUNT counters
     float4* accum = nullptr;     // internal W*H accumulation buffer for the host-pointer entry points
@@ -88,7 +87,7 @@ struct WaveParams {
     uint32_t fetch_thr;      // k_trace re-fills a warp from the queue when fewer lanes than this still traverse
     uint32_t tail_thr;       // the same for k_tail, whose "re-fill" also shades the lanes' pending hits
     uint32_t use_cull;       // k_generate skips provably missed elements of camera rays (render.cu cone_of_sphere)
-    uint32_t cam_rays;       // iteration-0 records hold camera rays in the one-sector layout (render.cu: path record)
+    uint32_t keep_t;         // resolve() also leaves t in out[pid].x (rbrt_gpu_trace_rays reports it; a render does not need it)
     uint4* rec;
     uint32_t* candq; uint32_t* matq[2][3];
     float4* out; uint16_t* hist; IterCtr* ctr; unsigned long long* stats;

@@ -83,54 +83,53 @@ __device__ __forceinline__ void flush(const WaveParams& P, uint32_t it, const De
 }
 
 // ------------------------------------------------------------------ path record
-// Everything a path's queued ray needs sits in ONE 64-byte, 64-byte-aligned record = two 32-byte DRAM sectors:
-//   bytes  0..15  hit      uint4  (stage A's sphere pre-result for traversal candidates; the final hit for shading work)
-//   bytes 16..39  ray      origin.xyz, direction.xyz
-//   bytes 40..63  history  u16[12]: element scattered at in bounce iterations 0..11 (later ones: WaveParams::hist)
-// The bounce iterations' shade launches are bound by random 32-byte sector traffic to DRAM (3.3 TB/s of sectors at it 1,
-// more resident warps or prefetching only made them slower): with separate ray_o / ray_d / hit / history arrays an item
-// touched five sectors and used half of each, now it touches these two and uses all of them.
-#define REC_HIST 12
-__device__ __forceinline__ uint4* rec_ptr(const WaveParams& P, uint32_t pid) { return P.rec + 4 * (size_t)pid; }
-__device__ __forceinline__ uint4 load_hit(const WaveParams& P, uint32_t pid) { return rec_ptr(P, pid)[0]; }
-__device__ __forceinline__ void store_hit(const WaveParams& P, uint32_t pid, uint4 h) { rec_ptr(P, pid)[0] = h; }
-// CAMERA RAYS (iteration 0 of a render, WaveParams::cam_rays) all start at the frame's camera position, so their record is ONE sector:
-//   bytes  0..15  hit   bytes 16..27  direction.xyz   (origin = cam[frame of pid].pos; sector 1 is not touched before the first scatter)
-// k_generate writes it whole with one 256-bit store, and k_trace / k_shade of iteration 0 read 32 instead of 64 bytes per ray.  Before, the
-// 16 + 16 + 8-byte stores left sector 1 with 8 valid bytes, which L2 had to complete from DRAM before writing it back: 1.26 GB of reads
-// per 2^26 paths in a kernel that reads nothing.  The first scatter (store_hist, k = 0) then writes sector 1 whole (zero history).
-__device__ __forceinline__ uint32_t frame_of_path(const WaveParams& P, uint32_t pid) {
-    return P.n_frames > 1u ? fast_div(fast_div(pid, P.fd_paths_px), P.fd_s_count) : 0u;
+// Everything a path's queued work item needs sits in ONE 32-byte, 32-byte-aligned record = ONE DRAM sector, always read with one
+// 256-bit load and always written WHOLE with one 256-bit store (a partly written sector costs a read: L2 completes it from DRAM
+// before it can write it back).  Two formats, told apart by the queue the path sits in:
+//   traversal candidate (candq)   {bits(t_sphere), sphere | first_mesh << 16, origin.xyz, direction.xyz}
+//       stage A's sphere pre-result (sphere = 0xFFFF: none) and the first mesh whose box the ray entered; `closest`, the distance the
+//       mesh must beat (scene.rs:36), is re-derived from t_sphere with the expression the sphere test itself uses (sphere.rs:49-50)
+//   pending hit (matq[kind])      {hit_point.xyz, direction.xyz, element | is_mesh << 16, triangle}
+//       what scatter() takes: the hit point (= ray.point_at(t), computed where t is known), the incoming direction, and where the
+//       normal comes from.  Neither the ray's origin nor t is needed after the hit.
+// The scatter history (element ids, for the attenuation product when the path ends) lives in per-iteration rows, WaveParams::hist:
+// a 2-byte entry inside the record would be a partial write to it at every bounce.
+// History of this layout (C3 frame, one frame at a time): five separate arrays 37.6 ms -> one 64-byte record {hit, ray, 12 history
+// entries} 36.5 -> camera rays in one sector (34.65 -> 33.80, profiles/r2_exp_camera_records.jsonl) -> this one-sector record.
+#define NO_SPHERE 0xFFFFu
+__device__ __forceinline__ uint4* rec_ptr(const WaveParams& P, uint32_t pid) { return P.rec + 2 * (size_t)pid; }
+__device__ __forceinline__ void store_rec(const WaveParams& P, uint32_t pid, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                          uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(rec_ptr(P, pid)), "r"(w0), "r"(w1), "r"(w2), "r"(w3),
+                 "r"(w4), "r"(w5), "r"(w6), "r"(w7) : "memory");
 }
-__device__ __forceinline__ void load_ray(const WaveParams& P, uint32_t pid, uint32_t it, f3& o, f3& d) {
-    const float4 a = reinterpret_cast<const float4*>(rec_ptr(P, pid))[1];
-    if (P.cam_rays && it == 0u) {
-        const CamDev& c = P.cam[frame_of_path(P, pid)];
-        o = mk3(c.pos[0], c.pos[1], c.pos[2]); d = mk3(a.x, a.y, a.z);
-        return;
-    }
-    const float2 b = reinterpret_cast<const float2*>(rec_ptr(P, pid))[4];
-    o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
+__device__ __forceinline__ void load_rec(const WaveParams& P, uint32_t pid, uint4& a, uint4& b) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(rec_ptr(P, pid)) : "memory");
 }
-__device__ __forceinline__ void store_ray(const WaveParams& P, uint32_t pid, f3 o, f3 d) {
-    reinterpret_cast<float4*>(rec_ptr(P, pid))[1] = make_float4(o.x, o.y, o.z, d.x);
-    reinterpret_cast<float2*>(rec_ptr(P, pid))[4] = make_float2(d.y, d.z);
+#define FB(x) __float_as_uint(x)
+#define BF(x) __uint_as_float(x)
+__device__ __forceinline__ void store_candidate(const WaveParams& P, uint32_t pid, float t_s, uint32_t sphere, uint32_t mi, f3 o, f3 d) {
+    store_rec(P, pid, FB(t_s), sphere | (mi << 16), FB(o.x), FB(o.y), FB(o.z), FB(d.x), FB(d.y), FB(d.z));
 }
-__device__ __forceinline__ void store_camera_record(const WaveParams& P, uint32_t pid, uint4 h, f3 d) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(rec_ptr(P, pid)), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w),
-                 "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(0u) : "memory");
+// closest = dist_from_ray_orig of the sphere pre-result: `p = o + t*d; dist = length(o - p)` (sphere.rs:49-50, triangle.rs:425-426)
+__device__ __forceinline__ void load_candidate_rec(const WaveParams& P, uint32_t pid, float& t_s, uint32_t& sphere, uint32_t& mi, float& closest, f3& o, f3& d) {
+    uint4 a, b; load_rec(P, pid, a, b);
+    t_s = BF(a.x); sphere = a.y & 0xFFFFu; mi = a.y >> 16;
+    o = mk3(BF(a.z), BF(a.w), BF(b.x)); d = mk3(BF(b.y), BF(b.z), BF(b.w));
+    closest = 3.40282347e+38f;                                            // f32::MAX (scene.rs:21)
+    if (sphere != NO_SPHERE) { const f3 p = o + t_s * d; closest = len3(o - p); }
 }
-__device__ __forceinline__ uint32_t load_hist(const WaveParams& P, uint32_t pid, uint32_t k) {
-    return k < REC_HIST ? reinterpret_cast<const uint16_t*>(rec_ptr(P, pid))[20 + k] : P.hist[(size_t)(k - REC_HIST) * P.cap + pid];
+__device__ __forceinline__ void store_pending(const WaveParams& P, uint32_t pid, f3 point, f3 d, uint32_t elem, bool is_mesh, uint32_t tri) {
+    store_rec(P, pid, FB(point.x), FB(point.y), FB(point.z), FB(d.x), FB(d.y), FB(d.z), elem | (is_mesh ? 0x10000u : 0u), tri);
 }
-__device__ __forceinline__ void store_hist(const WaveParams& P, uint32_t pid, uint32_t k, uint32_t elem) {
-    if (P.cam_rays && k == 0u) {                                          // first scatter of a camera ray: sector 1 whole (ray tail = 0 until stage A stores it)
-        asm volatile("st.global.v8.b32 [%0], {%1,%1,%2,%1,%1,%1,%1,%1};" :: "l"(rec_ptr(P, pid) + 2), "r"(0u), "r"(elem & 0xFFFFu) : "memory");
-        return;
-    }
-    if (k < REC_HIST) reinterpret_cast<uint16_t*>(rec_ptr(P, pid))[20 + k] = (uint16_t)elem;
-    else P.hist[(size_t)(k - REC_HIST) * P.cap + pid] = (uint16_t)elem;
+__device__ __forceinline__ void load_pending(const WaveParams& P, uint32_t pid, f3& point, f3& d, uint32_t& elem, bool& is_mesh, uint32_t& tri) {
+    uint4 a, b; load_rec(P, pid, a, b);
+    point = mk3(BF(a.x), BF(a.y), BF(a.z)); d = mk3(BF(a.w), BF(b.x), BF(b.y));
+    elem = b.z & 0xFFFFu; is_mesh = (b.z >> 16) != 0u; tri = b.w;
 }
+__device__ __forceinline__ uint32_t load_hist(const WaveParams& P, uint32_t pid, uint32_t k) { return P.hist[(size_t)k * P.cap + pid]; }
+__device__ __forceinline__ void store_hist(const WaveParams& P, uint32_t pid, uint32_t k, uint32_t elem) { P.hist[(size_t)k * P.cap + pid] = (uint16_t)elem; }
 
 // Path id -> (frame of the batch, sample of the batch, pixel enumeration index): pid = ((f * s_count) + s_local) * paths_px + j
 __device__ __forceinline__ void path_coords(const WaveParams& P, uint32_t pid, uint32_t& f, uint32_t& s_local, uint32_t& j) {
@@ -206,16 +205,13 @@ __device__ __forceinline__ uint32_t stage_a(const WaveParams& P, uint32_t it, ui
         const MeshDev& M = P.S.meshes[mi];
         if (PRIMARY && cull && outside_cone(cull[P.S.n_spheres + mi], d)) continue;
         if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
-        const uint4 h = make_uint4(__float_as_uint(t_s), elem, __float_as_uint(closest), (mi << 8) | (uint32_t)(kind & 0xFF));
-        if (PRIMARY && P.cam_rays) store_camera_record(P, pid, h, d);
-        else { store_ray(P, pid, o, d); store_hit(P, pid, h); }
+        store_candidate(P, pid, t_s, kind == 0 ? elem : NO_SPHERE, mi, o, d);
         return CLS_CAND;
     }
     if (kind == 0) {
         if (it < P.max_depth) {                                           // depth > 0: scatter() will run (lib.rs:54)
-            const uint4 h = make_uint4(__float_as_uint(t_s), elem, 0u, 0u);
-            if (PRIMARY && P.cam_rays) store_camera_record(P, pid, h, d);
-            else { store_ray(P, pid, o, d); store_hit(P, pid, h); }
+            store_pending(P, pid, o + t_s * d, d, elem, false, 0u);       // ray.point_at(t) (sphere.rs:49)
+            if (P.keep_t) reinterpret_cast<float*>(P.out + pid)[0] = t_s;
             return __ldg(P.S.mat_kind + elem);
         }
         end_path(P, pid, mk3(0, 0, 0));                                   // depth exhausted -> black (lib.rs:63-66)
@@ -281,11 +277,12 @@ __global__ void __launch_bounds__(256) k_generate(WaveParams P) {
 
 // ------------------------------------------------------------------ stage B: BVH traversal with dynamic fetch
 // Resolution of a queued ray once all its meshes are done: the rest of Scene::hit + the miss arm of colorize.
-__device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_t pid, f3 d, int kind, uint32_t elem, uint32_t tri, float t) {
+__device__ __forceinline__ int resolve(const WaveParams& P, uint32_t it, uint32_t pid, f3 o, f3 d, int kind, uint32_t elem, uint32_t tri, float t) {
     if (kind >= 0) {
         if (it < P.max_depth) {
             uint32_t e = kind == 0 ? elem : P.S.n_spheres + elem;
-            store_hit(P, pid, make_uint4(__float_as_uint(t), e, tri, (uint32_t)kind));
+            store_pending(P, pid, o + t * d, d, e, kind == 1, tri);       // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
+            if (P.keep_t) reinterpret_cast<float*>(P.out + pid)[0] = t;   // rbrt_gpu_trace_rays reports t (k_rays_collect)
             return (int)__ldg(P.S.mat_kind + e);
         }
         end_path(P, pid, mk3(0, 0, 0));
@@ -370,7 +367,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
                 if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
                 start_mesh(M); want_fetch = false; break;
             }
-            if (want_fetch) { done_kind = resolve(P, it, pid, d, bkind, belem, btri, bt); has_ray = false; }
+            if (want_fetch) { done_kind = resolve(P, it, pid, o, d, bkind, belem, btri, bt); has_ray = false; }
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -393,10 +390,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
                     uint32_t qi = base + __popc(m & lt);
                     if (qi < n) {
                         pid = P.candq[qi];
-                        uint4 h = load_hit(P, pid);
-                        load_ray(P, pid, it, o, d);
-                        bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
-                        bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
+                        load_candidate_rec(P, pid, bt, belem, mi, closest, o, d);
+                        bkind = belem != NO_SPHERE ? 0 : -1; btri = 0;
                         has_ray = true;
                         start_mesh(P.S.meshes[mi]);                       // stage A found this mesh's box hit
                     }
@@ -421,11 +416,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS) k_trace(WaveParam
 // material kind to shade, or -1 when the path ended.
 template <bool BRUTE>
 __device__ __forceinline__ int process_candidate(const WaveParams& P, uint32_t it, uint32_t pid, TraceCounters* cnt) {
-    uint4 h = load_hit(P, pid);
-    f3 o, d; load_ray(P, pid, it, o, d);
-    float bt = __uint_as_float(h.x), closest = __uint_as_float(h.z);
-    uint32_t belem = h.y, btri = 0; int bkind = (h.w & 0xFFu) == 0u ? 0 : -1;
-    for (uint32_t mi = h.w >> 8; mi < P.S.n_meshes; ++mi) {
+    f3 o, d; float bt, closest; uint32_t belem, mi0, btri = 0;
+    load_candidate_rec(P, pid, bt, belem, mi0, closest, o, d);
+    int bkind = belem != NO_SPHERE ? 0 : -1;
+    for (uint32_t mi = mi0; mi < P.S.n_meshes; ++mi) {
         const MeshDev& M = P.S.meshes[mi];
         if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
         float t; uint32_t ti; bool ok;
@@ -445,7 +439,7 @@ __device__ __forceinline__ int process_candidate(const WaveParams& P, uint32_t i
         float dist = len3(o - p);
         if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) { closest = dist; bkind = 1; belem = mi; btri = ti; bt = t; }
     }
-    return resolve(P, it, pid, d, bkind, belem, btri, bt);
+    return resolve(P, it, pid, o, d, bkind, belem, btri, bt);
 }
 
 // Brute-force stage B (RBRT_TRACE_BRUTE): the reference's own every-triangle loop, no dynamic fetch.
@@ -476,19 +470,16 @@ __global__ void __launch_bounds__(256) k_trace_brute(WaveParams P, uint32_t it) 
 template <bool ET>
 __device__ __forceinline__ uint32_t shade_item(const WaveParams& P, uint32_t it, uint32_t kind, uint32_t pid,
                                                uint32_t& rays, uint32_t& nan_count) {
-    uint4 h = load_hit(P, pid);
-    f3 o, d; load_ray(P, pid, it, o, d);
-    float t = __uint_as_float(h.x);
-    uint32_t elem = h.y;
-    f3 point = o + t * d;                                                 // ray.point_at(t) (sphere.rs:49, mesh.rs:247)
+    f3 point, d; uint32_t elem, tri; bool is_mesh;
+    load_pending(P, pid, point, d, elem, is_mesh, tri);
     f3 normal;
-    if (h.w == 0u) {                                                      // sphere: p - c, un-normalised (sphere.rs:56); BasicTriangle: stored normal
+    if (!is_mesh) {                                                       // sphere: p - c, un-normalised (sphere.rs:56); BasicTriangle: stored normal
         if (ET) normal = element_normal(P.S, elem, point);
         else { float4 s4 = __ldg(P.S.spheres + elem); normal = point - mk3(s4.x, s4.y, s4.z); }
     }
     else {                                                              // mesh: stored unit normal (mesh.rs:253-257)
         const MeshDev& M = P.S.meshes[elem - P.S.n_spheres];
-        float4 nn = __ldg(P.S.normals + M.nrm_base + h.z);
+        float4 nn = __ldg(P.S.normals + M.nrm_base + tri);
         normal = mk3(nn.x, nn.y, nn.z);
     }
     uint32_t f, s_local, jp;
@@ -667,10 +658,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
         sp = 0; stack.put(sp++, SENTINEL); cur = M.root_ref;
     };
     auto load_candidate = [&]() {                                         // the ray stage A queued for this path
-        uint4 h = load_hit(P, pid);
-        load_ray(P, pid, it, o, d);
-        bt = __uint_as_float(h.x); belem = h.y; closest = __uint_as_float(h.z);
-        bkind = (h.w & 0xFFu) == 0u ? 0 : -1; btri = 0; mi = h.w >> 8;
+        load_candidate_rec(P, pid, bt, belem, mi, closest, o, d);
+        bkind = belem != NO_SPHERE ? 0 : -1; btri = 0;
         has_ray = true;
         if (COUNT) ++n_cand;
         start_mesh(P.S.meshes[mi]);
@@ -691,7 +680,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 4) k_tail(WaveParams P, uint32_t
                 if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
                 start_mesh(M); more = true; break;
             }
-            if (!more) { pending = resolve(P, it, pid, d, bkind, belem, btri, bt); has_ray = false; }   // -1: the path ended
+            if (!more) { pending = resolve(P, it, pid, o, d, bkind, belem, btri, bt); has_ray = false; }   // -1: the path ended
             else idle = false;
         }
         // ---- (2) lanes without a path take the next queued item (one atomic per warp)
@@ -883,20 +872,20 @@ __global__ void __launch_bounds__(256) k_rays_collect(WaveParams P, const rbrt_r
     out.kind = RBRT_HIT_NONE; out.elem_idx = 0; out.tri_idx = 0; out.t = 0.0f; out.dist = 0.0f;
     out.point.x = out.point.y = out.point.z = 0.0f; out.normal.x = out.normal.y = out.normal.z = 0.0f;
     if (__float_as_uint(P.out[pid].w) == 0xFFFFFFFFu) {                   // the path did not end: a hit is waiting to be shaded
-        const uint4 h = load_hit(P, pid);
+        f3 p, d_rec; uint32_t elem, tri; bool is_mesh;
+        load_pending(P, pid, p, d_rec, elem, is_mesh, tri);
         const rbrt_ray q = rays[pid];
-        const f3 o = mk3(q.origin.x, q.origin.y, q.origin.z), d = mk3(q.direction.x, q.direction.y, q.direction.z);
-        const float t = __uint_as_float(h.x);
-        const f3 p = o + t * d;
+        const f3 o = mk3(q.origin.x, q.origin.y, q.origin.z);
+        const float t = P.out[pid].x;                                     // WaveParams::keep_t
         f3 nrm;
-        if (h.w == 0u) {
-            nrm = element_normal(P.S, h.y, p);
-            out.kind = (P.S.n_etris && __ldg(P.S.elem_kind + h.y)) ? RBRT_HIT_TRIANGLE : RBRT_HIT_SPHERE;
-            out.elem_idx = h.y;
+        if (!is_mesh) {
+            nrm = element_normal(P.S, elem, p);
+            out.kind = (P.S.n_etris && __ldg(P.S.elem_kind + elem)) ? RBRT_HIT_TRIANGLE : RBRT_HIT_SPHERE;
+            out.elem_idx = elem;
         } else {
-            const uint32_t mi = h.y - P.S.n_spheres;
-            const float4 nn = __ldg(P.S.normals + P.S.meshes[mi].nrm_base + h.z); nrm = mk3(nn.x, nn.y, nn.z);
-            out.kind = RBRT_HIT_MESH; out.elem_idx = mi; out.tri_idx = h.z;
+            const uint32_t mi = elem - P.S.n_spheres;
+            const float4 nn = __ldg(P.S.normals + P.S.meshes[mi].nrm_base + tri); nrm = mk3(nn.x, nn.y, nn.z);
+            out.kind = RBRT_HIT_MESH; out.elem_idx = mi; out.tri_idx = tri;
         }
         out.t = t; out.dist = len3(o - p);                                // sphere.rs:50, mesh.rs:248
         out.point.x = p.x; out.point.y = p.y; out.point.z = p.z;
@@ -964,11 +953,11 @@ static int ensure_wave_buffers(WaveBuffers& wb, uint32_t cap, uint32_t depth) {
     free_wave_buffers(wb);
     wb.accum = accum; wb.accum_px = accum_px; wb.rgb = rgb; wb.hdr = hdr; wb.out_px = out_px; wb.ev.swap(ev);
     size_t b = 0;
-    CKR(cudaMalloc(&wb.rec, 64ull * cap)); b += 64ull * cap;
+    CKR(cudaMalloc(&wb.rec, 32ull * cap)); b += 32ull * cap;
     CKR(cudaMalloc(&wb.candq, 4ull * cap)); b += 4ull * cap;
     for (int i = 0; i < 6; ++i) { CKR(cudaMalloc(&wb.matq[i / 3][i % 3], 4ull * cap)); b += 4ull * cap; }
     CKR(cudaMalloc(&wb.out, 16ull * cap)); b += 16ull * cap;
-    { const uint64_t rows = depth > REC_HIST ? depth - REC_HIST : 1; CKR(cudaMalloc(&wb.hist, 2ull * cap * rows)); b += 2ull * cap * rows; }
+    { const uint64_t rows = std::max<uint64_t>(depth, 1); CKR(cudaMalloc(&wb.hist, 2ull * cap * rows)); b += 2ull * cap * rows; }
     CKR(cudaMalloc(&wb.ctr, sizeof(IterCtr) * (depth + 2)));
     CKR(cudaMalloc(&wb.stats, 8 * ST_COUNT));
     wb.cap = cap; wb.depth_cap = depth; wb.bytes = b;
@@ -1057,7 +1046,7 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
         uint32_t target = o.batch_paths;
         const uint64_t PF = (uint64_t)P * n_frames;                                           // paths of one sample of every frame of the batch
         if (PF > 0x7FFFFFFFull) { set_error("batch too large"); return RBRT_E_INVALID; }
-        const uint64_t per_path = 108ull + 2ull * (max_depth > REC_HIST ? max_depth - REC_HIST : 1);
+        const uint64_t per_path = 76ull + 2ull * std::max<uint64_t>(max_depth, 1);            // record 32 + queues 28 + radiance 16 + history rows
         const uint64_t limit_paths = pool_limit_bytes() ? std::max<uint64_t>(pool_limit_bytes() / per_path, 1) : ~0ull;   // rbrt_gpu_set_pool_limit
         const uint32_t S_all = sh.s1 - sh.s0, S_half = (S_all + 1) / 2;
         if (!target) {
@@ -1095,8 +1084,7 @@ int render_accum(const Scene& sc, int li, const rbrt_camera* cams, const uint64_
             wp.cap = w.cap; wp.paths_px = P; wp.fd_paths_px = make_fastdiv(P); wp.max_depth = max_depth;
             static const bool no_cull_env = getenv("RBRT_NO_PRIMARY_CULL") != nullptr;      // tuning / A-B knob
             wp.use_cull = no_cull_env ? 0u : 1u;
-            static const bool two_sector_env = getenv("RBRT_TWO_SECTOR_CAMERA_RECORDS") != nullptr;   // A-B knob: camera rays in the general record layout
-            wp.cam_rays = two_sector_env ? 0u : 1u;
+            wp.keep_t = 0u;
             const char* thr_env = getenv("RBRT_FETCH_THRESHOLD");             // tuning knob
             wp.fetch_thr = thr_env ? (uint32_t)std::min(32, std::max(1, atoi(thr_env))) : FETCH_THRESHOLD;
             const char* tthr_env = getenv("RBRT_TAIL_FETCH_THRESHOLD");
@@ -1297,7 +1285,7 @@ int trace_rays_wavefront(const Scene& sc, const rbrt_ray* d_rays, uint64_t n, rb
         WaveParams wp;
         memset(&wp, 0, sizeof(wp));
         wp.S = rp.dev; wp.n_frames = 1; wp.cap = wb.cap; wp.paths_px = cap; wp.fd_paths_px = make_fastdiv(cap); wp.fd_s_count = make_fastdiv(1);
-        wp.s_count = 1; wp.max_depth = 50; wp.fetch_thr = FETCH_THRESHOLD; wp.tail_thr = TAIL_FETCH_THRESHOLD;
+        wp.s_count = 1; wp.max_depth = 50; wp.fetch_thr = FETCH_THRESHOLD; wp.tail_thr = TAIL_FETCH_THRESHOLD; wp.keep_t = 1u;
         wp.rec = wb.rec; wp.candq = wb.candq;
         for (int i = 0; i < 6; ++i) wp.matq[i / 3][i % 3] = wb.matq[i / 3][i % 3];
         wp.out = wb.out; wp.hist = wb.hist; wp.ctr = wb.ctr; wp.stats = wb.stats;
