@@ -199,8 +199,9 @@ def peaks():
 def algorithmic_bytes(st, n_spheres, n_meshes):
     """Trace kernel (stage B: LBVH traversal of the rays that entered a mesh AABB), DESIGN.md section 4:
     bytes/step = 64 V + 48 T + 64 C   (V node visits x 64-B node, T triangle tests x 48-B record, C traversed rays x
-    64 B of queue / path-record traffic: 4 B queue index + 40 B of the path record (16 B sphere pre-result + 24 B ray) read,
-    16 B hit record + 4 B material-queue index written).  The sphere and mesh-AABB tests of SURVEY.md section 8(d)
+    64 B of queue / path-record traffic: 4 B queue index + the 32-byte path record read; the 32-byte pending-hit record (or
+    16 B of radiance on a miss) + 4 B material-queue index written — up to 72 B, still charged as the 64 B of the earlier
+    40 + 16-byte record so that the figure stays comparable and conservative).  The sphere and mesh-AABB tests of SURVEY.md section 8(d)
     (16 S + 24 M per ray) run in the producing kernels (k_generate / k_shade) and are not charged to this kernel."""
     return 64 * st["node_visits"] + 48 * st["tri_tests"] + 64 * st["traversed_rays"]      # counts of k_trace only (tail kernel subtracted by the caller)
 
