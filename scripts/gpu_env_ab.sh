@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of a run-time knob: scripts/exp.py per workload in $WLS with and without the environment assignment $1 (e.g. RBRT_TWO_SECTOR_CAMERA_RECORDS=1), twice
+# A/B of a run-time knob: scripts/exp.py per workload in $WLS with and without the environment assignment $1 (e.g. RBRT_NO_PRIMARY_CULL=1), twice
 mkdir -p gpurun_out; out=gpurun_out/r2_exp_env_ab.jsonl; : > $out
 for rep in 1 2; do for wl in ${WLS:-c3}; do
   python scripts/exp.py $wl default | grep "^{" >> $out 2>> gpurun_out/r2_exp_env_ab.err

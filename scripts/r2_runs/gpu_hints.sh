@@ -1,5 +1,5 @@
 #!/bin/bash
-# L2 cache-hint experiment (RBRT_HINTS bit mask, csrc/Makefile `variant`): C3 through scripts/exp.py, one line per variant.
+# L2 cache-hint experiment of round 2 (needed the RBRT_HINTS bit-mask macro of that commit; only the node hint was kept, as RBRT_NODE_L2_EVICT_LAST): C3 through scripts/exp.py, one line per variant.
 mkdir -p gpurun_out; : > gpurun_out/r2_exp_l2_hints.jsonl
 python scripts/exp.py c3 base >> gpurun_out/r2_exp_l2_hints.jsonl 2>> gpurun_out/r2_exp_l2_hints.err
 for h in ${HINTS:-1 5 13 15 7}; do
