@@ -5,6 +5,7 @@ ImageBuffer (RGB8, row-major, `.save(path)`), like `image::ImageBuffer<Rgb<u8>, 
 All buffers that cross this call are HOST buffers; device copies happen inside the library.
 """
 import os
+import struct
 
 import numpy as np
 
@@ -35,6 +36,17 @@ class ImageBuffer:
             data = encode_png(self.pixels)
         elif ext in (".ppm", ".pnm"):
             data = b"P6\n%d %d\n255\n" % (self.width, self.height) + self.pixels.tobytes()
+        elif ext == ".bmp":                                  # 24-bit BI_RGB: bottom-up rows of BGR, padded to 4 bytes (as rbrt_cli.cpp)
+            w, h = self.width, self.height
+            stride = (3 * w + 3) & ~3
+            rows = np.zeros((h, stride), np.uint8)
+            rows[:, :3 * w] = self.pixels[::-1, :, ::-1].reshape(h, 3 * w)
+            hdr = struct.pack("<2sIII", b"BM", 54 + stride * h, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, 24, 0, stride * h, 2835, 2835, 0, 0)
+            data = hdr + rows.tobytes()
+        elif ext == ".tga":                                  # uncompressed true-colour, top-left origin, BGR
+            if self.width > 65535 or self.height > 65535:
+                raise ValueError(f"Unable to save target img to {path}! image too large for TGA")
+            data = struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, self.width, self.height, 24, 0x20) + np.ascontiguousarray(self.pixels[:, :, ::-1]).tobytes()
         else:
             raise ValueError(f"Unable to save target img to {path}! unsupported extension {ext!r}")
         with open(path, "wb") as f:

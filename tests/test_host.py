@@ -142,6 +142,28 @@ def test_png_round_trip(tmp_path):
     assert R.ImageBuffer(img).get_pixel(5, 7) == tuple(int(v) for v in img[7, 5])   # (x, y) like image::ImageBuffer
 
 
+def test_bmp_and_tga_hold_the_same_pixels(tmp_path):
+    """The other lossless formats `image::save` picks by extension (main.rs:86); same byte layout as the C++ CLI's writers
+    (tests/test_cli_cpp.py decodes those the same way)."""
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, size=(10, 13, 3), dtype=np.uint8)       # 13 px: BMP rows need 1 byte of padding
+    b, t = tmp_path / "o.bmp", tmp_path / "o.tga"
+    R.ImageBuffer(img).save(str(b)); R.ImageBuffer(img).save(str(t))
+    bmp, tga = b.read_bytes(), t.read_bytes()
+    stride = (3 * 13 + 3) & ~3
+    assert bmp[:2] == b"BM" and len(bmp) == 54 + stride * 10 and int.from_bytes(bmp[2:6], "little") == len(bmp) and int.from_bytes(bmp[10:14], "little") == 54
+    assert int.from_bytes(bmp[18:22], "little") == 13 and int.from_bytes(bmp[22:26], "little") == 10 and int.from_bytes(bmp[28:30], "little") == 24
+    assert np.array_equal(np.frombuffer(bmp[54:], np.uint8).reshape(10, stride)[::-1, :39].reshape(10, 13, 3)[:, :, ::-1], img)
+    assert len(tga) == 18 + 390 and tga[2] == 2 and tga[12:16] == bytes([13, 0, 10, 0]) and tga[16] == 24 and tga[17] == 0x20
+    assert np.array_equal(np.frombuffer(tga[18:], np.uint8).reshape(10, 13, 3)[:, :, ::-1], img)
+    try:
+        from PIL import Image
+        for f in (b, t):
+            assert np.array_equal(np.asarray(Image.open(str(f)).convert("RGB")), img)
+    except ImportError:
+        pass
+
+
 def test_camera_new_argument_order():
     cam = R.Camera.new(Vec3(0, 5, 4), Vec3(0, -0.1, -1), Vec3(0, 1, -0.4), 600, 800, 28.0)   # height BEFORE width
     assert (cam.img_height_pix, cam.img_width_pix) == (600, 800) and cam.img_width_mm == 35.0
