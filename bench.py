@@ -268,6 +268,7 @@ def run_reference(args):
     def oracle_transform(ptr, n_vertices, scale, rot_c, tr_c):
         O.check(O.lib().rbrt_ref_transform_vertices(ptr, n_vertices, scale, rot_c, tr_c))
     M._transform_in_place = oracle_transform
+    M._load_obj_soup = M.load_obj_soup_python                             # the product's loader is in librbrt_gpu.so
     desc, W, H, spp = WORKLOADS[args.workload]
     spheres, meshes, camkw = build_workload(args.workload)
     O, osc = oracle_scene(spheres, meshes)

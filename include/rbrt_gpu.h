@@ -212,6 +212,18 @@ int rbrt_camera_new(rbrt_vec3 position, rbrt_vec3 look_at, rbrt_vec3 up,
 int rbrt_transform_vertices(float* xyz, uint64_t n_vertices, float scale,
                             rbrt_vec3 rotation_rad, rbrt_vec3 translation);
 
+/* = load_mesh_vertices_from_file(filepath, translation, rotation, scale) (mesh.rs:78-121): reads the
+ *   .obj the way the reference consumes tobj 4's default output (every model's position indices cut
+ *   into triples; `f` and `l` records, `o` / `g` / `usemtl` model boundaries, relative indices; see
+ *   csrc/obj_loader.cpp), applies the transform above to every corner and returns a malloc'ed
+ *   num_triangles x 9 f32 soup (*tri_vertices_out = NULL for none) — what rbrt_mesh_desc.tri_vertices
+ *   takes.  Free it with rbrt_mesh_free.  Where the reference panics (`assert!(loaded_mesh.is_ok())`,
+ *   mesh.rs:89: unreadable file, malformed record, index out of bounds) this returns RBRT_E_INVALID
+ *   and rbrt_last_error() names the line.  Parses on all host threads (RBRT_HOST_THREADS caps them). */
+int rbrt_mesh_load_obj(const char* filepath, rbrt_vec3 translation, rbrt_vec3 rotation_rad, float scale,
+                       float** tri_vertices_out, uint64_t* num_triangles_out);
+void rbrt_mesh_free(float* tri_vertices);
+
 /* ---- GPU entry points ------------------------------------------------------------------- */
 
 /* Select the CUDA device this process renders on (one process per GPU). */

@@ -54,6 +54,10 @@ extern "C" {
     pub fn rbrt_camera_new(position: RbrtVec3, look_at: RbrtVec3, up: RbrtVec3, img_height_pix: u32, img_width_pix: u32,
                            focal_len_mm: f32, out: *mut RbrtCamera) -> c_int;
     pub fn rbrt_transform_vertices(xyz: *mut f32, n_vertices: u64, scale: f32, rotation_rad: RbrtVec3, translation: RbrtVec3) -> c_int;
+    /// = load_mesh_vertices_from_file (mesh.rs:78-121): .obj -> transformed triangle soup (num_triangles x 9 f32, malloc'ed; rbrt_mesh_free).
+    pub fn rbrt_mesh_load_obj(filepath: *const c_char, translation: RbrtVec3, rotation_rad: RbrtVec3, scale: f32,
+                              tri_vertices_out: *mut *mut f32, num_triangles_out: *mut u64) -> c_int;
+    pub fn rbrt_mesh_free(tri_vertices: *mut f32);
     pub fn rbrt_gpu_init(device: c_int) -> c_int;
     /// Multi-GPU inside the library: one process driving n GPUs (devices = null: 0..n-1) ...
     pub fn rbrt_gpu_init_multi(devices: *const c_int, n_devices: c_int, transport: c_int) -> c_int;

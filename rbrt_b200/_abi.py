@@ -122,6 +122,8 @@ P = C.POINTER
 GPU_SIGNATURES = {
     "rbrt_camera_new": (C.c_int, [Vec3C, Vec3C, Vec3C, C.c_uint32, C.c_uint32, C.c_float, P(CameraC)]),
     "rbrt_transform_vertices": (C.c_int, [P(C.c_float), C.c_uint64, C.c_float, Vec3C, Vec3C]),
+    "rbrt_mesh_load_obj": (C.c_int, [C.c_char_p, Vec3C, Vec3C, C.c_float, P(P(C.c_float)), P(C.c_uint64)]),
+    "rbrt_mesh_free": (None, [P(C.c_float)]),
     "rbrt_gpu_init": (C.c_int, [C.c_int]),
     "rbrt_gpu_init_multi": (C.c_int, [P(C.c_int), C.c_int, C.c_int]),
     "rbrt_gpu_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -7,8 +7,8 @@
 //
 // Third-party pieces of the reference that are re-stated here, host-side and outside the hot path (parity unpinned by the
 // reference's tests): serde_yaml 0.9 -> a parser for the block-style YAML subset the scene files use (nested mappings by
-// indentation, `- ` sequences, scalars, `#` comments, `---`); tobj 4 -> `v` / `f` records, one model per `o`/`g`, position
-// indices only, faces consumed as index triples (tobj default LoadOptions: no triangulation); image 0.25 -> an 8-bit RGB
+// indentation, `- ` sequences, scalars, `#` comments, `---`); tobj 4 -> the library's rbrt_mesh_load_obj (csrc/obj_loader.cpp:
+// `v` / `f` / `l` records, models per `o` / `g` / `usemtl`, faces consumed as index triples, no triangulation); image 0.25 -> an 8-bit RGB
 // PNG written with zlib (lossless, so any conforming encoder stores the same pixels), binary PPM, 24-bit BMP or uncompressed TGA by extension.
 #include <zlib.h>
 
@@ -215,37 +215,20 @@ bool create_material_from_description(const MaterialBp& m, rbrt_material* out) {
 }
 
 // ------------------------------------------------------------------ mesh.rs:78-121
-std::vector<float> load_mesh_vertices_from_file(const std::string& path, rbrt_vec3 translation, rbrt_vec3 rotation, float scale) {
-    std::ifstream f(path);
-    if (!f) die("assertion failed: loaded_mesh.is_ok() (cannot open " + path + ")");   // mesh.rs:89
-    std::vector<float> pos;
-    std::vector<std::vector<long>> models(1);
-    std::string line;
-    while (std::getline(f, line)) {
-        std::istringstream ss(line);
-        std::string tag;
-        if (!(ss >> tag)) continue;
-        if (tag == "v") { float x, y, z; if (ss >> x >> y >> z) { pos.push_back(x); pos.push_back(y); pos.push_back(z); } }
-        else if (tag == "f") {
-            std::string tok;
-            while (ss >> tok) {
-                long i = strtol(tok.c_str(), nullptr, 10);       // "v", "v/vt", "v//vn", "v/vt/vn": the leading integer
-                models.back().push_back(i > 0 ? i - 1 : (long)(pos.size() / 3) + i);
-            }
-        } else if ((tag == "o" || tag == "g") && !models.back().empty()) models.emplace_back();
-    }
-    std::vector<float> tris;
-    const long nv = (long)(pos.size() / 3);
-    for (auto& m : models)
-        for (size_t t = 0; t + 2 < m.size() + 0 && t / 3 < m.size() / 3; t += 3)
-            for (int k = 0; k < 3; ++k) {
-                long i = m[t + k];
-                if (i < 0 || i >= nv) die(path + ": face index out of range");
-                tris.push_back(pos[3 * i]); tris.push_back(pos[3 * i + 1]); tris.push_back(pos[3 * i + 2]);
-            }
-    if (!tris.empty() && rbrt_transform_vertices(tris.data(), tris.size() / 3, scale, rotation, translation) != RBRT_OK) die("rbrt_transform_vertices failed");
-    printf("Successfully loaded %zu triangles from file %s!\n", tris.size() / 9, path.c_str());   // mesh.rs:115-119
-    return tris;
+// The .obj reader and the vertex transform are the library's (rbrt_mesh_load_obj, csrc/obj_loader.cpp): tobj's records and
+// model boundaries, parsed on all host threads.  A load the reference would panic on (mesh.rs:89) ends the process the same way.
+struct Soup {
+    float* v = nullptr; uint64_t n = 0;
+    Soup() = default;
+    Soup(Soup&& o) noexcept : v(o.v), n(o.n) { o.v = nullptr; o.n = 0; }
+    Soup(const Soup&) = delete;
+    ~Soup() { rbrt_mesh_free(v); }
+};
+Soup load_mesh_vertices_from_file(const std::string& path, rbrt_vec3 translation, rbrt_vec3 rotation, float scale) {
+    Soup s;
+    if (rbrt_mesh_load_obj(path.c_str(), translation, rotation, scale, &s.v, &s.n) != RBRT_OK) die(std::string("assertion failed: loaded_mesh.is_ok() (") + rbrt_last_error() + ")");
+    printf("Successfully loaded %llu triangles from file %s!\n", (unsigned long long)s.n, path.c_str());   // mesh.rs:115-119
+    return s;
 }
 
 // ------------------------------------------------------------------ image save (main.rs:86)
@@ -363,15 +346,14 @@ int main(int argc, char** argv) {
     if (rbrt_camera_new(bp.position, bp.look_at, bp.up, height, width, bp.focal, &cam) != RBRT_OK) die("rbrt_camera_new failed");   // height BEFORE width (main.rs:71-78)
 
     // create_scene_from_scene_blueprint (blueprints.rs:132-158): meshes first, then spheres; unknown materials are skipped
-    std::vector<std::vector<float>> soups;
+    std::vector<Soup> soups;
     std::vector<rbrt_mesh_desc> meshes;
     for (auto& m : bp.meshes) {
         rbrt_material mat;
         if (!create_material_from_description(m.mat, &mat)) { printf("Failed to parse material info provided with mesh!\n"); continue; }
         soups.push_back(load_mesh_vertices_from_file(m.obj, m.translation, m.rotation, m.scale));
-        meshes.push_back(rbrt_mesh_desc{nullptr, soups.back().size() / 9, mat});
+        meshes.push_back(rbrt_mesh_desc{soups.back().v, soups.back().n, mat});
     }
-    for (size_t i = 0; i < meshes.size(); ++i) meshes[i].tri_vertices = soups[i].data();
     std::vector<rbrt_sphere_desc> spheres;
     for (auto& s : bp.spheres) {
         rbrt_material mat;

@@ -1,6 +1,6 @@
-// host_math.cpp — the two pieces of rbrt_lib host arithmetic that feed the hot path and must be
-// bit-identical to the reference: Camera::new (cam.rs:22-62) and the per-vertex mesh transform of
-// load_mesh_vertices_from_file (mesh.rs:102-112, vec3.rs:139-155).  Plain f32, compiled with
+// host_math.cpp — rbrt_lib host arithmetic that feeds the hot path and must be bit-identical to the
+// reference: Camera::new (cam.rs:22-62).  (The per-vertex mesh transform of load_mesh_vertices_from_file,
+// mesh.rs:102-112 / vec3.rs:139-155, is in obj_loader.cpp.)  Plain f32, compiled with
 // -ffp-contract=off so no a*b+c is fused (Rust never contracts).
 #include <math.h>
 #include "../../include/rbrt_gpu.h"
@@ -39,16 +39,4 @@ extern "C" int rbrt_camera_new(rbrt_vec3 position, rbrt_vec3 look_at, rbrt_vec3 
     return RBRT_OK;
 }
 
-extern "C" int rbrt_transform_vertices(float* xyz, uint64_t n_vertices, float scale, rbrt_vec3 rot, rbrt_vec3 tr) {
-    if (n_vertices && !xyz) return RBRT_E_INVALID;
-    float s_x = sinf(rot.x), s_y = sinf(rot.y), s_z = sinf(rot.z);
-    float c_x = cosf(rot.x), c_y = cosf(rot.y), c_z = cosf(rot.z);
-    for (uint64_t i = 0; i < n_vertices; ++i) {
-        float x = xyz[3 * i] * scale, y = xyz[3 * i + 1] * scale, z = xyz[3 * i + 2] * scale;   // mesh.rs:102-106
-        float rx = (c_x * c_z - c_y * s_x * s_z) * x - (c_x * s_z + c_y * c_z * s_x) * y + s_x * s_y * z;   // vec3.rs:150-152
-        float ry = (c_z * s_x + c_x * c_y * s_z) * x + (c_x * c_y * c_z - s_x * s_z) * y - c_x * s_y * z;
-        float rz = s_y * s_z * x + c_z * s_y * y + c_y * z;
-        xyz[3 * i] = rx + tr.x; xyz[3 * i + 1] = ry + tr.y; xyz[3 * i + 2] = rz + tr.z;          // mesh.rs:108-112
-    }
-    return RBRT_OK;
-}
+// rbrt_transform_vertices (mesh.rs:102-112) lives in obj_loader.cpp, next to the loader that applies it.
