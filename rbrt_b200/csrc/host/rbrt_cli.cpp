@@ -6,8 +6,8 @@
 // rbrt_lib/src/mesh.rs:78-121, and the reference's messages.  The hot path is entirely inside librbrt_gpu.so.
 //
 // Third-party pieces of the reference that are re-stated here, host-side and outside the hot path (parity unpinned by the
-// reference's tests): serde_yaml 0.9 -> a parser for the block-style YAML subset the scene files use (nested mappings by
-// indentation, `- ` sequences, scalars, `#` comments, `---`); tobj 4 -> the library's rbrt_mesh_load_obj (csrc/obj_loader.cpp:
+// reference's tests): serde_yaml 0.9 -> scene_yaml.hpp (block and flow YAML, anchors, serde's struct / Option / f32 rules);
+// tobj 4 -> the library's rbrt_mesh_load_obj (csrc/obj_loader.cpp:
 // `v` / `f` / `l` records, models per `o` / `g` / `usemtl`, faces consumed as index triples, no triangulation); image 0.25 -> an 8-bit RGB
 // PNG written with zlib (lossless, so any conforming encoder stores the same pixels), binary PPM, 24-bit BMP or uncompressed TGA by extension.
 #include <zlib.h>
@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../../include/rbrt_gpu.h"
+#include "scene_yaml.hpp"
 
 namespace {
 
@@ -34,159 +35,19 @@ namespace {
     exit(101);
 }
 
-// ------------------------------------------------------------------ YAML subset
-struct Node {
-    enum Kind { Scalar, Map, Seq } kind = Scalar;
-    std::string scalar;
-    std::vector<std::pair<std::string, std::shared_ptr<Node>>> map;
-    std::vector<std::shared_ptr<Node>> seq;
-    const Node* get(const std::string& k) const {
-        for (auto& kv : map) if (kv.first == k) return kv.second.get();
-        return nullptr;
-    }
-};
-
-struct Line { int indent; std::string text; };
-
-std::string strip(const std::string& s) {
-    size_t a = 0, b = s.size();
-    while (a < b && isspace((unsigned char)s[a])) ++a;
-    while (b > a && isspace((unsigned char)s[b - 1])) --b;
-    return s.substr(a, b - a);
-}
-std::string unquote(std::string s) {
-    s = strip(s);
-    if (s.size() >= 2 && ((s.front() == '"' && s.back() == '"') || (s.front() == '\'' && s.back() == '\''))) return s.substr(1, s.size() - 2);
-    return s;
-}
-std::string strip_comment(const std::string& s) {
-    bool q1 = false, q2 = false;
-    for (size_t i = 0; i < s.size(); ++i) {
-        if (s[i] == '"' && !q1) q2 = !q2;
-        else if (s[i] == '\'' && !q2) q1 = !q1;
-        else if (s[i] == '#' && !q1 && !q2 && (i == 0 || isspace((unsigned char)s[i - 1]))) return s.substr(0, i);
-    }
-    return s;
-}
-
-std::shared_ptr<Node> parse_block(const std::vector<Line>& L, size_t& i, int indent);
-
-// value that follows "key:" — inline scalar, or a nested block on the following lines
-std::shared_ptr<Node> parse_value(const std::vector<Line>& L, size_t& i, const std::string& rest, int parent_indent) {
-    std::string r = strip(rest);
-    if (!r.empty()) { auto n = std::make_shared<Node>(); n->scalar = unquote(r); return n; }
-    if (i < L.size() && (L[i].indent > parent_indent || (L[i].indent == parent_indent && L[i].text.rfind("- ", 0) == 0)))
-        return parse_block(L, i, L[i].indent);
-    return std::make_shared<Node>();                        // empty value
-}
-
-std::shared_ptr<Node> parse_block(const std::vector<Line>& L, size_t& i, int indent) {
-    auto n = std::make_shared<Node>();
-    if (L[i].text.rfind("- ", 0) == 0 || L[i].text == "-") {
-        n->kind = Node::Seq;
-        while (i < L.size() && L[i].indent == indent && (L[i].text.rfind("- ", 0) == 0 || L[i].text == "-")) {
-            // rewrite "- key: v" as an item block whose first line is "key: v" indented by 2
-            std::vector<Line> item;
-            std::string first = L[i].text.size() > 2 ? L[i].text.substr(2) : "";
-            int item_indent = indent + 2;
-            size_t j = i + 1;
-            if (!strip(first).empty()) item.push_back(Line{item_indent, strip(first)});
-            while (j < L.size() && L[j].indent > indent) { item.push_back(L[j]); ++j; }
-            if (item.empty()) n->seq.push_back(std::make_shared<Node>());
-            else if (item.size() == 1 && item[0].text.find(':') == std::string::npos) { auto s = std::make_shared<Node>(); s->scalar = unquote(item[0].text); n->seq.push_back(s); }
-            else { size_t k = 0; n->seq.push_back(parse_block(item, k, item[0].indent)); }
-            i = j;
-        }
-        return n;
-    }
-    n->kind = Node::Map;
-    while (i < L.size() && L[i].indent == indent) {
-        const std::string& t = L[i].text;
-        size_t c = t.find(':');
-        if (c == std::string::npos) die("Unable to parse scene blueprint: expected `key: value`, got `" + t + "`");
-        std::string key = unquote(t.substr(0, c)), rest = t.substr(c + 1);
-        ++i;
-        n->map.emplace_back(key, parse_value(L, i, rest, indent));
-    }
-    return n;
-}
-
-std::shared_ptr<Node> parse_yaml(std::istream& in) {
-    std::vector<Line> L;
-    std::string raw;
-    while (std::getline(in, raw)) {
-        std::string s = strip_comment(raw);
-        if (strip(s).empty() || strip(s) == "---" || strip(s) == "...") continue;
-        int ind = 0;
-        while (ind < (int)s.size() && s[ind] == ' ') ++ind;
-        L.push_back(Line{ind, strip(s)});
-    }
-    if (L.empty()) die("Unable to parse scene blueprint: empty document");
-    size_t i = 0;
-    return parse_block(L, i, L[0].indent);
-}
-
-float as_f32(const Node* n, const char* what) {
-    if (!n || n->kind != Node::Scalar || n->scalar.empty()) die(std::string("Unable to parse scene blueprint: missing field `") + what + "`");
-    char* end = nullptr;
-    float v = strtof(n->scalar.c_str(), &end);
-    if (end == n->scalar.c_str()) die(std::string("Unable to parse scene blueprint: `") + what + "` is not a number");
-    return v;
-}
-rbrt_vec3 as_vec3(const Node* n, const char* what) {
-    if (!n || n->kind != Node::Map) die(std::string("Unable to parse scene blueprint: missing field `") + what + "`");
-    return rbrt_vec3{as_f32(n->get("x"), what), as_f32(n->get("y"), what), as_f32(n->get("z"), what)};
-}
-std::string as_str(const Node* n, const char* what) {
-    if (!n || n->kind != Node::Scalar) die(std::string("Unable to parse scene blueprint: missing field `") + what + "`");
-    return n->scalar;
-}
-
-// ------------------------------------------------------------------ blueprints.rs:15-48
-struct MaterialBp { std::string type; bool has_albedo = false; rbrt_vec3 albedo{0, 0, 0}; bool has_param = false; float param = 0; };
-struct MeshBp { std::string obj; float scale; rbrt_vec3 translation, rotation; MaterialBp mat; };
-struct SphereBp { float radius; rbrt_vec3 center; MaterialBp mat; };
-struct SceneBp { rbrt_vec3 up, look_at, position; float focal; std::vector<MeshBp> meshes; std::vector<SphereBp> spheres; };
-
-MaterialBp material_bp(const Node* n) {
-    MaterialBp m;
-    m.type = as_str(n->get("material_type"), "material_type");
-    if (const Node* a = n->get("albedo")) if (a->kind == Node::Map) { m.has_albedo = true; m.albedo = as_vec3(a, "albedo"); }
-    if (const Node* p = n->get("material_param")) if (p->kind == Node::Scalar && !p->scalar.empty() && p->scalar != "~" && p->scalar != "null") { m.has_param = true; m.param = as_f32(p, "material_param"); }
-    return m;
-}
+// ------------------------------------------------------------------ blueprints.rs:15-48,76-92 (scene_yaml.hpp)
+using scene_yaml::MaterialBp;
+using scene_yaml::SceneBp;
 
 SceneBp load_blueprints_from_yaml_file(const std::string& path) {   // blueprints.rs:76-92
-    std::ifstream f(path);
+    std::ifstream f(path, std::ios::binary);
     if (!f) die("Failed to open " + path + " to load content.");
-    auto root = parse_yaml(f);
-    if (root->kind != Node::Map) die("Unable to parse content of file " + path + " to scene blueprint");
-    SceneBp bp;
-    const Node* cam = root->get("camera_blueprint");
-    if (!cam) die("Unable to parse content of file " + path + " to scene blueprint: missing field `camera_blueprint`");
-    bp.up = as_vec3(cam->get("camera_up"), "camera_up");
-    bp.look_at = as_vec3(cam->get("camera_look_at"), "camera_look_at");
-    bp.position = as_vec3(cam->get("camera_position"), "camera_position");
-    bp.focal = as_f32(cam->get("camera_focal_length_mm"), "camera_focal_length_mm");
-    if (const Node* ms = root->get("mesh_blueprints"))
-        for (auto& it : ms->seq) {
-            MeshBp m;
-            m.obj = as_str(it->get("obj_filepath"), "obj_filepath");
-            m.scale = as_f32(it->get("scale"), "scale");
-            m.translation = as_vec3(it->get("translation"), "translation");
-            m.rotation = as_vec3(it->get("rotation_rad"), "rotation_rad");
-            m.mat = material_bp(it.get());
-            bp.meshes.push_back(m);
-        }
-    if (const Node* ss = root->get("sphere_blueprints"))
-        for (auto& it : ss->seq) {
-            SphereBp s;
-            s.radius = as_f32(it->get("radius"), "radius");
-            s.center = as_vec3(it->get("center"), "center");
-            s.mat = material_bp(it.get());
-            bp.spheres.push_back(s);
-        }
-    return bp;
+    std::stringstream buf; buf << f.rdbuf();
+    try {
+        return scene_yaml::parse_scene(buf.str());
+    } catch (const scene_yaml::ParseError& e) {
+        die("Unable to parse content of file \"" + path + "\" to scene blueprint: " + e.msg);
+    }
 }
 
 std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
@@ -296,6 +157,7 @@ void usage() {
            "      --gpus <n>                   (extension) render on the first n GPUs of this box: tile-sharded inside the library [default: 1]\n"
            "      --transport <auto|nccl|peer> (extension) how the GPUs exchange the scene and the image [default: auto]\n"
            "      --check                      (extension) parse the scene, print a summary and exit without rendering\n"
+           "      --dump                       (extension, with --check) also print every blueprint field as read (f32 bit patterns)\n"
            "  -h, --help                       Print help\n  -V, --version                    Print version\n");
 }
 
@@ -311,7 +173,7 @@ uint32_t parse_u32(const char* s, const char* what) {
 int main(int argc, char** argv) {
     std::string target = "dbg_out.png", config = "scenes/example_scene.yaml";      // main.rs:14-50
     uint32_t height = 600, width = 800, samples = 5;
-    uint64_t seed = 0; int device = 0; bool check_only = false;
+    uint64_t seed = 0; int device = 0; bool check_only = false, dump = false;
     uint32_t gpus = 1; int transport = RBRT_TRANSPORT_AUTO;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -336,12 +198,26 @@ int main(int argc, char** argv) {
             else die("error: invalid value '" + t + "' for '--transport' [possible values: auto, nccl, peer]");
         }
         else if (key == "--check") check_only = true;
+        else if (key == "--dump") dump = true;
         else if (key == "-h" || key == "--help") { usage(); return 0; }
         else if (key == "-V" || key == "--version") { printf("rbrt 0.1 (%s)\n", rbrt_gpu_version()); return 0; }
         else { fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str()); return 2; }
     }
 
     SceneBp bp = load_blueprints_from_yaml_file(config);
+    if (check_only && dump) {                                                      // what serde would have put into SceneBlueprint
+        auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+        auto v3 = [&](const char* name, rbrt_vec3 v) { printf("%s %08x %08x %08x\n", name, bits(v.x), bits(v.y), bits(v.z)); };
+        auto mat = [&](const MaterialBp& m) {
+            printf("material_type %zu:%s\n", m.type.size(), m.type.c_str());
+            if (m.has_albedo) v3("albedo", m.albedo); else printf("albedo None\n");
+            if (m.has_param) printf("material_param %08x\n", bits(m.param)); else printf("material_param None\n");
+        };
+        v3("camera_up", bp.up); v3("camera_look_at", bp.look_at); v3("camera_position", bp.position); printf("camera_focal_length_mm %08x\n", bits(bp.focal));
+        for (auto& m : bp.meshes) { printf("mesh\nobj_filepath %zu:%s\nscale %08x\n", m.obj.size(), m.obj.c_str(), bits(m.scale)); v3("translation", m.translation); v3("rotation_rad", m.rotation); mat(m.mat); }
+        for (auto& sp : bp.spheres) { printf("sphere\nradius %08x\n", bits(sp.radius)); v3("center", sp.center); mat(sp.mat); }
+        return 0;
+    }
     rbrt_camera cam;
     if (rbrt_camera_new(bp.position, bp.look_at, bp.up, height, width, bp.focal, &cam) != RBRT_OK) die("rbrt_camera_new failed");   // height BEFORE width (main.rs:71-78)
 
