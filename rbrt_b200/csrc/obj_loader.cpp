@@ -36,8 +36,11 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
+#include <new>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -234,12 +237,24 @@ unsigned host_threads() {
     return n ? std::min(n, 64u) : 1u;
 }
 
-template <class F> void parallel_for(uint64_t n, unsigned threads, F&& body) {      // body(begin, end)
+// body(begin, end) on `threads` host threads.  An exception in a worker (std::bad_alloc) is carried to the caller; when a thread
+// cannot be started the rest of the range runs on the calling thread.
+template <class F> void parallel_for(uint64_t n, unsigned threads, F&& body) {
     if (threads <= 1 || n < 2) { body((uint64_t)0, n); return; }
     threads = (unsigned)std::min<uint64_t>(threads, n);
     std::vector<std::thread> pool;
-    for (unsigned t = 0; t < threads; ++t) pool.emplace_back([&, t] { body(n * t / threads, n * (t + 1) / threads); });
+    pool.reserve(threads);                                                 // (so that only these two allocations can fail before any work has started)
+    std::vector<std::exception_ptr> errors(threads);
+    unsigned started = 0;
+    for (; started + 1 < threads; ++started) {
+        const unsigned t = started;
+        try {
+            pool.emplace_back([&, t] { try { body(n * t / threads, n * (t + 1) / threads); } catch (...) { errors[t] = std::current_exception(); } });
+        } catch (const std::system_error&) { break; }
+    }
+    try { body(n * started / threads, n); } catch (...) { errors[threads - 1] = std::current_exception(); }    // the caller takes the last share (and what no thread took)
     for (auto& th : pool) th.join();
+    for (auto& e : errors) if (e) std::rethrow_exception(e);
 }
 
 }  // namespace
@@ -248,14 +263,33 @@ extern "C" int rbrt_transform_vertices(float* xyz, uint64_t n_vertices, float sc
     if (n_vertices && !xyz) return RBRT_E_INVALID;
     const float sc[6] = {sinf(rot.x), sinf(rot.y), sinf(rot.z), cosf(rot.x), cosf(rot.y), cosf(rot.z)};
     // every vertex is independent: large soups are split over the host threads (same arithmetic per vertex)
-    parallel_for(n_vertices, n_vertices >= (1u << 16) ? host_threads() : 1, [&](uint64_t b, uint64_t e) { transform_range(xyz + 3 * b, e - b, scale, sc, tr); });
+    try {
+        parallel_for(n_vertices, n_vertices >= (1u << 16) ? host_threads() : 1, [&](uint64_t b, uint64_t e) { transform_range(xyz + 3 * b, e - b, scale, sc, tr); });
+    } catch (...) { transform_range(xyz, n_vertices, scale, sc, tr); }               // transform_range cannot throw: this is parallel_for failing to allocate, before any vertex was touched
     return RBRT_OK;
 }
 
 extern "C" void rbrt_mesh_free(float* tri_vertices) { free(tri_vertices); }
 
+static int load_obj(const char* filepath, rbrt_vec3 translation, rbrt_vec3 rotation_rad, float scale, float** tri_vertices_out, uint64_t* num_triangles_out);
+
 extern "C" int rbrt_mesh_load_obj(const char* filepath, rbrt_vec3 translation, rbrt_vec3 rotation_rad, float scale,
                                   float** tri_vertices_out, uint64_t* num_triangles_out) {
+    try {                                                                             // the C-ABI never unwinds
+        return load_obj(filepath, translation, rotation_rad, scale, tri_vertices_out, num_triangles_out);
+    } catch (const std::bad_alloc&) {
+        rbrt::set_error("out of host memory while reading %s", filepath ? filepath : "(null)");
+    } catch (const std::exception& e) {
+        rbrt::set_error("%s: %s", filepath ? filepath : "(null)", e.what());
+    } catch (...) {
+        rbrt::set_error("%s: unknown failure", filepath ? filepath : "(null)");
+    }
+    if (tri_vertices_out && *tri_vertices_out) { free(*tri_vertices_out); *tri_vertices_out = nullptr; }
+    if (num_triangles_out) *num_triangles_out = 0;
+    return RBRT_E_ALLOC;
+}
+
+static int load_obj(const char* filepath, rbrt_vec3 translation, rbrt_vec3 rotation_rad, float scale, float** tri_vertices_out, uint64_t* num_triangles_out) {
     if (!filepath || !tri_vertices_out || !num_triangles_out) { rbrt::set_error("null argument"); return RBRT_E_INVALID; }
     *tri_vertices_out = nullptr; *num_triangles_out = 0;
     int fd = open(filepath, O_RDONLY);
@@ -386,6 +420,7 @@ extern "C" int rbrt_mesh_load_obj(const char* filepath, rbrt_vec3 translation, r
     if (!n_tris) return RBRT_OK;
     float* out = (float*)malloc(sizeof(float) * 9 * n_tris);
     if (!out) { rbrt::set_error("out of host memory for %llu triangles", (unsigned long long)n_tris); return RBRT_E_ALLOC; }
+    *tri_vertices_out = out;                                              // (the wrapper frees it should the gather throw)
     const float sc[6] = {sinf(rotation_rad.x), sinf(rotation_rad.y), sinf(rotation_rad.z), cosf(rotation_rad.x), cosf(rotation_rad.y), cosf(rotation_rad.z)};
     parallel_for(n_tris, n_tris >= (1u << 14) ? threads : 1, [&](uint64_t tb, uint64_t te) {
         size_t m = (size_t)(std::upper_bound(tri_base.begin(), tri_base.end(), tb) - tri_base.begin()) - 1;
@@ -404,6 +439,6 @@ extern "C" int rbrt_mesh_load_obj(const char* filepath, rbrt_vec3 translation, r
         }
         transform_range(out + 9 * tb, 3 * (te - tb), scale, sc, translation);
     });
-    *tri_vertices_out = out; *num_triangles_out = n_tris;
+    *num_triangles_out = n_tris;
     return RBRT_OK;
 }

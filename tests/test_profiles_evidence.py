@@ -63,3 +63,20 @@ def test_reference_arm_line_did_not_load_the_product_library():
     assert r["impl"] == "reference" and r["product_lib_loaded"] is False and r["metric"] == "Mrays/s"
     assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["d2h_bytes_per_step"] == 0 and r["e2e"]["value"] == r["value"]
     assert r["cpu_baseline"]["value"] == r["value"]
+
+
+def test_device_code_is_the_gpu_verified_build():
+    """Commits after the round's last GPU run only touched host code: the SASS of the library in the tree is still the SASS of the build that
+    passed the GPU tests and produced the committed bench lines (profiles/r2_device_code.md)."""
+    import hashlib
+    import re
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib = os.path.join(ROOT, "rbrt_b200", "librbrt_gpu.so")
+    if not os.path.exists(cuobjdump) or not os.path.exists(lib):
+        pytest.skip("cuobjdump or the built library is not here")
+    with open(os.path.join(PROF, "r2_device_code.md")) as f:
+        want = re.search(r"^\s+([0-9a-f]{32})\s*$", f.read(), re.M).group(1)
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    got = hashlib.md5("".join(ln + "\n" for ln in sass.splitlines() if not ln.startswith("identifier = ")).encode()).hexdigest()
+    assert got == want, "device code differs from the GPU-verified build: re-run pytest -m gpu and the bench, then update profiles/r2_device_code.md"
