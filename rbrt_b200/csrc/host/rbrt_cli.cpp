@@ -9,7 +9,7 @@
 // reference's tests): serde_yaml 0.9 -> scene_yaml.hpp (block and flow YAML, anchors, serde's struct / Option / f32 rules);
 // tobj 4 -> the library's rbrt_mesh_load_obj (csrc/obj_loader.cpp:
 // `v` / `f` / `l` records, models per `o` / `g` / `usemtl`, faces consumed as index triples, no triangulation); image 0.25 -> an 8-bit RGB
-// PNG written with zlib (lossless, so any conforming encoder stores the same pixels), binary PPM, 24-bit BMP or uncompressed TGA by extension.
+// PNG written with zlib (lossless, so any conforming encoder stores the same pixels), binary PPM, 24-bit BMP, uncompressed TGA, baseline TIFF or QOI by extension.
 #include <zlib.h>
 
 #include <cctype>
@@ -138,6 +138,48 @@ bool save_image(const std::string& path, const std::vector<uint8_t>& rgb, uint32
         if (w > 65535 || h > 65535) return false;
         out.insert(out.end(), hdr, hdr + 18);
         for (size_t i = 0; i < (size_t)w * h; ++i) { out.push_back(rgb[3 * i + 2]); out.push_back(rgb[3 * i + 1]); out.push_back(rgb[3 * i]); }
+    } else if (ext == ".tif" || ext == ".tiff") {                // baseline TIFF 6.0: little-endian, one uncompressed RGB strip, IFD after it
+        const uint64_t n64 = 3ull * w * h;
+        if (n64 > 0xFFFFF000ull) return false;
+        const uint32_t n = (uint32_t)n64, ifd_at = 8 + n + (n & 1), bits_at = ifd_at + 2 + 10 * 12 + 4;
+        auto le16 = [&](uint32_t x) { out.push_back((uint8_t)x); out.push_back((uint8_t)(x >> 8)); };
+        auto le32 = [&](uint32_t x) { for (int s = 0; s < 32; s += 8) out.push_back((uint8_t)(x >> s)); };
+        auto tag = [&](uint32_t t, uint32_t type, uint32_t count, uint32_t value) { le16(t); le16(type); le32(count); le32(value); };
+        out.push_back('I'); out.push_back('I'); le16(42); le32(ifd_at);
+        out.insert(out.end(), rgb.begin(), rgb.end());
+        if (n & 1) out.push_back(0);
+        le16(10);
+        tag(256, 4, 1, w); tag(257, 4, 1, h); tag(258, 3, 3, bits_at); tag(259, 3, 1, 1); tag(262, 3, 1, 2); tag(273, 4, 1, 8); tag(277, 3, 1, 3);
+        tag(278, 4, 1, h); tag(279, 4, 1, n); tag(284, 3, 1, 1);
+        le32(0);
+        le16(8); le16(8); le16(8);
+    } else if (ext == ".qoi") {                                  // qoiformat.org, 3 channels: run / index / diff / luma / rgb
+        const uint8_t hdr[14] = {'q', 'o', 'i', 'f', (uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
+                                 (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 3, 0};
+        out.insert(out.end(), hdr, hdr + 14);
+        uint8_t index[64][4] = {};                                 // RGBA, all zero at the start: an untouched slot (alpha 0) never equals a pixel (alpha 255)
+        uint8_t pr = 0, pg = 0, pb = 0; int run = 0;
+        const size_t px = (size_t)w * h;
+        for (size_t i = 0; i < px; ++i) {
+            const uint8_t r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+            if (r == pr && g == pg && b == pb) {
+                if (++run == 62 || i + 1 == px) { out.push_back((uint8_t)(0xC0 | (run - 1))); run = 0; }
+                continue;
+            }
+            if (run) { out.push_back((uint8_t)(0xC0 | (run - 1))); run = 0; }
+            const int k = (r * 3 + g * 5 + b * 7 + 255 * 11) % 64;
+            if (index[k][0] == r && index[k][1] == g && index[k][2] == b && index[k][3] == 255) out.push_back((uint8_t)k);
+            else {
+                index[k][0] = r; index[k][1] = g; index[k][2] = b; index[k][3] = 255;
+                const int dr = (int8_t)(r - pr), dg = (int8_t)(g - pg), db = (int8_t)(b - pb);
+                if (dr >= -2 && dr <= 1 && dg >= -2 && dg <= 1 && db >= -2 && db <= 1) out.push_back((uint8_t)(0x40 | (dr + 2) << 4 | (dg + 2) << 2 | (db + 2)));
+                else if (dg >= -32 && dg <= 31 && dr - dg >= -8 && dr - dg <= 7 && db - dg >= -8 && db - dg <= 7) { out.push_back((uint8_t)(0x80 | (dg + 32))); out.push_back((uint8_t)((dr - dg + 8) << 4 | (db - dg + 8))); }
+                else { out.push_back(0xFE); out.push_back(r); out.push_back(g); out.push_back(b); }
+            }
+            pr = r; pg = g; pb = b;
+        }
+        for (int i = 0; i < 7; ++i) out.push_back(0);
+        out.push_back(1);
     } else return false;                                         // lossy formats of the `image` crate (jpeg, ...) are not offered
     FILE* fp = fopen(path.c_str(), "wb");
     if (!fp) return false;
@@ -158,6 +200,7 @@ void usage() {
            "      --transport <auto|nccl|peer> (extension) how the GPUs exchange the scene and the image [default: auto]\n"
            "      --check                      (extension) parse the scene, print a summary and exit without rendering\n"
            "      --dump                       (extension, with --check) also print every blueprint field as read (f32 bit patterns)\n"
+           "      --from-ppm <file>            (extension) no rendering: read a binary PPM (P6) and save it as --target_file (format by extension)\n"
            "  -h, --help                       Print help\n  -V, --version                    Print version\n");
 }
 
@@ -175,6 +218,7 @@ int main(int argc, char** argv) {
     uint32_t height = 600, width = 800, samples = 5;
     uint64_t seed = 0; int device = 0; bool check_only = false, dump = false;
     uint32_t gpus = 1; int transport = RBRT_TRANSPORT_AUTO;
+    std::string from_ppm;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto value = [&](const char* name) -> const char* {
@@ -199,11 +243,23 @@ int main(int argc, char** argv) {
         }
         else if (key == "--check") check_only = true;
         else if (key == "--dump") dump = true;
+        else if (key == "--from-ppm") from_ppm = value("--from-ppm");
         else if (key == "-h" || key == "--help") { usage(); return 0; }
         else if (key == "-V" || key == "--version") { printf("rbrt 0.1 (%s)\n", rbrt_gpu_version()); return 0; }
         else { fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str()); return 2; }
     }
 
+    if (!from_ppm.empty()) {                                                        // the image writers on their own (main.rs:84-91)
+        std::ifstream f(from_ppm, std::ios::binary);
+        std::string magic; uint32_t w = 0, h = 0, maxv = 0;
+        if (!(f >> magic >> w >> h >> maxv) || magic != "P6" || maxv != 255 || !w || !h) die("cannot read " + from_ppm + " as a binary PPM");
+        f.get();
+        std::vector<uint8_t> rgb((size_t)w * h * 3);
+        if (!f.read((char*)rgb.data(), (std::streamsize)rgb.size())) die("cannot read " + from_ppm + " as a binary PPM");
+        printf("Saving rendered image to %s\n", target.c_str());
+        if (!save_image(target, rgb, w, h)) die("Unable to save target img to " + target + "! Maybe the directory does not exist?");
+        return 0;
+    }
     SceneBp bp = load_blueprints_from_yaml_file(config);
     if (check_only && dump) {                                                      // what serde would have put into SceneBlueprint
         auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };

@@ -47,10 +47,59 @@ class ImageBuffer:
             if self.width > 65535 or self.height > 65535:
                 raise ValueError(f"Unable to save target img to {path}! image too large for TGA")
             data = struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, self.width, self.height, 24, 0x20) + np.ascontiguousarray(self.pixels[:, :, ::-1]).tobytes()
+        elif ext in (".tif", ".tiff"):                       # baseline TIFF: little-endian, one uncompressed RGB strip
+            data = encode_tiff(self.pixels)
+        elif ext == ".qoi":
+            data = encode_qoi(self.pixels)
         else:
             raise ValueError(f"Unable to save target img to {path}! unsupported extension {ext!r}")
         with open(path, "wb") as f:
             f.write(data)
+
+
+def encode_tiff(pixels):
+    """Baseline TIFF 6.0 (as rbrt_cli.cpp writes it): header, the pixel strip, then the IFD with the ten required RGB tags."""
+    h, w = pixels.shape[:2]
+    n = 3 * w * h
+    ifd_at = 8 + n + (n & 1)
+    bits_at = ifd_at + 2 + 10 * 12 + 4
+    tags = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 3, bits_at), (259, 3, 1, 1), (262, 3, 1, 2), (273, 4, 1, 8), (277, 3, 1, 3),
+            (278, 4, 1, h), (279, 4, 1, n), (284, 3, 1, 1)]
+    ifd = struct.pack("<H", len(tags)) + b"".join(struct.pack("<HHII", t, ty, c, v) for t, ty, c, v in tags) + struct.pack("<I", 0)
+    return struct.pack("<2sHI", b"II", 42, ifd_at) + pixels.tobytes() + b"\0" * (n & 1) + ifd + struct.pack("<HHH", 8, 8, 8)
+
+
+def encode_qoi(pixels):
+    """QOI (qoiformat.org), 3 channels: the ops in the encoder's usual order run / index / diff / luma / rgb (as rbrt_cli.cpp)."""
+    h, w = pixels.shape[:2]
+    out = bytearray(struct.pack(">4sIIBB", b"qoif", w, h, 3, 0))
+    index = [None] * 64                                      # (slots start as RGBA 0,0,0,0: they never equal a pixel, whose alpha is 255)
+    pr, pg, pb = 0, 0, 0
+    run = 0
+    flat = pixels.reshape(-1, 3).tolist()
+    last = len(flat) - 1
+    for i, (r, g, b) in enumerate(flat):
+        if (r, g, b) == (pr, pg, pb):
+            run += 1
+            if run == 62 or i == last:
+                out.append(0xC0 | (run - 1)); run = 0
+            continue
+        if run:
+            out.append(0xC0 | (run - 1)); run = 0
+        k = (r * 3 + g * 5 + b * 7 + 255 * 11) % 64
+        if index[k] == (r, g, b):
+            out.append(k)
+        else:
+            index[k] = (r, g, b)
+            dr, dg, db = ((r - pr + 128) & 255) - 128, ((g - pg + 128) & 255) - 128, ((b - pb + 128) & 255) - 128
+            if -2 <= dr <= 1 and -2 <= dg <= 1 and -2 <= db <= 1:
+                out.append(0x40 | (dr + 2) << 4 | (dg + 2) << 2 | (db + 2))
+            elif -32 <= dg <= 31 and -8 <= dr - dg <= 7 and -8 <= db - dg <= 7:
+                out += bytes((0x80 | (dg + 32), (dr - dg + 8) << 4 | (db - dg + 8)))
+            else:
+                out += bytes((0xFE, r, g, b))
+        pr, pg, pb = r, g, b
+    return bytes(out) + b"\0" * 7 + b"\1"
 
 
 def make_opts(seed=0, max_depth=0, trace_mode=_abi.TRACE_BVH, shard_mode=_abi.SHARD_NONE, shard_rank=0, shard_count=0,

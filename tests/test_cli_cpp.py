@@ -113,6 +113,30 @@ def test_cli_parses_scene_like_the_python_mirror(cli, tmp_path):
     assert len(bp.sphere_blueprints) == 3 and len(bp.mesh_blueprints) == 1
 
 
+def test_cli_image_writers_hold_the_pixels(cli, tmp_path):
+    """The CLI's writers for every format it offers (main.rs:86: `image::save` picks by extension), without a GPU: `--from-ppm` feeds them an
+    image; PNG, BMP, TGA, TIFF and QOI files decode (PIL) to the same pixels, and the Python mirror writes byte-identical BMP / TGA / TIFF / QOI."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    smooth = (np.cumsum(rng.integers(-3, 4, size=(40, 31, 3)), axis=1) % 256).astype(np.uint8)
+    smooth[5:9] = 0; smooth[20:23, 4:20] = smooth[20, 3]
+    palette = rng.integers(0, 256, size=(5, 3), dtype=np.uint8)[rng.integers(0, 5, size=(16, 16))]
+    for k, img in enumerate((rng.integers(0, 256, size=(10, 13, 3), dtype=np.uint8), smooth, palette, np.zeros((3, 70, 3), np.uint8))):
+        src = str(tmp_path / f"in{k}.ppm")
+        R.ImageBuffer(img).save(src)
+        for ext in ("png", "ppm", "bmp", "tga", "tif", "tiff", "qoi"):
+            out = str(tmp_path / f"o{k}.{ext}")
+            r = subprocess.run([cli, "--from-ppm", src, "-t", out], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), img), (k, ext)
+            if ext not in ("png",):                                                  # (zlib streams may differ; the pixels may not)
+                mine = str(tmp_path / f"p{k}.{ext}")
+                R.ImageBuffer(img).save(mine)
+                assert open(mine, "rb").read() == open(out, "rb").read(), (k, ext)
+    lossy = subprocess.run([cli, "--from-ppm", src, "-t", str(tmp_path / "o.jpg")], capture_output=True, text=True)
+    assert lossy.returncode == 101 and "Unable to save target img" in lossy.stderr   # main.rs:86-91
+
+
 def test_cli_missing_fields_are_fatal(cli, tmp_path):
     y, _ = write_scene(tmp_path)
     txt = open(y).read().replace("    material_param: 0.005\n", "")

@@ -164,6 +164,24 @@ def test_bmp_and_tga_hold_the_same_pixels(tmp_path):
         pass
 
 
+def test_tiff_and_qoi_hold_the_same_pixels(tmp_path):
+    """Two more lossless formats of `image::save`; decoded here with PIL.  The images have runs, repeats, small and large steps and black
+    pixels so that every QOI op is written (run, index, diff, luma, rgb)."""
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    noise = rng.integers(0, 256, size=(9, 11, 3), dtype=np.uint8)
+    smooth = (np.cumsum(rng.integers(-3, 4, size=(40, 31, 3)), axis=1) % 256).astype(np.uint8)       # diff / luma ops
+    smooth[5:9] = 0; smooth[20:23, 4:20] = smooth[20, 3]                                             # runs (also > 62 long), black after colour
+    palette = rng.integers(0, 256, size=(5, 3), dtype=np.uint8)[rng.integers(0, 5, size=(16, 16))]   # index ops
+    for k, img in enumerate((noise, smooth, palette, np.zeros((3, 70, 3), np.uint8), np.full((1, 1, 3), 7, np.uint8))):
+        for ext in ("tif", "tiff", "qoi"):
+            f = tmp_path / f"o{k}.{ext}"
+            R.ImageBuffer(img).save(str(f))
+            assert np.array_equal(np.asarray(Image.open(str(f)).convert("RGB")), img), (k, ext)
+    ops = (tmp_path / "o1.qoi").read_bytes()[14:-8]
+    assert any(b >> 6 == 3 and b < 0xFE for b in ops) and any(b >> 6 == 1 for b in ops) and any(b >> 6 == 2 for b in ops)
+
+
 def test_camera_new_argument_order():
     cam = R.Camera.new(Vec3(0, 5, 4), Vec3(0, -0.1, -1), Vec3(0, 1, -0.4), 600, 800, 28.0)   # height BEFORE width
     assert (cam.img_height_pix, cam.img_width_pix) == (600, 800) and cam.img_width_mm == 35.0
