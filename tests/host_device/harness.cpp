@@ -1,0 +1,190 @@
+// harness.cpp — TEST INFRASTRUCTURE (tests/test_device_source_on_host.py): the product's device headers compiled for the host.
+//
+// rbrt_b200/csrc/{common,intersect,shade}.cuh hold the per-ray arithmetic of the hot path — Scene::hit with its sphere,
+// BasicTriangle, bounding-box and Moeller-Trumbore tests, camera rays, the three scatter()s, Philox, sky, `as u8`.  Here those
+// headers are compiled by g++ (-ffp-contract=off, the cuda_runtime.h stand-in of this directory) and driven by the plainest
+// possible loop: one ray at a time, brute force over the triangles (`scene_hit<true>`, the kernel `rbrt_gpu_trace_rays` runs
+// in RBRT_TRACE_BRUTE mode), recursion of lib.rs:43-73 unrolled into a loop.  The tests compare the result bit for bit with
+// the oracle and the golden fixtures, so a slip in one of those headers shows up in the CPU-only test run of every round and
+// not only on the GPU box.  What this does NOT cover: the device compiler (nvcc / ptxas — `__fmul_rn` and friends on the
+// device against plain `*` under -ffp-contract=off here), the LBVH build and traversal, the wavefront machinery of render.cu.
+// Those are the GPU tests' business.  This is not a fallback: nothing under rbrt_b200/ can reach it.
+//
+// The scene is flattened here the way api.cu / bvh_build.cu (k_emit_tris) lay it out for the kernels: element records,
+// {v0, e1, e2} + original index per tested triangle (N_eff of the lane rule), unit normals, exact AABB over all triangles.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "intersect.cuh"
+#include "shade.cuh"
+#include "../../include/rbrt_gpu.h"
+
+using namespace rbrt;
+
+namespace {
+
+struct HostScene {
+    std::vector<float4> spheres, etris, tris, normals, mat;
+    std::vector<uint32_t> elem_kind, mat_kind;
+    std::vector<MeshDev> meshes;
+    SceneDev dev;
+};
+
+uint64_t tested_triangles(uint64_t n, uint32_t lanes) {            // mesh.rs:136-144 + triangle.rs:167,296 (as api.cu)
+    uint64_t r = n % lanes, total = n + r, tested = (total / lanes) * lanes;
+    return tested < n ? tested : n;
+}
+
+void flatten(HostScene& hs, const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris,
+             const rbrt_mesh_desc* meshes, uint32_t nm, uint32_t lanes) {
+    hs.spheres.resize(ne); hs.elem_kind.resize(ne); hs.mat.resize(ne + nm); hs.mat_kind.resize(ne + nm);
+    uint32_t n_et = 0;
+    for (uint32_t i = 0; i < ne; ++i) {
+        rbrt_material m;
+        if (order[i].kind == RBRT_ELEM_SPHERE) {
+            const rbrt_sphere_desc& s = spheres[order[i].index];
+            hs.spheres[i] = make_float4(s.center.x, s.center.y, s.center.z, s.radius);
+            hs.elem_kind[i] = RBRT_ELEM_SPHERE; m = s.material;
+        } else {                                                    // BasicTriangle::new (triangle.rs:19-27)
+            const rbrt_triangle_desc& t = btris[order[i].index];
+            f3 a = mk3(t.corners[0].x, t.corners[0].y, t.corners[0].z), b = mk3(t.corners[1].x, t.corners[1].y, t.corners[1].z), c = mk3(t.corners[2].x, t.corners[2].y, t.corners[2].z);
+            f3 e1 = b - a, e2 = c - a, n = norm3(cross3(e1, e2));
+            uint32_t ti = (uint32_t)(hs.etris.size() / 4);
+            hs.spheres[i] = make_float4(__uint_as_float(ti), 0.0f, 0.0f, 0.0f);
+            hs.etris.push_back(make_float4(a.x, a.y, a.z, 0.0f)); hs.etris.push_back(make_float4(e1.x, e1.y, e1.z, 0.0f));
+            hs.etris.push_back(make_float4(e2.x, e2.y, e2.z, 0.0f)); hs.etris.push_back(make_float4(n.x, n.y, n.z, 0.0f));
+            hs.elem_kind[i] = RBRT_ELEM_TRIANGLE; m = t.material; ++n_et;
+        }
+        hs.mat[i] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.param); hs.mat_kind[i] = m.kind;
+    }
+    hs.meshes.resize(nm);
+    for (uint32_t mi = 0; mi < nm; ++mi) {
+        const rbrt_mesh_desc& m = meshes[mi];
+        hs.mat[ne + mi] = make_float4(m.material.albedo.x, m.material.albedo.y, m.material.albedo.z, m.material.param); hs.mat_kind[ne + mi] = m.material.kind;
+        MeshDev md; memset(&md, 0, sizeof(md));
+        const uint64_t n_eff = tested_triangles(m.num_triangles, lanes);
+        md.tri_base = (uint32_t)(hs.tris.size() / 3); md.n_tris = (uint32_t)n_eff; md.nrm_base = (uint32_t)hs.normals.size(); md.elem = ne + mi;
+        for (int k = 0; k < 3; ++k) { md.lo[k] = INFINITY; md.hi[k] = -INFINITY; }
+        for (uint64_t t = 0; t < m.num_triangles; ++t) {
+            const float* v = m.tri_vertices + 9 * t;
+            for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) { md.lo[k] = fminf(md.lo[k], v[3 * c + k]); md.hi[k] = fmaxf(md.hi[k], v[3 * c + k]); }   // aabbox.rs:62-88
+            if (t >= n_eff) continue;
+            f3 v0 = mk3(v[0], v[1], v[2]), e1 = mk3(v[3], v[4], v[5]) - v0, e2 = mk3(v[6], v[7], v[8]) - v0;        // mesh.rs:57-60
+            f3 n = norm3(cross3(e1, e2));                                                                             // triangle.rs:30-34
+            hs.tris.push_back(make_float4(v0.x, v0.y, v0.z, __uint_as_float((uint32_t)t)));
+            hs.tris.push_back(make_float4(e1.x, e1.y, e1.z, 0.0f)); hs.tris.push_back(make_float4(e2.x, e2.y, e2.z, 0.0f));
+            hs.normals.push_back(make_float4(n.x, n.y, n.z, 0.0f));
+        }
+        hs.meshes[mi] = md;
+    }
+    SceneDev& d = hs.dev;
+    d.spheres = hs.spheres.data(); d.etris = hs.etris.data(); d.elem_kind = hs.elem_kind.data(); d.tris = hs.tris.data(); d.nodes = nullptr;
+    d.normals = hs.normals.data(); d.mat = hs.mat.data(); d.mat_kind = hs.mat_kind.data(); d.meshes = hs.meshes.data();
+    d.n_spheres = ne; d.n_meshes = nm; d.n_etris = n_et;
+}
+
+f3 hit_normal(const SceneDev& S, const Hit& h, f3 p) {
+    if (h.kind == 0) return element_normal(S, h.elem, p);                                        // sphere: p - c (sphere.rs:56); BasicTriangle: its normal
+    float4 nn = S.normals[S.meshes[h.elem].nrm_base + h.tri];                                     // mesh.rs:253-257
+    return mk3(nn.x, nn.y, nn.z);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Scene::hit for caller-supplied rays, records filled as k_trace_rays (render.cu) fills them
+int hd_trace_rays(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris, const rbrt_mesh_desc* meshes,
+                  uint32_t nm, uint32_t lanes, const rbrt_ray* rays, uint64_t n, rbrt_hit* hits) {
+    HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes);
+    for (uint64_t i = 0; i < n; ++i) {
+        f3 o = mk3(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z), d = mk3(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
+        Hit h = scene_hit<true>(hs.dev, o, d, nullptr);
+        rbrt_hit out; memset(&out, 0, sizeof(out));
+        out.kind = h.kind >= 0 ? h.kind : RBRT_HIT_NONE;
+        if (h.kind >= 0) {
+            f3 p = o + h.t * d, nrm = hit_normal(hs.dev, h, p);
+            if (h.kind == 0 && hs.dev.n_etris && hs.elem_kind[h.elem]) out.kind = RBRT_HIT_TRIANGLE;
+            out.elem_idx = h.elem; out.tri_idx = h.tri; out.t = h.t; out.dist = h.dist;
+            out.point = rbrt_vec3{p.x, p.y, p.z}; out.normal = rbrt_vec3{nrm.x, nrm.y, nrm.z};
+        }
+        hits[i] = out;
+    }
+    return 0;
+}
+
+// render_scene (lib.rs:75-124) with the product's device functions: hdr_out H x W x 3 (pre-gamma mean), rgb_out H x W x 3
+int hd_render(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris, const rbrt_mesh_desc* meshes,
+              uint32_t nm, uint32_t lanes, const rbrt_camera* cam, uint32_t spp, uint64_t seed, uint32_t max_depth, float* hdr_out, uint8_t* rgb_out,
+              uint64_t* rays_out, uint64_t* nan_out) {
+    HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes);
+    const SceneDev& S = hs.dev;
+    CamDev c;
+    const rbrt_vec3* src[4] = {&cam->position, &cam->right, &cam->up, &cam->img_center_point};
+    float* dst[4] = {c.pos, c.right, c.up, c.center};
+    for (int k = 0; k < 4; ++k) { dst[k][0] = src[k]->x; dst[k][1] = src[k]->y; dst[k][2] = src[k]->z; }
+    c.mm_per_pix_hor = cam->mm_per_pix_hor; c.mm_per_pix_vert = cam->mm_per_pix_vert; c.width = cam->img_width_pix; c.height = cam->img_height_pix;
+    RngKey key; key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);
+    if (!max_depth) max_depth = 50;                                                               // lib.rs:99
+    uint64_t rays = 0, nans = 0;
+    std::vector<uint32_t> hist(max_depth + 1);
+    const float inv_spp = XDIV(1.0f, (float)spp);                                                 // lib.rs:101: multiply by the reciprocal
+    for (uint32_t row = 0; row < c.height; ++row)
+        for (uint32_t col = 0; col < c.width; ++col) {
+            const uint32_t pixel = row * c.width + col;
+            f3 acc = mk3(0.0f, 0.0f, 0.0f);
+            for (uint32_t s = 0; s < spp; ++s) {
+                f3 o, d;
+                camera_ray(c, row, col, key, pixel, s, o, d);
+                f3 color = mk3(0.0f, 0.0f, 0.0f);
+                for (uint32_t it = 0;; ++it) {                                                     // `it` scatters lie behind this ray
+                    ++rays;
+                    Hit h = scene_hit<true>(S, o, d, nullptr);
+                    if (h.kind == -2) { ++nans; break; }                                          // the reference panics (sphere.rs:33); the product ends the path black
+                    if (h.kind < 0) {                                                             // miss: sky, then att_1 * (att_2 * (... * sky)) (lib.rs:62-71)
+                        color = sky(d);
+                        for (int k = (int)it - 1; k >= 0; --k) {
+                            float4 m = S.mat[hist[k]];
+                            color = (S.mat_kind[hist[k]] == 2u ? mk3(1.0f, 1.0f, 1.0f) : mk3(m.x, m.y, m.z)) * color;
+                        }
+                        break;
+                    }
+                    if (it >= max_depth) break;                                                   // depth == 0: black, scatter() not called (lib.rs:54-55)
+                    f3 p = o + h.t * d, nrm = hit_normal(S, h, p), out_d;
+                    const uint32_t elem = h.kind == 0 ? h.elem : S.meshes[h.elem].elem;
+                    if (!scatter(S.mat_kind[elem], S.mat[elem], d, p, nrm, key, pixel, s, it + 1, out_d)) break;   // absorbed (metal.rs:24)
+                    hist[it] = elem; o = p; d = out_d;
+                }
+                acc = acc + color;                                                                // lib.rs:96-100, samples in order
+            }
+            f3 mean = acc * inv_spp;
+            float* hp = hdr_out + 3 * (size_t)pixel; hp[0] = mean.x; hp[1] = mean.y; hp[2] = mean.z;
+            uint8_t* rp = rgb_out + 3 * (size_t)pixel;                                            // lib.rs:118-120
+            rp[0] = as_u8(XMUL(XSQRT(mean.x), 256.0f)); rp[1] = as_u8(XMUL(XSQRT(mean.y), 256.0f)); rp[2] = as_u8(XMUL(XSQRT(mean.z), 256.0f));
+        }
+    if (rays_out) *rays_out = rays;
+    if (nan_out) *nan_out = nans;
+    return 0;
+}
+
+// scatter() in isolation, as rbrt_gpu_scatter / k_scatter_kat call it (bounce index and Philox key given by the caller)
+int hd_scatter(const rbrt_scatter_in* in, uint64_t n, uint64_t seed, rbrt_scatter_out* out) {
+    RngKey key; key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);
+    for (uint64_t i = 0; i < n; ++i) {
+        const rbrt_scatter_in& q = in[i];
+        f3 od;
+        const bool ok = scatter(q.material.kind, make_float4(q.material.albedo.x, q.material.albedo.y, q.material.albedo.z, q.material.param),
+                                mk3(q.in_ray.direction.x, q.in_ray.direction.y, q.in_ray.direction.z), mk3(q.hit_point.x, q.hit_point.y, q.hit_point.z),
+                                mk3(q.hit_normal.x, q.hit_normal.y, q.hit_normal.z), key, q.pixel, q.sample, q.bounce, od);
+        memset(&out[i], 0, sizeof(out[i]));
+        out[i].scattered = ok ? 1 : 0;
+        const bool glass = q.material.kind == 2u;                                                 // attenuation: albedo, or (1,1,1) for dielectrics (dielectric.rs:19)
+        out[i].attenuation = glass ? rbrt_vec3{1.0f, 1.0f, 1.0f} : q.material.albedo;
+        out[i].out_ray.origin = q.hit_point; out[i].out_ray.direction = rbrt_vec3{od.x, od.y, od.z};
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+"""The SOURCE of the product's per-ray arithmetic, checked without a GPU.
+
+rbrt_b200/csrc/common.cuh, intersect.cuh and shade.cuh (Scene::hit with its sphere / BasicTriangle / bounding-box / Moeller-Trumbore
+tests, camera rays, Lambertian / Metal / Dielectric scatter, Philox, sky, `as u8`) are compiled for the host by g++ behind a stand-in
+cuda_runtime.h (tests/host_device/) and driven by a plain one-ray-at-a-time brute-force loop.  The results must equal the oracle's and the
+golden fixtures' bit for bit.  This is test infrastructure, not a CPU path of the product (nothing under rbrt_b200/ can reach it): it makes
+the CPU-only test run of every round notice a slip in those headers.  The device compiler, the LBVH and the wavefront kernels are what the
+`-m gpu` tests cover."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import rbrt_b200 as R
+from rbrt_b200 import _abi
+from rbrt_b200.scene import element_arrays
+from rbrt_b200.vec3 import Vec3
+
+from . import golden_util as G
+from . import scenes as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HD = os.path.join(ROOT, "tests", "host_device")
+CSRC = os.path.join(ROOT, "rbrt_b200", "csrc")
+P = C.POINTER
+
+
+@pytest.fixture(scope="module")
+def hd():
+    out = os.path.join(HD, "build", "libhost_device.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = [os.path.join(HD, "harness.cpp"), os.path.join(HD, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("common.cuh", "intersect.cuh", "shade.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        # -I tests/host_device FIRST: `#include <cuda_runtime.h>` in common.cuh finds the stand-in.  No contraction, no FMA, as the oracle.
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mno-fma", "-Wno-unknown-pragmas", "-fPIC", "-shared",
+                        "-I", HD, "-I", CSRC, "-o", out, srcs[0]], check=True)
+    lib = C.CDLL(out)
+    scene_args = [P(_abi.ElementRefC), C.c_uint32, P(_abi.SphereDescC), P(_abi.TriangleDescC), P(_abi.MeshDescC), C.c_uint32, C.c_uint32]
+    lib.hd_trace_rays.argtypes = scene_args + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.hd_render.argtypes = scene_args + [P(_abi.CameraC), C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    lib.hd_scatter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    return lib
+
+
+def scene_args(scene):
+    order, spheres, tris, ne, ns, nt = element_arrays(scene.elements)
+    nm = len(scene.triangle_meshes)
+    meshes = (_abi.MeshDescC * max(nm, 1))(*[m.to_c() for m in scene.triangle_meshes])
+    return (order, ne, spheres, tris, meshes, nm, scene.simd_lanes), (order, spheres, tris, meshes)     # (arguments, keep-alive)
+
+
+def hd_hit(hd, scene, rays):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+    hits = np.zeros(len(rays), dtype=_abi.HIT_DTYPE)
+    args, keep = scene_args(scene)
+    assert hd.hd_trace_rays(*args, rays.ctypes.data, len(rays), hits.ctypes.data) == 0
+    return hits
+
+
+def hd_render(hd, scene, cam, spp, seed=0, max_depth=0):
+    h, w = cam.img_height_pix, cam.img_width_pix
+    hdr, rgb = np.empty((h, w, 3), np.float32), np.empty((h, w, 3), np.uint8)
+    rays, nans = C.c_uint64(0), C.c_uint64(0)
+    args, keep = scene_args(scene)
+    assert hd.hd_render(*args, cam.to_c(), spp, seed & (2 ** 64 - 1), max_depth, hdr.ctypes.data, rgb.ctypes.data, C.byref(rays), C.byref(nans)) == 0
+    return hdr, rgb, rays.value, nans.value
+
+
+def assert_hits(a, b, what):
+    eq = S.hits_equal(a, b)
+    assert eq.all(), f"{what}: {int((~eq).sum())} of {len(a)} hits differ; first: got {a[np.argmin(eq)]} want {b[np.argmin(eq)]}"
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", G.NAMES)
+def test_golden_fixtures(hd, name):
+    """The committed fixtures (oracle outputs; what the GPU tests compare with): hits of the stored rays, the complete render."""
+    z, scene, cam = G.load(name)
+    assert_hits(hd_hit(hd, scene, z["rays"]), z["hits"], name)
+    hdr, rgb, rays, _ = hd_render(hd, scene, cam, int(z["spp"]), int(z["seed"]))
+    assert np.array_equal(bits(hdr), bits(z["hdr"])), f"{name}: {int((bits(hdr) != bits(z['hdr'])).any(axis=2).sum())} pixels differ"
+    assert np.array_equal(rgb, z["rgb"]) and rays == int(z["n_rays_rendered"])
+
+
+def test_scene_hit_against_the_oracle(hd, oracle):
+    """Live oracle: the lane rule (N % 8, N % 4 tails), quirk scene, BasicTriangle elements mixed with spheres, ties between equal elements."""
+    for lanes in (8, 4):
+        for n_keep in (1275, 1277, 1280, 5, 3, 1):
+            scene = S.small_mesh_scene(3, n_keep, simd_lanes=lanes)
+            rays = np.concatenate([oracle.primary_rays(S.example_camera(48, 36).to_c(), 3, 0), S.random_rays(2048, (5.0, 1.4, -12.5), 4.0, 1)], 0)
+            assert_hits(hd_hit(hd, scene, rays), oracle.OracleScene.from_scene(scene).hit(rays), f"n={n_keep} lanes={lanes}")
+    scene = S.quirk_scene()
+    rays = np.concatenate([oracle.primary_rays(S.quirk_camera(64, 48).to_c(), 9, s) for s in range(3)], 0)
+    assert_hits(hd_hit(hd, scene, rays), oracle.OracleScene.from_scene(scene).hit(rays), "quirk scene")
+    # BasicTriangle elements between spheres (triangle.rs:9-28,92-130), two coincident elements (the earlier one wins, scene.rs:27)
+    mixed = R.Scene()
+    mixed.elements += [R.Sphere(Vec3(0, 0, -6), 1.0, R.Lambertian(Vec3(0.5, 0.5, 0.5))),
+                       R.BasicTriangle([Vec3(-3, -1, -5), Vec3(3, -1, -5), Vec3(0, 2.5, -5)], R.Metal(Vec3(0.9, 0.9, 0.9), 0.1)),
+                       R.Sphere(Vec3(0, 0, -6), 1.0, R.Dielectric(1.5)),
+                       R.BasicTriangle([Vec3(-3, -1, -5), Vec3(3, -1, -5), Vec3(0, 2.5, -5)], R.Lambertian(Vec3(0.1, 0.2, 0.3))),
+                       R.Sphere(Vec3(0, -101, -6), 100.0, R.Lambertian(Vec3(0.2, 0.8, 0.2)))]
+    rays = S.random_rays(4096, (0.0, 0.0, -5.5), 3.0, 4)
+    got, want = hd_hit(hd, mixed, rays), oracle.OracleScene.from_scene(mixed).hit(rays)
+    assert_hits(got, want, "mixed elements")
+    assert {0, 2} <= set(np.unique(got["kind"]).tolist())                   # spheres and BasicTriangle elements were both hit
+
+
+def test_renders_against_the_oracle(hd, oracle):
+    """Complete renders, all three materials, depth budgets 0 / 3 / 50 (lib.rs:54-55), three seeds; every bit of the HDR image, the u8 image
+    and the ray count."""
+    cases = [(S.spheres_scene(), S.example_camera(40, 30), 3), (S.quirk_scene(), S.quirk_camera(32, 24), 4),
+             (S.small_mesh_scene(2, None, material=R.Dielectric(0.2)), S.example_camera(32, 24), 2)]
+    for k, (scene, cam, spp) in enumerate(cases):
+        osc = oracle.OracleScene.from_scene(scene)
+        for seed, depth in ((0, 0), (0x5EED, 3), (2 ** 63 + 5, 0), (7, 1)):
+            st = {}
+            want = osc.render_hdr(cam.to_c(), spp, _abi.RenderOptsC(seed=seed, max_depth=depth), st)
+            hdr, rgb, rays, nans = hd_render(hd, scene, cam, spp, seed, depth)
+            assert np.array_equal(bits(hdr), bits(want)), (k, seed, depth, int((bits(hdr) != bits(want)).any(axis=2).sum()))
+            assert rays == st["rays"] and nans == st.get("nan_rays", 0)
+            assert np.array_equal(rgb, osc.render(cam.to_c(), spp, _abi.RenderOptsC(seed=seed, max_depth=depth)))
+
+
+def test_scatter_against_the_oracle(hd, oracle):
+    """scatter() alone on the inputs of tests/test_gpu_scatter.py (random + grazing + normal incidence, ref_idx 0.2 ... 3.5)."""
+    from .test_gpu_scatter import oracle_scatter
+    rng = np.random.default_rng(17)
+    mats = [R.Lambertian(Vec3(0.7, 0.3, 0.2)), R.Metal(Vec3(0.8, 0.8, 0.8), 0.005), R.Metal(Vec3(0.9, 0.9, 0.5), 0.0),
+            R.Metal(Vec3(0.5, 0.6, 0.7), 0.9), R.Dielectric(1.8), R.Dielectric(1.5), R.Dielectric(0.2), R.Dielectric(1.0), R.Dielectric(3.5)]
+    items = []
+    for k in range(3000):
+        d, n = rng.normal(size=3).astype(np.float32), rng.normal(size=3).astype(np.float32)
+        if k % 4 == 0:
+            n *= np.float32(rng.uniform(0.01, 1000.0))
+        if k % 7 == 0:
+            t = np.cross(n, rng.normal(size=3)).astype(np.float32)
+            d = (t / np.float32(np.linalg.norm(t)) + np.float32(0.02) * n / np.float32(np.linalg.norm(n)) * np.float32(rng.choice([-1, 1]))).astype(np.float32)
+        if k % 11 == 0:
+            d = (-n).astype(np.float32)
+        items.append((mats[k % len(mats)], d, (rng.normal(size=3) * 20).astype(np.float32), n, int(rng.integers(0, 2 ** 21)), int(rng.integers(0, 1024)),
+                      int(rng.integers(1, 51))))
+    arr = (_abi.ScatterInC * len(items))()
+    for k, (mat, d, p, nrm, pixel, sample, bounce) in enumerate(items):
+        a = arr[k]
+        a.material = mat.to_c()
+        a.in_ray.direction = _abi.Vec3C(*[float(x) for x in d]); a.hit_point = _abi.Vec3C(*[float(x) for x in p]); a.hit_normal = _abi.Vec3C(*[float(x) for x in nrm])
+        a.pixel, a.sample, a.bounce = pixel, sample, bounce
+    out = (_abi.ScatterOutC * len(items))()
+    seed = 0x5EED0123456789
+    assert hd.hd_scatter(C.cast(arr, C.c_void_p), len(items), seed, C.cast(out, C.c_void_p)) == 0
+    o_sc, o_att, o_od = oracle_scatter(oracle, items, seed)
+    g_sc = np.array([o.scattered for o in out], np.int32)
+    g_att = np.array([[o.attenuation.x, o.attenuation.y, o.attenuation.z] for o in out], np.float32)
+    g_od = np.array([[o.out_ray.direction.x, o.out_ray.direction.y, o.out_ray.direction.z] for o in out], np.float32)
+    assert np.array_equal(g_sc, o_sc) and np.array_equal(bits(g_att), bits(o_att)) and np.array_equal(bits(g_od), bits(o_od))
+    assert 0 < g_sc.sum() < len(items)
