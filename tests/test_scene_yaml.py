@@ -232,7 +232,7 @@ def scene_text(draw):
     return text
 
 
-@settings(max_examples=250, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=250, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(text=scene_text())
 def test_generated_scene_files_read_the_same(tmp_path, text):
     both(tmp_path, text)
