@@ -89,3 +89,25 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                     txt = open(os.path.join(d, f), errors="replace").read()
                     assert "oracle_ffi" not in txt and "rbrt_ref_" not in txt and "librbrt_oracle" not in txt, os.path.join(d, f)
+
+
+def test_plain_c_host_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    """integration/c/render_scene.c — main.rs:70-91 from C99 over the header, -Wall -Wextra -Werror -pedantic.  It loads a mesh through
+    rbrt_mesh_load_obj (CPU) and then needs the GPU: on a machine without one it must stop with the library's message and exit code 3."""
+    import torch
+    from rbrt_b200 import synth
+    src = os.path.join(ROOT, "integration", "c", "render_scene.c")
+    exe = tmp_path / "render_scene"
+    libdir = os.path.join(ROOT, "rbrt_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-L", libdir, "-lrbrt_gpu",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    obj = tmp_path / "m.obj"
+    n = synth.write_bunny_standin(str(obj), subdiv=2)
+    out = subprocess.run([str(exe), str(obj), str(tmp_path / "o.ppm")], capture_output=True, text=True)
+    assert f"Successfully loaded {n} triangles" in out.stdout
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and (tmp_path / "o.ppm").read_bytes().startswith(b"P6\n256 192\n255\n")
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stderr
+    bad = subprocess.run([str(exe), str(tmp_path / "missing.obj"), str(tmp_path / "o.ppm")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr
