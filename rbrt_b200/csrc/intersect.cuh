@@ -211,7 +211,13 @@ __device__ __forceinline__ RaySlabs ray_slabs(const MeshDev& M, f3 o, f3 d) {
 // compiler that mask was re-applied at every node visit — six LOP3 per visit on the pipe that binds the kernel)
 __device__ __forceinline__ float q16(uint32_t w, uint32_t sel) {
     uint32_t r;
+#ifdef __CUDA_ARCH__
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
+#else                                                                     // host build of this header (tests/host_device): what PRMT does, byte by byte
+    const uint64_t pool = ((uint64_t)0x4B000000u << 32) | w;
+    r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+#endif
     return __uint_as_float(r);
 }
 

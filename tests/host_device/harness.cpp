@@ -4,14 +4,16 @@
 // BasicTriangle, bounding-box and Moeller-Trumbore tests, camera rays, the three scatter()s, Philox, sky, `as u8`.  Here those
 // headers are compiled by g++ (-ffp-contract=off, the cuda_runtime.h stand-in of this directory) and driven by the plainest
 // possible loop: one ray at a time, brute force over the triangles (`scene_hit<true>`, the kernel `rbrt_gpu_trace_rays` runs
-// in RBRT_TRACE_BRUTE mode), recursion of lib.rs:43-73 unrolled into a loop.  The tests compare the result bit for bit with
+// in RBRT_TRACE_BRUTE mode) or the one-lane BVH traversal (`scene_hit<false>`, RBRT_TRACE_BVH mode) over a tree built here,
+// recursion of lib.rs:43-73 unrolled into a loop.  The tests compare the result bit for bit with
 // the oracle and the golden fixtures, so a slip in one of those headers shows up in the CPU-only test run of every round and
 // not only on the GPU box.  What this does NOT cover: the device compiler (nvcc / ptxas — `__fmul_rn` and friends on the
-// device against plain `*` under -ffp-contract=off here), the LBVH build and traversal, the wavefront machinery of render.cu.
+// device against plain `*` under -ffp-contract=off here), the GPU's LBVH build, the warp-voted traversal and the wavefront machinery of render.cu.
 // Those are the GPU tests' business.  This is not a fallback: nothing under rbrt_b200/ can reach it.
 //
 // The scene is flattened here the way api.cu / bvh_build.cu (k_emit_tris) lay it out for the kernels: element records,
 // {v0, e1, e2} + original index per tested triangle (N_eff of the lane rule), unit normals, exact AABB over all triangles.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -26,6 +28,7 @@ using namespace rbrt;
 namespace {
 
 struct HostScene {
+    std::vector<uint4> nodes;                                  // 4 x uint4 per 4-wide node, all meshes (MeshDev::node_base)
     std::vector<float4> spheres, etris, tris, normals, mat;
     std::vector<uint32_t> elem_kind, mat_kind;
     std::vector<MeshDev> meshes;
@@ -37,8 +40,73 @@ uint64_t tested_triangles(uint64_t n, uint32_t lanes) {            // mesh.rs:13
     return tested < n ? tested : n;
 }
 
+// ---- a 4-wide BVH in the node format of intersect.cuh, built on the host -----------------------------------------------------
+// The product builds its tree on the GPU (bvh_build.cu: Morton LBVH -> refit + rotations -> 4-wide collapse), which cannot run
+// here.  What CAN be checked without a GPU is the product's TRAVERSAL source (ray_slabs, the PRMT decode, bvh4_step, leaf_step,
+// the prune bounds, scene_hit<false>'s t_limit) — on any valid tree in that format.  This builder makes one: median splits of
+// the centroid range, two binary levels folded into one node (largest box first, like collapse_node), boxes = triangle AABBs +
+// the pad, quantised onto the mesh's 16-bit grid OUTWARD plus one step, by the formulas of bvh_build.cu (k_mesh_setup, quant_lo /
+// quant_hi).  It shares no code with the GPU builder; a traversal that agrees with the brute-force loop on it for every ray has
+// its own arithmetic right.
+struct Box { float lo[3], hi[3]; };
+inline void grow(Box& b, const Box& o) { for (int k = 0; k < 3; ++k) { b.lo[k] = fminf(b.lo[k], o.lo[k]); b.hi[k] = fmaxf(b.hi[k], o.hi[k]); } }
+inline Box empty_box() { Box b; for (int k = 0; k < 3; ++k) { b.lo[k] = INFINITY; b.hi[k] = -INFINITY; } return b; }
+inline float half_area(const Box& b) { float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2]; return dx * dy + dy * dz + dz * dx; }
+inline uint32_t quant_lo(float v, float org, float step) {
+    float q = floorf((v - org) / step) - 1.0f;
+    while (q > 0.0f && fmaf(q, step, org) > v) q -= 1.0f;
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+inline uint32_t quant_hi(float v, float org, float step) {
+    float q = ceilf((v - org) / step) + 1.0f;
+    while (q < 65535.0f && fmaf(q, step, org) < v) q += 1.0f;
+    return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
+}
+
+struct TreeBuilder {
+    const std::vector<Box>& tb;                                // per triangle (already padded), in the order `order` lists them
+    std::vector<uint32_t>& order;
+    uint32_t leaf_size;
+    const MeshDev& md;
+    std::vector<uint4>& out; size_t base;                      // nodes of this mesh start at out[4 * base]
+    struct Part { uint32_t a, b; Box box; };                   // triangles order[a..b)
+    Part part(uint32_t a, uint32_t b) const { Part p{a, b, empty_box()}; for (uint32_t i = a; i < b; ++i) grow(p.box, tb[order[i]]); return p; }
+    void split(const Part& p, Part& l, Part& r) {
+        Box cb = empty_box();
+        for (uint32_t i = p.a; i < p.b; ++i) { const Box& t = tb[order[i]]; Box c; for (int k = 0; k < 3; ++k) c.lo[k] = c.hi[k] = 0.5f * (t.lo[k] + t.hi[k]); grow(cb, c); }
+        int ax = 0; for (int k = 1; k < 3; ++k) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+        const uint32_t mid = p.a + (p.b - p.a) / 2;
+        std::nth_element(order.begin() + p.a, order.begin() + mid, order.begin() + p.b,
+                         [&](uint32_t x, uint32_t y) { return tb[x].lo[ax] + tb[x].hi[ax] < tb[y].lo[ax] + tb[y].hi[ax]; });
+        l = part(p.a, mid); r = part(mid, p.b);
+    }
+    // writes the node of `p` (more than leaf_size triangles) into slot `slot`
+    void node(const Part& p, uint32_t slot) {
+        std::vector<Part> kids(2);
+        split(p, kids[0], kids[1]);
+        for (int round = 0; round < 2; ++round) {
+            int best = -1; float best_a = -1.0f;
+            for (size_t k = 0; k < kids.size(); ++k) if (kids[k].b - kids[k].a > leaf_size && half_area(kids[k].box) > best_a) { best_a = half_area(kids[k].box); best = (int)k; }
+            if (best < 0) break;
+            Part l, r; split(kids[best], l, r);
+            kids[best] = l; kids.push_back(r);
+        }
+        uint32_t q[4][3]; int32_t refs[4];
+        for (size_t k = 0; k < 4; ++k) {
+            if (k < kids.size()) {
+                for (int c = 0; c < 3; ++c) q[k][c] = quant_lo(kids[k].box.lo[c], md.qorg[c], md.qstep[c]) | (quant_hi(kids[k].box.hi[c], md.qorg[c], md.qstep[c]) << 16);
+                if (kids[k].b - kids[k].a > leaf_size) { const uint32_t child = (uint32_t)(out.size() / 4 - base); out.resize(out.size() + 4); refs[k] = (int32_t)child; node(kids[k], child); }
+                else refs[k] = make_leaf_ref(kids[k].a, kids[k].b - kids[k].a);
+            } else { q[k][0] = q[k][1] = q[k][2] = 0x0000FFFFu; refs[k] = make_leaf_ref(0, 1); }      // unused slot: inverted box
+        }
+        uint4* o = out.data() + 4 * (base + slot);
+        o[0] = make_uint4(q[0][0], q[0][1], q[0][2], q[1][0]); o[1] = make_uint4(q[1][1], q[1][2], q[2][0], q[2][1]);
+        o[2] = make_uint4(q[2][2], q[3][0], q[3][1], q[3][2]); o[3] = make_uint4((uint32_t)refs[0], (uint32_t)refs[1], (uint32_t)refs[2], (uint32_t)refs[3]);
+    }
+};
+
 void flatten(HostScene& hs, const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris,
-             const rbrt_mesh_desc* meshes, uint32_t nm, uint32_t lanes) {
+             const rbrt_mesh_desc* meshes, uint32_t nm, uint32_t lanes, uint32_t leaf_size = 0) {   // leaf_size > 0: also build the trees
     hs.spheres.resize(ne); hs.elem_kind.resize(ne); hs.mat.resize(ne + nm); hs.mat_kind.resize(ne + nm);
     uint32_t n_et = 0;
     for (uint32_t i = 0; i < ne; ++i) {
@@ -70,17 +138,46 @@ void flatten(HostScene& hs, const rbrt_element_ref* order, uint32_t ne, const rb
         for (uint64_t t = 0; t < m.num_triangles; ++t) {
             const float* v = m.tri_vertices + 9 * t;
             for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) { md.lo[k] = fminf(md.lo[k], v[3 * c + k]); md.hi[k] = fmaxf(md.hi[k], v[3 * c + k]); }   // aabbox.rs:62-88
-            if (t >= n_eff) continue;
+        }
+        std::vector<uint32_t> order(n_eff);
+        for (uint32_t t = 0; t < n_eff; ++t) order[t] = t;
+        md.node_base = (uint32_t)(hs.nodes.size() / 4); md.root_ref = make_leaf_ref(0, 1);
+        if (leaf_size && n_eff) {                                    // grid as k_mesh_setup lays it, then the tree; triangles go out in tree order
+            float mx = 0.0f;
+            for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(md.lo[k]), fabsf(md.hi[k]))); mx = fmaxf(mx, md.hi[k] - md.lo[k]); }
+            const float pad = 2e-5f * mx;
+            for (int k = 0; k < 3; ++k) {
+                float ext = (md.hi[k] + pad) - (md.lo[k] - pad), step = ext / 65500.0f;
+                if (!(step > 1e-30f)) step = 1e-30f;
+                md.qstep[k] = step; md.qorg[k] = (md.lo[k] - pad) - 8.0f * step;
+            }
+            std::vector<Box> tb(n_eff);
+            for (uint32_t t = 0; t < n_eff; ++t) {
+                const float* v = m.tri_vertices + 9 * (size_t)t;
+                Box b = empty_box();
+                for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) { b.lo[k] = fminf(b.lo[k], v[3 * c + k]); b.hi[k] = fmaxf(b.hi[k], v[3 * c + k]); }
+                for (int k = 0; k < 3; ++k) { b.lo[k] -= pad; b.hi[k] += pad; }
+                tb[t] = b;
+            }
+            TreeBuilder B{tb, order, leaf_size, md, hs.nodes, md.node_base};
+            if (n_eff <= leaf_size) md.root_ref = make_leaf_ref(0, (uint32_t)n_eff);
+            else { hs.nodes.resize(hs.nodes.size() + 4); md.root_ref = 0; B.node(B.part(0, (uint32_t)n_eff), 0); }
+        }
+        hs.normals.resize(md.nrm_base + n_eff);
+        for (uint32_t pos = 0; pos < n_eff; ++pos) {
+            const uint32_t t = order[pos];
+            const float* v = m.tri_vertices + 9 * (size_t)t;
             f3 v0 = mk3(v[0], v[1], v[2]), e1 = mk3(v[3], v[4], v[5]) - v0, e2 = mk3(v[6], v[7], v[8]) - v0;        // mesh.rs:57-60
             f3 n = norm3(cross3(e1, e2));                                                                             // triangle.rs:30-34
-            hs.tris.push_back(make_float4(v0.x, v0.y, v0.z, __uint_as_float((uint32_t)t)));
+            hs.tris.push_back(make_float4(v0.x, v0.y, v0.z, __uint_as_float(t)));                                       // BVH order, original index alongside
             hs.tris.push_back(make_float4(e1.x, e1.y, e1.z, 0.0f)); hs.tris.push_back(make_float4(e2.x, e2.y, e2.z, 0.0f));
-            hs.normals.push_back(make_float4(n.x, n.y, n.z, 0.0f));
+            hs.normals[md.nrm_base + t] = make_float4(n.x, n.y, n.z, 0.0f);                                             // original order
         }
         hs.meshes[mi] = md;
     }
     SceneDev& d = hs.dev;
-    d.spheres = hs.spheres.data(); d.etris = hs.etris.data(); d.elem_kind = hs.elem_kind.data(); d.tris = hs.tris.data(); d.nodes = nullptr;
+    d.spheres = hs.spheres.data(); d.etris = hs.etris.data(); d.elem_kind = hs.elem_kind.data(); d.tris = hs.tris.data();
+    d.nodes = reinterpret_cast<const float4*>(hs.nodes.data());
     d.normals = hs.normals.data(); d.mat = hs.mat.data(); d.mat_kind = hs.mat_kind.data(); d.meshes = hs.meshes.data();
     d.n_spheres = ne; d.n_meshes = nm; d.n_etris = n_et;
 }
@@ -97,11 +194,15 @@ extern "C" {
 
 // Scene::hit for caller-supplied rays, records filled as k_trace_rays (render.cu) fills them
 int hd_trace_rays(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris, const rbrt_mesh_desc* meshes,
-                  uint32_t nm, uint32_t lanes, const rbrt_ray* rays, uint64_t n, rbrt_hit* hits) {
-    HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes);
+                  uint32_t nm, uint32_t lanes, uint32_t leaf_size /* 0: brute force; 1..8: through a 4-wide BVH with such leaves */,
+                  const rbrt_ray* rays, uint64_t n, rbrt_hit* hits, uint64_t* node_visits, uint64_t* tri_tests) {
+    HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes, leaf_size);
+    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    uint64_t nodes_total = 0, tris_total = 0;
     for (uint64_t i = 0; i < n; ++i) {
         f3 o = mk3(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z), d = mk3(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
-        Hit h = scene_hit<true>(hs.dev, o, d, nullptr);
+        Hit h = leaf_size ? scene_hit<false>(hs.dev, o, d, &cnt) : scene_hit<true>(hs.dev, o, d, &cnt);
+        nodes_total += cnt.nodes; tris_total += cnt.tris; cnt.nodes = 0; cnt.tris = 0;
         rbrt_hit out; memset(&out, 0, sizeof(out));
         out.kind = h.kind >= 0 ? h.kind : RBRT_HIT_NONE;
         if (h.kind >= 0) {
@@ -112,6 +213,8 @@ int hd_trace_rays(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_
         }
         hits[i] = out;
     }
+    if (node_visits) *node_visits = nodes_total;
+    if (tri_tests) *tri_tests = tris_total;
     return 0;
 }
 

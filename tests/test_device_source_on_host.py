@@ -3,9 +3,9 @@
 rbrt_b200/csrc/common.cuh, intersect.cuh and shade.cuh (Scene::hit with its sphere / BasicTriangle / bounding-box / Moeller-Trumbore
 tests, camera rays, Lambertian / Metal / Dielectric scatter, Philox, sky, `as u8`) are compiled for the host by g++ behind a stand-in
 cuda_runtime.h (tests/host_device/) and driven by a plain one-ray-at-a-time brute-force loop.  The results must equal the oracle's and the
-golden fixtures' bit for bit.  This is test infrastructure, not a CPU path of the product (nothing under rbrt_b200/ can reach it): it makes
-the CPU-only test run of every round notice a slip in those headers.  The device compiler, the LBVH and the wavefront kernels are what the
-`-m gpu` tests cover."""
+golden fixtures' bit for bit; the BVH traversal source runs over 4-wide trees built on the host in the product's node format.  This is test infrastructure, not a CPU path of the product (nothing under rbrt_b200/ can reach it): it makes
+the CPU-only test run of every round notice a slip in those headers.  The device compiler, the GPU's LBVH build, the warp-voted traversal and
+the wavefront kernels are what the `-m gpu` tests cover."""
 import ctypes as C
 import os
 import subprocess
@@ -34,11 +34,11 @@ def hd():
     srcs = [os.path.join(HD, "harness.cpp"), os.path.join(HD, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("common.cuh", "intersect.cuh", "shade.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         # -I tests/host_device FIRST: `#include <cuda_runtime.h>` in common.cuh finds the stand-in.  No contraction, no FMA, as the oracle.
-        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mno-fma", "-Wno-unknown-pragmas", "-fPIC", "-shared",
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mno-fma", "-DRBRT_LDG128", "-Wno-unknown-pragmas", "-fPIC", "-shared",
                         "-I", HD, "-I", CSRC, "-o", out, srcs[0]], check=True)
     lib = C.CDLL(out)
     scene_args = [P(_abi.ElementRefC), C.c_uint32, P(_abi.SphereDescC), P(_abi.TriangleDescC), P(_abi.MeshDescC), C.c_uint32, C.c_uint32]
-    lib.hd_trace_rays.argtypes = scene_args + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.hd_trace_rays.argtypes = scene_args + [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_render.argtypes = scene_args + [P(_abi.CameraC), C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_scatter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     return lib
@@ -51,11 +51,15 @@ def scene_args(scene):
     return (order, ne, spheres, tris, meshes, nm, scene.simd_lanes), (order, spheres, tris, meshes)     # (arguments, keep-alive)
 
 
-def hd_hit(hd, scene, rays):
+def hd_hit(hd, scene, rays, leaf_size=0, counters=None):
+    """leaf_size 0: the brute-force loop (scene_hit<true>); 1..8: the BVH traversal (scene_hit<false>) over a host-built 4-wide tree."""
     rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
     hits = np.zeros(len(rays), dtype=_abi.HIT_DTYPE)
     args, keep = scene_args(scene)
-    assert hd.hd_trace_rays(*args, rays.ctypes.data, len(rays), hits.ctypes.data) == 0
+    nodes, tris = C.c_uint64(0), C.c_uint64(0)
+    assert hd.hd_trace_rays(*args, leaf_size, rays.ctypes.data, len(rays), hits.ctypes.data, C.byref(nodes), C.byref(tris)) == 0
+    if counters is not None:
+        counters.update(nodes=nodes.value, tris=tris.value)
     return hits
 
 
@@ -108,6 +112,40 @@ def test_scene_hit_against_the_oracle(hd, oracle):
     got, want = hd_hit(hd, mixed, rays), oracle.OracleScene.from_scene(mixed).hit(rays)
     assert_hits(got, want, "mixed elements")
     assert {0, 2} <= set(np.unique(got["kind"]).tolist())                   # spheres and BasicTriangle elements were both hit
+
+
+def test_bvh_traversal_source_against_the_oracle(hd, oracle):
+    """The TRAVERSAL the trace kernels share (ray_slabs, the 16-bit node decode, bvh4_step's ordering and stack, leaf_step, the prune bounds,
+    scene_hit<false>'s limit from the spheres) over 4-wide trees built on the host in the product's node format: same hits as the oracle's
+    O(N) sweep, for every leaf size, with rays that are axis-parallel, start inside the mesh, graze it, or carry zero components."""
+    from rbrt_b200 import synth
+    rng = np.random.default_rng(8)
+    centre = np.array((5.0, 1.4, -12.5), np.float32)
+    for lanes, n_keep in ((8, 1280), (8, 1277), (4, 1277), (8, 9), (8, 3), (8, 1)):
+        scene = S.small_mesh_scene(3, n_keep, simd_lanes=lanes)
+        rays = [oracle.primary_rays(S.example_camera(48, 36).to_c(), 3, 0), S.random_rays(3000, tuple(centre), 4.0, 1)]
+        inside = np.concatenate([np.tile(centre, (600, 1)) + rng.normal(0, 0.5, (600, 3)).astype(np.float32), rng.normal(size=(600, 3)).astype(np.float32)], 1)
+        axis = np.zeros((600, 6), np.float32)
+        axis[:, :3] = centre + rng.uniform(-4, 4, (600, 3)).astype(np.float32)
+        axis[np.arange(600), 3 + rng.integers(0, 3, 600)] = rng.choice([-1.0, 1.0], 600)                 # two zero direction components
+        planar = inside.copy(); planar[:, 3 + 1] = 0.0                                                    # one zero component
+        rays = np.concatenate(rays + [inside, axis, planar], 0).astype(np.float32)
+        want = oracle.OracleScene.from_scene(scene).hit(rays)
+        brute = {}
+        assert_hits(hd_hit(hd, scene, rays, 0, brute), want, f"brute n={n_keep}")
+        for leaf in (1, 2, 4, 8):
+            cnt = {}
+            assert_hits(hd_hit(hd, scene, rays, leaf, cnt), want, f"bvh n={n_keep} lanes={lanes} leaf={leaf}")
+            if n_keep >= 1277:
+                assert 0 < cnt["nodes"] and cnt["tris"] < brute["tris"] / 20                              # the tree did prune
+    # a larger mesh (20 480 triangles) + the fixture's spheres in front of and behind it: the limit handed to the traversal comes from the spheres
+    scene = S.spheres_scene()
+    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(5, 3.0, (5.0, 1.4, -12.5)), R.Dielectric(0.2)))
+    rays = np.concatenate([oracle.primary_rays(S.example_camera(96, 72).to_c(), 5, 0), S.random_rays(4000, (5.0, 1.4, -12.5), 5.0, 2)], 0)
+    want = oracle.OracleScene.from_scene(scene).hit(rays)
+    assert (want["kind"] == 1).sum() > 500 and (want["kind"] == 0).sum() > 500
+    for leaf in (1, 4):
+        assert_hits(hd_hit(hd, scene, rays, leaf), want, f"icosphere 5 leaf={leaf}")
 
 
 def test_renders_against_the_oracle(hd, oracle):
