@@ -188,20 +188,59 @@ f3 hit_normal(const SceneDev& S, const Hit& h, f3 p) {
     return mk3(nn.x, nn.y, nn.z);
 }
 
+// Scene::hit with the traversal the trace kernels run (traverse_voted: one node visit or ONE triangle test per step, leaf_step_one +
+// the branch-free tri_intersect_masks), for a "warp" of one lane.  The frame around it — spheres first, then per mesh the box test,
+// the limit from the best hit so far, closing the mesh — restates what k_trace does per ray (render.cu, start_mesh / the loop head).
+Hit scene_hit_voted(const SceneDev& S, f3 o, f3 d, TraceCounters* cnt) {
+    Hit best; best.kind = -1; best.elem = 0; best.tri = 0; best.t = 0.0f; best.dist = 0.0f;
+    float closest = 3.40282347e+38f;
+    for (uint32_t i = 0; i < S.n_spheres; ++i) {
+        float t, dist;
+        int r = element_intersect(S, i, o, d, t, dist);
+        if (r < 0) { best.kind = -2; return best; }
+        if (r && dist < closest) { closest = dist; best.kind = 0; best.elem = i; best.t = t; best.dist = dist; }
+    }
+    for (uint32_t mi = 0; mi < S.n_meshes; ++mi) {
+        const MeshDev& M = S.meshes[mi];
+        if (M.n_tris == 0 || !mesh_bbox_hit(M, o, d)) continue;
+        float t_limit = RBRT_T_CAP;
+        if (closest < 3.0e38f) {
+            float dl = len3(d), omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+            float lim = (closest * 1.001f + 1e-5f * (omax + closest) + 1e-6f) / dl;
+            if (lim == lim) t_limit = fminf(t_limit, lim);
+        }
+        float t_prune = t_limit, best_t = 1000000.0f; uint32_t best_idx = 0xFFFFFFFFu;
+        const uint4* nodes = reinterpret_cast<const uint4*>(S.nodes) + 4 * (size_t)M.node_base;
+        const RaySlabs R = ray_slabs(M, o, d);
+        int32_t lstack[RBRT_STACK]; const StackL stack = {lstack};
+        int sp = 0; stack.put(sp++, RBRT_SENTINEL);
+        int32_t cur = M.root_ref;
+        uint32_t n_nodes = 0, n_tris = 0;
+        traverse_voted<true, false>(nodes, S.tris, M.tri_base, R, o, d, t_limit, stack, sp, cur, best_t, best_idx, t_prune, 1, n_nodes, n_tris);
+        if (cnt) { cnt->nodes += n_nodes; cnt->tris += n_tris; }
+        if (best_idx == 0xFFFFFFFFu) continue;
+        f3 p = o + best_t * d;
+        float dist = len3(o - p);
+        if (dist > RBRT_MIN_DIST && dist < RBRT_MAX_DIST && dist < closest) { closest = dist; best.kind = 1; best.elem = mi; best.tri = best_idx; best.t = best_t; best.dist = dist; }
+    }
+    return best;
+}
+
 }  // namespace
 
 extern "C" {
 
 // Scene::hit for caller-supplied rays, records filled as k_trace_rays (render.cu) fills them
 int hd_trace_rays(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris, const rbrt_mesh_desc* meshes,
-                  uint32_t nm, uint32_t lanes, uint32_t leaf_size /* 0: brute force; 1..8: through a 4-wide BVH with such leaves */,
+                  uint32_t nm, uint32_t lanes, uint32_t leaf_size /* 0: brute force; 1..8: through a 4-wide BVH with such leaves; + 16: the voted traversal */,
                   const rbrt_ray* rays, uint64_t n, rbrt_hit* hits, uint64_t* node_visits, uint64_t* tri_tests) {
+    const bool voted = (leaf_size & 16u) != 0; leaf_size &= 15u;
     HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes, leaf_size);
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     uint64_t nodes_total = 0, tris_total = 0;
     for (uint64_t i = 0; i < n; ++i) {
         f3 o = mk3(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z), d = mk3(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
-        Hit h = leaf_size ? scene_hit<false>(hs.dev, o, d, &cnt) : scene_hit<true>(hs.dev, o, d, &cnt);
+        Hit h = !leaf_size ? scene_hit<true>(hs.dev, o, d, &cnt) : (voted ? scene_hit_voted(hs.dev, o, d, &cnt) : scene_hit<false>(hs.dev, o, d, &cnt));
         nodes_total += cnt.nodes; tris_total += cnt.tris; cnt.nodes = 0; cnt.tris = 0;
         rbrt_hit out; memset(&out, 0, sizeof(out));
         out.kind = h.kind >= 0 ? h.kind : RBRT_HIT_NONE;

@@ -134,8 +134,11 @@ def test_bvh_traversal_source_against_the_oracle(hd, oracle):
         brute = {}
         assert_hits(hd_hit(hd, scene, rays, 0, brute), want, f"brute n={n_keep}")
         for leaf in (1, 2, 4, 8):
-            cnt = {}
+            cnt, vcnt = {}, {}
             assert_hits(hd_hit(hd, scene, rays, leaf, cnt), want, f"bvh n={n_keep} lanes={lanes} leaf={leaf}")
+            # + 16: traverse_voted (one node visit or ONE triangle test per step: leaf_step_one, tri_intersect_masks), what k_trace / k_tail run
+            assert_hits(hd_hit(hd, scene, rays, leaf + 16, vcnt), want, f"voted n={n_keep} lanes={lanes} leaf={leaf}")
+            assert vcnt == cnt                                                                            # the same visits and tests, in another schedule
             if n_keep >= 1277:
                 assert 0 < cnt["nodes"] and cnt["tris"] < brute["tris"] / 20                              # the tree did prune
     # a larger mesh (20 480 triangles) + the fixture's spheres in front of and behind it: the limit handed to the traversal comes from the spheres
@@ -144,7 +147,7 @@ def test_bvh_traversal_source_against_the_oracle(hd, oracle):
     rays = np.concatenate([oracle.primary_rays(S.example_camera(96, 72).to_c(), 5, 0), S.random_rays(4000, (5.0, 1.4, -12.5), 5.0, 2)], 0)
     want = oracle.OracleScene.from_scene(scene).hit(rays)
     assert (want["kind"] == 1).sum() > 500 and (want["kind"] == 0).sum() > 500
-    for leaf in (1, 4):
+    for leaf in (1, 4, 17, 20):
         assert_hits(hd_hit(hd, scene, rays, leaf), want, f"icosphere 5 leaf={leaf}")
 
 
