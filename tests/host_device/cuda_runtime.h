@@ -2,7 +2,7 @@
 // the product's device headers (rbrt_b200/csrc/common.cuh, intersect.cuh, shade.cuh) with g++ for the HOST.  TEST INFRASTRUCTURE:
 // it lets `pytest -m "not gpu"` run the source of the product's per-ray arithmetic against the oracle in a container without a
 // GPU.  Nothing under rbrt_b200/ includes it; the product has no CPU path.
-// It provides only what those three headers touch: the qualifiers, float4 / uint4, and eight intrinsics with their IEEE meaning.
+// It provides only what those three headers touch: the qualifiers, float4 / uint4, and a handful of intrinsics with their IEEE meaning.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -27,5 +27,6 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }          // (only in the BVH slab tests, which the host build never runs)
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }                            // (the device's is an approximation: the cull tests perturb its result)
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint32_t __ballot_sync(uint32_t, int pred) { return pred ? 1u : 0u; }          // a "warp" of one lane

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "intersect.cuh"
+#include "cull.cuh"
 #include "shade.cuh"
 #include "../../include/rbrt_gpu.h"
 
@@ -326,6 +327,49 @@ int hd_scatter(const rbrt_scatter_in* in, uint64_t n, uint64_t seed, rbrt_scatte
         out[i].attenuation = glass ? rbrt_vec3{1.0f, 1.0f, 1.0f} : q.material.albedo;
         out[i].out_ray.origin = q.hit_point; out[i].out_ray.direction = rbrt_vec3{od.x, od.y, od.z};
     }
+    return 0;
+}
+
+// The camera-ray culling of stage A (cull.cuh) against the exact tests it stands in front of.  For sphere s and its m directions
+// (normalised here the way camera_ray normalises): skipped = outside_double_cone, hit = sphere_intersect != 0 (a NaN counts as "must be tested").
+// axis_scale / w_shift perturb the cone record the way the device's approximate rsqrtf may.  out = {pairs, skipped, skipped AND hit, hit}.
+int hd_cull_spheres(const float* origin, const float* spheres, uint32_t n, const float* dirs, uint32_t m, float axis_scale, float w_shift, uint64_t* out) {
+    const f3 o = mk3(origin[0], origin[1], origin[2]);
+    uint64_t pairs = 0, skipped = 0, wrong = 0, hits = 0;
+    for (uint32_t s = 0; s < n; ++s) {
+        const float4 sp = make_float4(spheres[4 * s], spheres[4 * s + 1], spheres[4 * s + 2], spheres[4 * s + 3]);
+        float4 q = cone_of_sphere(o, sp.x, sp.y, sp.z, fabsf(sp.w));
+        if (q.w != -2.0f) { q.x *= axis_scale; q.y *= axis_scale; q.z *= axis_scale; q.w += w_shift; }
+        for (uint32_t k = 0; k < m; ++k) {
+            const float* dv = dirs + 3 * ((size_t)s * m + k);
+            const f3 d = norm3(mk3(dv[0], dv[1], dv[2]));
+            float t, dist;
+            const bool hit = sphere_intersect(sp, o, d, t, dist) != 0, skip = outside_double_cone(q, d);
+            ++pairs; skipped += skip; hits += hit; wrong += skip && hit;
+        }
+    }
+    out[0] = pairs; out[1] = skipped; out[2] = wrong; out[3] = hits;
+    return 0;
+}
+
+// The same for mesh boxes: boxes = n x {lo xyz, hi xyz}; skipped = outside_cone of the box's bounding sphere (as k_generate builds it), hit = mesh_bbox_hit
+int hd_cull_boxes(const float* origin, const float* boxes, uint32_t n, const float* dirs, uint32_t m, float axis_scale, float w_shift, uint64_t* out) {
+    const f3 o = mk3(origin[0], origin[1], origin[2]);
+    uint64_t pairs = 0, skipped = 0, wrong = 0, hits = 0;
+    for (uint32_t b = 0; b < n; ++b) {
+        MeshDev M; memset(&M, 0, sizeof(M));
+        for (int k = 0; k < 3; ++k) { M.lo[k] = boxes[6 * b + k]; M.hi[k] = boxes[6 * b + 3 + k]; }
+        const float hx = 0.5f * (M.hi[0] - M.lo[0]), hy = 0.5f * (M.hi[1] - M.lo[1]), hz = 0.5f * (M.hi[2] - M.lo[2]);
+        float4 q = cone_of_sphere(o, M.lo[0] + hx, M.lo[1] + hy, M.lo[2] + hz, 1.001f * sqrtf(hx * hx + hy * hy + hz * hz) + 1e-6f);
+        if (q.w != -2.0f) { q.x *= axis_scale; q.y *= axis_scale; q.z *= axis_scale; q.w += w_shift; }
+        for (uint32_t k = 0; k < m; ++k) {
+            const float* dv = dirs + 3 * ((size_t)b * m + k);
+            const f3 d = norm3(mk3(dv[0], dv[1], dv[2]));
+            const bool hit = mesh_bbox_hit(M, o, d), skip = outside_cone(q, d);
+            ++pairs; skipped += skip; hits += hit; wrong += skip && hit;
+        }
+    }
+    out[0] = pairs; out[1] = skipped; out[2] = wrong; out[3] = hits;
     return 0;
 }
 

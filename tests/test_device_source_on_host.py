@@ -31,7 +31,7 @@ P = C.POINTER
 def hd():
     out = os.path.join(HD, "build", "libhost_device.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    srcs = [os.path.join(HD, "harness.cpp"), os.path.join(HD, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("common.cuh", "intersect.cuh", "shade.cuh")]
+    srcs = [os.path.join(HD, "harness.cpp"), os.path.join(HD, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("common.cuh", "intersect.cuh", "shade.cuh", "cull.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         # -I tests/host_device FIRST: `#include <cuda_runtime.h>` in common.cuh finds the stand-in.  No contraction, no FMA, as the oracle.
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-mno-fma", "-DRBRT_LDG128", "-Wno-unknown-pragmas", "-fPIC", "-shared",
@@ -41,6 +41,8 @@ def hd():
     lib.hd_trace_rays.argtypes = scene_args + [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_render.argtypes = scene_args + [P(_abi.CameraC), C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_scatter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    for f in (lib.hd_cull_spheres, lib.hd_cull_boxes):
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
     return lib
 
 
@@ -200,3 +202,77 @@ def test_scatter_against_the_oracle(hd, oracle):
     g_od = np.array([[o.out_ray.direction.x, o.out_ray.direction.y, o.out_ray.direction.z] for o in out], np.float32)
     assert np.array_equal(g_sc, o_sc) and np.array_equal(bits(g_att), bits(o_att)) and np.array_equal(bits(g_od), bits(o_od))
     assert 0 < g_sc.sum() < len(items)
+
+
+def directions_around(axis, half_angle, m, rng):
+    """m directions per axis [n,3] (f64): most within a relative 1e-8 .. 1e-1 of the cone of `half_angle` [n] on either side, some anywhere,
+    some exactly along / against the axis; returned as f32 with lengths that are not exactly 1."""
+    n = len(axis)
+    a = axis / np.linalg.norm(axis, axis=1, keepdims=True)
+    helper = np.where(np.abs(a[:, :1]) < 0.9, np.array([[1.0, 0.0, 0.0]]), np.array([[0.0, 1.0, 0.0]]))
+    u = np.cross(a, helper); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    v = np.cross(a, u)
+    delta = 10.0 ** rng.uniform(-8, -1, (n, m)) * rng.choice([-1.0, 1.0], (n, m))
+    # ... of the TRUE cone (where the exact test changes its answer) for one half of them, of the cull's own cone (cos^2 lowered by the 1e-4 margin:
+    # where the cull changes ITS answer) for the other
+    cull_angle = np.arccos(np.sqrt(np.clip(np.cos(half_angle) ** 2 - 1e-4, 0.0, 1.0)))
+    theta = np.where(rng.random((n, m)) < 0.5, half_angle[:, None], cull_angle[:, None]) * (1.0 + delta)
+    anywhere = rng.random((n, m)) < 0.15
+    theta = np.where(anywhere, rng.uniform(0, np.pi, (n, m)), theta)
+    theta[:, 0] = 0.0; theta[:, 1] = np.pi                                  # along and against the axis
+    theta[:, 2] = np.pi - half_angle; theta[:, 3] = np.pi - half_angle * (1 + 1e-6)     # the cone BEHIND the origin (quirk Q16: not a provable miss for spheres)
+    phi = rng.uniform(0, 2 * np.pi, (n, m))
+    d = (np.cos(theta)[..., None] * a[:, None, :] + np.sin(theta)[..., None] * (np.cos(phi)[..., None] * u[:, None, :] + np.sin(phi)[..., None] * v[:, None, :]))
+    d *= 1.0 + rng.uniform(-2e-7, 2e-7, (n, m, 1))
+    return np.ascontiguousarray(d, dtype=np.float32)
+
+
+def test_camera_ray_culling_only_skips_provable_misses(hd):
+    """cull.cuh: the cone tests k_generate puts in front of the exact sphere test and the mesh-box test for camera rays.  A skipped test must be one
+    the exact arithmetic answers with "no hit" — for spheres and boxes of every size and distance, origins far from the world origin, directions
+    hugging the cone from both sides (and the mirrored cone behind the camera), with the cone record perturbed the way the device's approximate
+    rsqrtf may perturb it.  ~25 M (element, direction) pairs; both outcomes of both tests occur in quantity."""
+    rng = np.random.default_rng(23)
+    totals = np.zeros(4, np.uint64)
+    origins = [(0.0, 5.0, 4.0), (0.0, 0.0, 0.0), (-37.5, 12.25, 80.0), (1.0e4, -2.0e3, 5.0e3), (3.0e5, 3.0e5, -3.0e5)]
+    for oi, origin in enumerate(origins):
+        o = np.array(origin, np.float64)
+        n, m = 600, 1400
+        r = 10.0 ** rng.uniform(-3, 3, n)
+        dist = r * (1.0 + 10.0 ** rng.uniform(-2.2, 3.5, n))                # from 0.6 % outside the surface (never culled: within 1 %) to 3000 radii away
+        axis = rng.normal(size=(n, 3))
+        axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+        centre = o + axis * dist[:, None]
+        spheres = np.ascontiguousarray(np.concatenate([centre, r[:, None]], 1), dtype=np.float32)
+        # the angles are taken from the f32 values the kernel sees
+        c32, r32, o32 = spheres[:, :3].astype(np.float64), spheres[:, 3].astype(np.float64), np.array(origin, np.float32).astype(np.float64)
+        l = c32 - o32
+        D = np.linalg.norm(l, axis=1)
+        ok = D > r32 * 1.0001
+        half = np.arcsin(np.clip(r32 / np.maximum(D, 1e-300), 0, 1))
+        dirs = directions_around(np.where(ok[:, None], l, axis), np.where(ok, half, 0.3), m, rng)
+        o_f32 = np.array(origin, np.float32)
+        for scale, shift in ((1.0, 0.0), (1.0 + 3e-7, 2e-7), (1.0 - 3e-7, 2e-7)):
+            out = np.zeros(4, np.uint64)
+            assert hd.hd_cull_spheres(o_f32.ctypes.data, spheres.ctypes.data, n, dirs.ctypes.data, m, scale, shift, out.ctypes.data) == 0
+            assert out[2] == 0, f"origin {origin}: {int(out[2])} sphere tests were skipped although the exact test reports a hit (scale {scale}, shift {shift})"
+            totals += out
+        # boxes: random extents (flat ones too) around the same centres
+        ext = r[:, None] * 10.0 ** rng.uniform(-2, 0, (n, 3))
+        boxes = np.ascontiguousarray(np.concatenate([centre - ext, centre + ext], 1), dtype=np.float32)
+        b_lo, b_hi = boxes[:, :3].astype(np.float64), boxes[:, 3:].astype(np.float64)
+        bc, br = 0.5 * (b_lo + b_hi), 0.5 * np.linalg.norm(b_hi - b_lo, axis=1)
+        lb = bc - o32
+        Db = np.linalg.norm(lb, axis=1)
+        okb = Db > br * 1.0001
+        halfb = np.arcsin(np.clip(br / np.maximum(Db, 1e-300), 0, 1))
+        dirs = directions_around(np.where(okb[:, None], lb, axis), np.where(okb, halfb, 0.3), m, rng)
+        dirs[:, 4:40, rng.integers(0, 3)] = 0.0                              # axis-parallel components: the slab test divides by them (aabbox.rs:30-47)
+        for scale, shift in ((1.0, 0.0), (1.0 + 3e-7, 2e-7)):
+            out = np.zeros(4, np.uint64)
+            assert hd.hd_cull_boxes(o_f32.ctypes.data, boxes.ctypes.data, n, dirs.ctypes.data, m, scale, shift, out.ctypes.data) == 0
+            assert out[2] == 0, f"origin {origin}: {int(out[2])} box tests were skipped although the slab test reports a hit (scale {scale}, shift {shift})"
+            totals += out
+    pairs, skipped, wrong, hits = (int(x) for x in totals)
+    assert pairs > 2e7 and wrong == 0
+    assert skipped > 0.15 * pairs and hits > 0.15 * pairs                    # the cull is active and the exact tests do hit: neither side is vacuous
