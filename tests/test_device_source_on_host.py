@@ -143,6 +143,18 @@ def test_bvh_traversal_source_against_the_oracle(hd, oracle):
             assert vcnt == cnt                                                                            # the same visits and tests, in another schedule
             if n_keep >= 1277:
                 assert 0 < cnt["nodes"] and cnt["tris"] < brute["tris"] / 20                              # the tree did prune
+    # ties and near-ties: every triangle three times (exact copies and a copy shifted by a few ulp), shuffled — "the first index with the smallest t"
+    # (triangle.rs:392-410) must survive the prune bound that follows the best hit so far
+    base = synth.displaced_icosphere(2, 3.0, (5.0, 1.4, -12.5))
+    shifted = base + np.float32(3e-6) * rng.normal(size=(len(base), 1, 3)).astype(np.float32)
+    stack = np.concatenate([base, base, shifted], 0)[rng.permutation(3 * len(base))]
+    scene = R.Scene()
+    scene.triangle_meshes.append(R.TriangleMesh.from_triangles(stack, R.Lambertian(Vec3(0.5, 0.5, 0.5))))
+    rays = np.concatenate([oracle.primary_rays(S.example_camera(64, 48).to_c(), 11, 0), S.random_rays(3000, (5.0, 1.4, -12.5), 4.0, 6)], 0)
+    want = oracle.OracleScene.from_scene(scene).hit(rays)
+    assert (want["kind"] == 1).sum() > 500
+    for leaf in (1, 2, 8, 17, 24):
+        assert_hits(hd_hit(hd, scene, rays, leaf), want, f"stacked copies leaf={leaf}")
     # a larger mesh (20 480 triangles) + the fixture's spheres in front of and behind it: the limit handed to the traversal comes from the spheres
     scene = S.spheres_scene()
     scene.triangle_meshes.append(R.TriangleMesh.from_triangles(synth.displaced_icosphere(5, 3.0, (5.0, 1.4, -12.5)), R.Dielectric(0.2)))
