@@ -373,4 +373,37 @@ int hd_cull_boxes(const float* origin, const float* boxes, uint32_t n, const flo
     return 0;
 }
 
+// fast_div (common.cuh: the pixel mapping's division by launch-invariant divisors): mismatches against `/` over the given dividends and divisors
+uint64_t hd_fastdiv_mismatches(const uint32_t* divisors, uint32_t nd, const uint32_t* dividends, uint32_t nn) {
+    uint64_t bad = 0;
+    for (uint32_t i = 0; i < nd; ++i) {
+        const FastDiv f = make_fastdiv(divisors[i]);
+        for (uint32_t k = 0; k < nn; ++k) bad += fast_div(dividends[k], f) != dividends[k] / divisors[i];
+    }
+    return bad;
+}
+
+// shard_pixel (common.cuh) over ALL ranks of a tile-sharded W x H image, ShardDev filled as make_shard (render.cu) fills it:
+// visits[row * W + col] += 1 for every (rank, j) that maps to a pixel.  A correct mapping leaves every entry at exactly 1.
+int hd_shard_visits(uint32_t W, uint32_t H, uint32_t count, uint32_t* visits, uint32_t* max_paths_per_rank) {
+    CamDev cam; memset(&cam, 0, sizeof(cam)); cam.width = W; cam.height = H;
+    uint32_t most = 0;
+    for (uint32_t rank = 0; rank < count; ++rank) {
+        ShardDev sh; memset(&sh, 0, sizeof(sh));
+        sh.rank = rank; sh.count = count;
+        sh.tiles_x = (W + 7) / 8; sh.fd_tiles_x = make_fastdiv(sh.tiles_x); sh.tiles_total = sh.tiles_x * ((H + 3) / 4);
+        sh.tiles_mine = sh.tiles_total > sh.rank ? (sh.tiles_total - sh.rank + sh.count - 1) / sh.count : 0;
+        const uint32_t P = sh.tiles_mine * 32;
+        most = P > most ? P : most;
+        for (uint32_t j = 0; j < P; ++j) {
+            uint32_t row, col;
+            if (shard_pixel(sh, cam, j, row, col)) { if (row >= H || col >= W) return 1; ++visits[(size_t)row * W + col]; }
+        }
+        uint32_t row, col;                                         // one past the rank's range must not map to a pixel of ANOTHER rank's tile inside the image...
+        (void)shard_pixel(sh, cam, P, row, col);                   // (...it may: the kernels never ask; just make sure it does not crash)
+    }
+    if (max_paths_per_rank) *max_paths_per_rank = most;
+    return 0;
+}
+
 }  // extern "C"

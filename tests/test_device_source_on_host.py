@@ -41,6 +41,8 @@ def hd():
     lib.hd_trace_rays.argtypes = scene_args + [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_render.argtypes = scene_args + [P(_abi.CameraC), C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_scatter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.hd_fastdiv_mismatches.argtypes, lib.hd_fastdiv_mismatches.restype = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32], C.c_uint64
+    lib.hd_shard_visits.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, P(C.c_uint32)]
     for f in (lib.hd_cull_spheres, lib.hd_cull_boxes):
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
     return lib
@@ -288,3 +290,24 @@ def test_camera_ray_culling_only_skips_provable_misses(hd):
     pairs, skipped, wrong, hits = (int(x) for x in totals)
     assert pairs > 2e7 and wrong == 0
     assert skipped > 0.15 * pairs and hits > 0.15 * pairs                    # the cull is active and the exact tests do hit: neither side is vacuous
+
+
+def test_pixel_mapping_of_tile_shards(hd):
+    """common.cuh: fast_div equals `/` for every divisor the mapping can see, and shard_pixel over all ranks of a tile-sharded image visits every
+    pixel exactly once — for image sizes that are not multiples of the 8 x 4 tile, 1 .. 8 and odd rank counts, more ranks than tiles."""
+    rng = np.random.default_rng(3)
+    divisors = np.unique(np.concatenate([np.arange(1, 600), 2 ** np.arange(0, 32), 2 ** np.arange(1, 32) - 1, 2 ** np.arange(1, 31) + 1,
+                                         rng.integers(1, 2 ** 32, 300), [240, 480, 1920 // 8, 3840 // 8, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000]])).astype(np.uint32)
+    dividends = np.unique(np.concatenate([np.arange(0, 5000), 2 ** 32 - 1 - np.arange(0, 5000), rng.integers(0, 2 ** 32, 20000),
+                                          (divisors.astype(np.uint64)[:, None] * rng.integers(1, 2 ** 16, (len(divisors), 8)).astype(np.uint64) + np.array([-1, 0, 1, 0, -1, 1, 0, -1])).ravel() % 2 ** 32])).astype(np.uint32)
+    assert hd.hd_fastdiv_mismatches(divisors.ctypes.data, len(divisors), dividends.ctypes.data, len(dividends)) == 0
+    for W, H in ((1920, 1080), (64, 48), (13, 10), (8, 4), (7, 3), (1, 1), (257, 129), (3840, 2160)):
+        for count in (1, 2, 3, 4, 7, 8, 64):
+            if W * H > 3e6 and count not in (1, 8):
+                continue
+            visits = np.zeros(W * H, np.uint32)
+            most = C.c_uint32(0)
+            assert hd.hd_shard_visits(W, H, count, visits.ctypes.data, C.byref(most)) == 0
+            assert (visits == 1).all(), (W, H, count, int((visits != 1).sum()))
+            tiles = ((W + 7) // 8) * ((H + 3) // 4)
+            assert most.value == 32 * ((tiles + count - 1) // count)             # interleaved tiles: no rank has more than one tile above its share
