@@ -143,7 +143,8 @@ enum {
 typedef struct rbrt_scene_opts {
     uint32_t simd_lanes;     /* RBRT_LANES_*; 0 = 8 */
     uint32_t leaf_size;      /* max triangles per BVH leaf; 0 = default */
-    float    box_pad_rel;    /* conservative padding of BVH boxes relative to the mesh extent; 0 = default (2e-5), <0 = none */
+    float    box_pad_rel;    /* conservative padding of BVH boxes relative to the mesh's largest coordinate; 0 = default (2e-5, and never less
+                              * than 2^-21 * (that coordinate + 1000): rays may start 1000 units away), <0 = none */
     uint32_t flags;          /* RBRT_SCENE_* */
 } rbrt_scene_opts;
 

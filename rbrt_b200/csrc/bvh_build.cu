@@ -347,7 +347,14 @@ __global__ void k_mesh_setup(const int* __restrict__ mm, MeshDev proto, float pa
         md.lo[k] = lo[k]; md.hi[k] = hi[k];
         mx = fmaxf(mx, fmaxf(fabsf(lo[k]), fabsf(hi[k]))); mx = fmaxf(mx, hi[k] - lo[k]);
     }
-    const float pad = pad_rel * mx;
+    // Padding of the leaf boxes.  Relative to the mesh's coordinates it covers the rounding of the reference's own arithmetic for rays that start
+    // near the mesh; a ray may start up to t < 1000 away (triangle.rs:146), and then `o - v0` and the direction carry ~ulp(|o|): for a SMALL mesh
+    // NEAR THE WORLD ORIGIN the exact test shifts by more than 2e-5 * mx and accepts rays that miss the padded box (found with the host build of
+    // the traversal, tests/test_device_source_on_host.py: 0.5 % of edge-aimed rays from 990 units away on a mesh of size 0.2; a padding of 6e-5
+    // made them vanish).  Hence a floor of 2^-21 * (mx + 1000) = 4.8e-4 and up: it also covers the slab test's own reciprocal (MUFU.RCP, ~1 ulp:
+    // 1.2e-4 at t = 1000; the host build emulates 2 ulp of it and stays clean) and exceeds the relative pad only for mx < 24.4.
+    // pad_rel = 0 (box_pad_rel < 0: "none") stays none.
+    const float pad = pad_rel > 0.0f ? fmaxf(pad_rel * mx, 4.7683716e-7f * (mx + 1000.0f)) : 0.0f;
     bp->pad = pad;
     for (int k = 0; k < 3; ++k) {                                          // 16-bit grid over the padded mesh box, 8 steps of slack per side
         float ext = (hi[k] + pad) - (lo[k] - pad);

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,6 +26,9 @@
 #include "../../include/rbrt_gpu.h"
 
 using namespace rbrt;
+
+float hd_rcp_error = 0.0f;
+unsigned hd_rcp_calls = 0;
 
 namespace {
 
@@ -63,6 +67,9 @@ inline uint32_t quant_hi(float v, float org, float step) {
     while (q < 65535.0f && fmaf(q, step, org) < v) q += 1.0f;
     return (uint32_t)fminf(fmaxf(q, 0.0f), 65535.0f);
 }
+
+// rbrt_scene_opts.box_pad_rel as api.cu resolves it (default 2e-5); HD_BOX_PAD_REL overrides it for experiments
+inline float pad_rel() { const char* e = getenv("HD_BOX_PAD_REL"); return e ? (float)atof(e) : 2e-5f; }
 
 struct TreeBuilder {
     const std::vector<Box>& tb;                                // per triangle (already padded), in the order `order` lists them
@@ -146,7 +153,7 @@ void flatten(HostScene& hs, const rbrt_element_ref* order, uint32_t ne, const rb
         if (leaf_size && n_eff) {                                    // grid as k_mesh_setup lays it, then the tree; triangles go out in tree order
             float mx = 0.0f;
             for (int k = 0; k < 3; ++k) { mx = fmaxf(mx, fmaxf(fabsf(md.lo[k]), fabsf(md.hi[k]))); mx = fmaxf(mx, md.hi[k] - md.lo[k]); }
-            const float pad = 2e-5f * mx;
+            const float pad = pad_rel() > 0.0f ? fmaxf(pad_rel() * mx, (getenv("HD_NO_PAD_FLOOR") ? 0.0f : (getenv("HD_PAD_FLOOR") ? (float)atof(getenv("HD_PAD_FLOOR")) : 4.7683716e-7f) * (mx + 1000.0f))) : 0.0f;   // k_mesh_setup
             for (int k = 0; k < 3; ++k) {
                 float ext = (md.hi[k] + pad) - (md.lo[k] - pad), step = ext / 65500.0f;
                 if (!(step > 1e-30f)) step = 1e-30f;
@@ -230,6 +237,8 @@ Hit scene_hit_voted(const SceneDev& S, f3 o, f3 d, TraceCounters* cnt) {
 }  // namespace
 
 extern "C" {
+
+void hd_set_rcp_error(float e) { hd_rcp_error = e; hd_rcp_calls = 0; }
 
 // Scene::hit for caller-supplied rays, records filled as k_trace_rays (render.cu) fills them
 int hd_trace_rays(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris, const rbrt_mesh_desc* meshes,

@@ -109,3 +109,22 @@ def stress_scene():
     scene.elements += [R.Sphere(c, r, m) for c, r, m in spheres]
     scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, mat))
     return scene
+
+
+def edge_aimed_rays(tris, n, dist, seed=0):
+    """n rays that start `dist` away and aim at points on the edges and corners of the triangles [N,3,3]: where a closest-hit answer hangs on the
+    last bits of the arithmetic (used for far origins: `o - v0` and the direction then carry ~ulp(|o|) of noise)."""
+    rng = np.random.default_rng(seed)
+    ti = rng.integers(0, len(tris), n)
+    b = rng.random((n, 3))
+    kind = rng.integers(0, 3, n)
+    b[kind == 0, 0] = 0.0
+    b[kind == 1, :2] = 0.0
+    b /= b.sum(1, keepdims=True)
+    target = (np.asarray(tris, np.float64)[ti] * b[:, :, None]).sum(1)
+    back = rng.normal(size=(n, 3))
+    back /= np.linalg.norm(back, axis=1, keepdims=True)
+    o = (target - back * dist).astype(np.float32)
+    d = target - o.astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d.astype(np.float32)], 1).astype(np.float32)

@@ -43,6 +43,7 @@ def hd():
     lib.hd_scatter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.hd_fastdiv_mismatches.argtypes, lib.hd_fastdiv_mismatches.restype = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32], C.c_uint64
     lib.hd_shard_visits.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, P(C.c_uint32)]
+    lib.hd_set_rcp_error.argtypes = [C.c_float]
     for f in (lib.hd_cull_spheres, lib.hd_cull_boxes):
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
     return lib
@@ -311,3 +312,32 @@ def test_pixel_mapping_of_tile_shards(hd):
             assert (visits == 1).all(), (W, H, count, int((visits != 1).sum()))
             tiles = ((W + 7) // 8) * ((H + 3) // 4)
             assert most.value == 32 * ((tiles + count - 1) // count)             # interleaved tiles: no rank has more than one tile above its share
+
+
+def test_small_mesh_near_the_world_origin_far_ray_origins(hd, oracle, monkeypatch):
+    """Found with this host build: a box padding that is only RELATIVE to the mesh's coordinates is too small for a small mesh near the world
+    origin when rays start hundreds of units away (they may: t < 1000, triangle.rs:146) — the exact test's `o - v0` then carries ~ulp(|o|) and accepts
+    rays that miss the padded boxes.  k_mesh_setup (bvh_build.cu) therefore keeps the padding above 2^-21 * (mx + 1000); the harness' builder follows
+    the same rule.  With the floor the traversal returns the oracle's hits; without it (HD_NO_PAD_FLOOR) the same rays show the mismatches."""
+    from rbrt_b200 import synth
+    total_without = 0
+    for subdiv, size, centre, dist in ((1, 0.2, (0, 0, 0), 990.0), (0, 0.05, (0, 0, 0), 100.0), (0, 0.05, (0, 0, 0), 990.0), (2, 0.3, (0.05, 0.02, -0.03), 990.0),
+                                       (1, 0.2, (0, 0, 0), 10.0), (2, 1.0, (0, 0, 0), 990.0)):
+        tris = synth.displaced_icosphere(subdiv, size, centre)
+        scene = R.Scene()
+        scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, R.Lambertian(Vec3(0.5, 0.5, 0.5))))
+        rays = S.edge_aimed_rays(tris, 60000, dist, seed=subdiv + int(dist))
+        want = oracle.OracleScene.from_scene(scene).hit(rays)
+        assert (want["kind"] == 1).sum() > 30000
+        for leaf in (1, 4, 17):
+            assert_hits(hd_hit(hd, scene, rays, leaf), want, f"size {size} dist {dist} leaf {leaf}")
+        for err in (2.4e-7, -2.4e-7):                                        # the device's reciprocal in ray_slabs is not the exact quotient: twice its ~1 ulp, both ways
+            hd.hd_set_rcp_error(err)
+            try:
+                assert_hits(hd_hit(hd, scene, rays, 1), want, f"size {size} dist {dist} reciprocal error {err}")
+            finally:
+                hd.hd_set_rcp_error(0.0)
+        monkeypatch.setenv("HD_NO_PAD_FLOOR", "1")
+        total_without += int((~S.hits_equal(hd_hit(hd, scene, rays, 1), want)).sum())
+        monkeypatch.delenv("HD_NO_PAD_FLOOR")
+    assert total_without > 100                                               # the floor is what closes the gap

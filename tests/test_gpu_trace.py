@@ -264,3 +264,20 @@ def test_tangent_sphere_behind_the_ray_is_hit(gpu, oracle):
         assert want["kind"][0] == 0 and want["t"][0] == -5.0 and want["kind"][2] == 0 and want["kind"][3] == -1
         for mode in MODES:
             assert_same(sc.hit(rays, mode), want, f"{n_extra} extra spheres, mode {mode}")
+
+
+def test_small_mesh_near_the_world_origin_far_ray_origins(gpu, oracle):
+    """Rays that start up to 990 units away from a small mesh near the world origin, aimed at triangle edges (the reference accepts t < 1000,
+    triangle.rs:146): `o - v0` carries ~ulp(|o|) there, more than a box padding relative to the mesh's own coordinates covers.  The builder keeps the
+    padding above 2^-21 * (mx + 1000) (bvh_build.cu k_mesh_setup; found and sized with the host build of the traversal,
+    tests/test_device_source_on_host.py).  All three trace modes against the oracle, bit for bit."""
+    for subdiv, size, centre, dist in ((1, 0.2, (0, 0, 0), 990.0), (0, 0.05, (0, 0, 0), 100.0), (0, 0.05, (0, 0, 0), 990.0), (2, 0.3, (0.05, 0.02, -0.03), 990.0),
+                                       (2, 1.0, (0, 0, 0), 990.0)):
+        tris = synth.displaced_icosphere(subdiv, size, centre)
+        scene = R.Scene()
+        scene.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, R.Lambertian(Vec3(0.5, 0.5, 0.5))))
+        rays = S.edge_aimed_rays(tris, 60000, dist, seed=subdiv + int(dist))
+        want = oracle.OracleScene.from_scene(scene).hit(rays)
+        assert (want["kind"] == 1).sum() > 30000
+        for mode in MODES:
+            assert_same(scene.hit(rays, mode), want, f"size {size} dist {dist} mode {mode}")
