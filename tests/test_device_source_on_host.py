@@ -341,3 +341,58 @@ def test_small_mesh_near_the_world_origin_far_ray_origins(hd, oracle, monkeypatc
         total_without += int((~S.hits_equal(hd_hit(hd, scene, rays, 1), want)).sum())
         monkeypatch.delenv("HD_NO_PAD_FLOOR")
     assert total_without > 100                                               # the floor is what closes the gap
+
+
+def test_traversal_in_awkward_regimes(hd, oracle):
+    """Regimes the GPU suite's scenes do not reach, swept once with scripts/host_model/explore.py at 200 000 rays each and kept here at a smaller size:
+    bounce rays that start ON the surface (also nearly tangent, also inward), direction components down to 1e-38, a flat mesh with in-plane rays,
+    coordinates of 1e5, un-normalised directions from 1e-2 to 1e6, a sphere coinciding with the mesh (sphere / mesh near-ties: the limit handed to the
+    traversal) seen from 10 to 900 units away."""
+    from rbrt_b200 import synth
+    rng = np.random.default_rng(42)
+    n = 40000
+    tris = synth.displaced_icosphere(4, 3.0, (5.0, 1.4, -12.5))
+
+    def mesh_scene(t):
+        sc = R.Scene()
+        sc.triangle_meshes.append(R.TriangleMesh.from_triangles(np.asarray(t, np.float32), R.Lambertian(Vec3(0.5, 0.5, 0.5))))
+        return sc
+
+    def check(name, scene, rays, min_hits):
+        rays = np.ascontiguousarray(rays, dtype=np.float32)
+        want = oracle.OracleScene.from_scene(scene).hit(rays)
+        assert (want["kind"] == 1).sum() >= min_hits, (name, int((want["kind"] == 1).sum()))
+        for leaf in (1, 17, 4):
+            assert_hits(hd_hit(hd, scene, rays, leaf), want, f"{name} leaf {leaf}")
+
+    ti = rng.integers(0, len(tris), n)
+    b = rng.random((n, 3)); b /= b.sum(1, keepdims=True)
+    p = (tris[ti].astype(np.float64) * b[:, :, None]).sum(1)
+    nrm = np.cross(tris[ti, 1] - tris[ti, 0], tris[ti, 2] - tris[ti, 0]).astype(np.float64); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tangent = d - (d * nrm).sum(1, keepdims=True) * nrm * (1 - 10.0 ** rng.uniform(-6, -1, (n, 1)))
+    d = np.where(rng.random((n, 1)) < 0.5, d, tangent); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    scene = mesh_scene(tris)
+    check("bounce rays from the surface", scene, np.concatenate([p, d], 1), 10000)
+    check("inward rays from the surface", scene, np.concatenate([p, -np.abs((d * nrm).sum(1, keepdims=True)) * nrm + 0.3 * d], 1), 10000)
+    d2 = d.copy(); d2[np.arange(n), rng.integers(0, 3, n)] *= 10.0 ** rng.uniform(-38, -5, n)
+    check("tiny direction components", scene, np.concatenate([np.array((5.0, 1.4, -12.5)) + rng.normal(0, 4, (n, 3)), d2], 1), 3000)
+    base = np.concatenate([S.random_rays(n // 2, (5.0, 1.4, -12.5), 4.0, 1), S.edge_aimed_rays(tris, n // 2, 30.0, 2)], 0)
+    for scale, min_hits in ((1e-2, 50), (0.1, 10000), (10.0, 10000), (1e3, 10000), (1e6, 50)):
+        r = base.copy(); r[:, 3:] *= np.float32(scale)
+        check(f"|d| = {scale:g}", scene, r, min_hits)
+    g = np.linspace(-2, 2, 21)
+    X, Y = np.meshgrid(g, g)
+    Pz = np.stack([X, Y, np.full_like(X, -5.0)], -1)
+    flat = np.array([t for i in range(20) for j in range(20) for t in ([Pz[i, j], Pz[i + 1, j], Pz[i, j + 1]], [Pz[i + 1, j], Pz[i + 1, j + 1], Pz[i, j + 1]])])
+    inplane = np.concatenate([np.stack([rng.uniform(-3, 3, n // 4), rng.uniform(-3, 3, n // 4), np.full(n // 4, -5.0)], 1),
+                              np.stack([rng.normal(size=n // 4), rng.normal(size=n // 4), np.zeros(n // 4)], 1)], 1)
+    check("flat mesh", mesh_scene(flat), np.concatenate([S.random_rays(n // 2, (0, 0, -5), 3.0, 3), inplane, S.edge_aimed_rays(flat, n // 4, 50.0, 1)], 0), 5000)
+    c = (1e5, 0.5e5, -1e5)
+    far = synth.displaced_icosphere(3, 300.0, c)
+    check("coordinates of 1e5", mesh_scene(far), np.concatenate([S.edge_aimed_rays(far, n // 2, 900.0, 3), S.random_rays(n // 2, c, 400.0, 4)], 0), 10000)
+    both = R.Scene()
+    both.elements.append(R.Sphere(Vec3(5.0, 1.4, -12.5), 3.0, R.Dielectric(1.5)))
+    both.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, R.Lambertian(Vec3(0.5, 0.5, 0.5))))
+    for dist in (10.0, 300.0, 900.0):
+        check(f"sphere inside the mesh from {dist:g}", both, S.edge_aimed_rays(tris, n, dist, 3 + int(dist)), 10000)
