@@ -396,3 +396,16 @@ def test_traversal_in_awkward_regimes(hd, oracle):
     both.triangle_meshes.append(R.TriangleMesh.from_triangles(tris, R.Lambertian(Vec3(0.5, 0.5, 0.5))))
     for dist in (10.0, 300.0, 900.0):
         check(f"sphere inside the mesh from {dist:g}", both, S.edge_aimed_rays(tris, n, dist, 3 + int(dist)), 10000)
+    # three meshes in YAML order — two interpenetrating, one of them the SAME mesh twice (exact ties between meshes: the earlier one wins, scene.rs:36) —
+    # and an empty one: the best hit so far bounds the traversal of the next mesh
+    several = R.Scene()
+    other = synth.displaced_icosphere(3, 2.5, (6.0, 1.0, -11.5), seed=99)
+    for t, m in ((other, R.Metal(Vec3(0.9, 0.9, 0.9), 0.1)), (tris, R.Lambertian(Vec3(0.5, 0.5, 0.5))), (np.zeros((0, 3, 3), np.float32), R.Dielectric(1.5)),
+                 (tris, R.Dielectric(0.2))):
+        several.triangle_meshes.append(R.TriangleMesh.from_triangles(t, m))
+    several.elements.append(R.Sphere(Vec3(4.0, 1.4, -9.0), 1.0, R.Dielectric(1.8)))
+    rays = np.concatenate([S.edge_aimed_rays(tris, n // 2, 40.0, 12), S.edge_aimed_rays(other, n // 2, 700.0, 13), S.random_rays(n // 2, (5.5, 1.2, -12.0), 3.0, 14)], 0)
+    want = oracle.OracleScene.from_scene(several).hit(rays)
+    assert set(np.unique(want["elem_idx"][want["kind"] == 1]).tolist()) == {0, 1} and (want["kind"] == 0).sum() > 100     # mesh 3 never beats its twin, mesh 1
+    for leaf in (1, 17, 4):
+        assert_hits(hd_hit(hd, several, rays, leaf), want, f"several meshes leaf {leaf}")
