@@ -269,9 +269,10 @@ int hd_trace_rays(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_
 
 // render_scene (lib.rs:75-124) with the product's device functions: hdr_out H x W x 3 (pre-gamma mean), rgb_out H x W x 3
 int hd_render(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc* spheres, const rbrt_triangle_desc* btris, const rbrt_mesh_desc* meshes,
-              uint32_t nm, uint32_t lanes, const rbrt_camera* cam, uint32_t spp, uint64_t seed, uint32_t max_depth, float* hdr_out, uint8_t* rgb_out,
-              uint64_t* rays_out, uint64_t* nan_out) {
-    HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes);
+              uint32_t nm, uint32_t lanes, uint32_t leaf_size /* as hd_trace_rays: 0 brute force, 1..8 BVH, + 16 voted */, const rbrt_camera* cam, uint32_t spp,
+              uint64_t seed, uint32_t max_depth, float* hdr_out, uint8_t* rgb_out, uint64_t* rays_out, uint64_t* nan_out) {
+    const bool voted = (leaf_size & 16u) != 0; leaf_size &= 15u;
+    HostScene hs; flatten(hs, order, ne, spheres, btris, meshes, nm, lanes, leaf_size);
     const SceneDev& S = hs.dev;
     CamDev c;
     const rbrt_vec3* src[4] = {&cam->position, &cam->right, &cam->up, &cam->img_center_point};
@@ -293,7 +294,7 @@ int hd_render(const rbrt_element_ref* order, uint32_t ne, const rbrt_sphere_desc
                 f3 color = mk3(0.0f, 0.0f, 0.0f);
                 for (uint32_t it = 0;; ++it) {                                                     // `it` scatters lie behind this ray
                     ++rays;
-                    Hit h = scene_hit<true>(S, o, d, nullptr);
+                    Hit h = !leaf_size ? scene_hit<true>(S, o, d, nullptr) : (voted ? scene_hit_voted(S, o, d, nullptr) : scene_hit<false>(S, o, d, nullptr));
                     if (h.kind == -2) { ++nans; break; }                                          // the reference panics (sphere.rs:33); the product ends the path black
                     if (h.kind < 0) {                                                             // miss: sky, then att_1 * (att_2 * (... * sky)) (lib.rs:62-71)
                         color = sky(d);

@@ -39,7 +39,7 @@ def hd():
     lib = C.CDLL(out)
     scene_args = [P(_abi.ElementRefC), C.c_uint32, P(_abi.SphereDescC), P(_abi.TriangleDescC), P(_abi.MeshDescC), C.c_uint32, C.c_uint32]
     lib.hd_trace_rays.argtypes = scene_args + [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
-    lib.hd_render.argtypes = scene_args + [P(_abi.CameraC), C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    lib.hd_render.argtypes = scene_args + [C.c_uint32, P(_abi.CameraC), C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.hd_scatter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.hd_fastdiv_mismatches.argtypes, lib.hd_fastdiv_mismatches.restype = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32], C.c_uint64
     lib.hd_shard_visits.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, P(C.c_uint32)]
@@ -68,12 +68,12 @@ def hd_hit(hd, scene, rays, leaf_size=0, counters=None):
     return hits
 
 
-def hd_render(hd, scene, cam, spp, seed=0, max_depth=0):
+def hd_render(hd, scene, cam, spp, seed=0, max_depth=0, leaf_size=0):
     h, w = cam.img_height_pix, cam.img_width_pix
     hdr, rgb = np.empty((h, w, 3), np.float32), np.empty((h, w, 3), np.uint8)
     rays, nans = C.c_uint64(0), C.c_uint64(0)
     args, keep = scene_args(scene)
-    assert hd.hd_render(*args, cam.to_c(), spp, seed & (2 ** 64 - 1), max_depth, hdr.ctypes.data, rgb.ctypes.data, C.byref(rays), C.byref(nans)) == 0
+    assert hd.hd_render(*args, leaf_size, cam.to_c(), spp, seed & (2 ** 64 - 1), max_depth, hdr.ctypes.data, rgb.ctypes.data, C.byref(rays), C.byref(nans)) == 0
     return hdr, rgb, rays.value, nans.value
 
 
@@ -91,9 +91,10 @@ def test_golden_fixtures(hd, name):
     """The committed fixtures (oracle outputs; what the GPU tests compare with): hits of the stored rays, the complete render."""
     z, scene, cam = G.load(name)
     assert_hits(hd_hit(hd, scene, z["rays"]), z["hits"], name)
-    hdr, rgb, rays, _ = hd_render(hd, scene, cam, int(z["spp"]), int(z["seed"]))
-    assert np.array_equal(bits(hdr), bits(z["hdr"])), f"{name}: {int((bits(hdr) != bits(z['hdr'])).any(axis=2).sum())} pixels differ"
-    assert np.array_equal(rgb, z["rgb"]) and rays == int(z["n_rays_rendered"])
+    for leaf in (0, 1, 17):                                                             # brute force, BVH, voted BVH
+        hdr, rgb, rays, _ = hd_render(hd, scene, cam, int(z["spp"]), int(z["seed"]), 0, leaf)
+        assert np.array_equal(bits(hdr), bits(z["hdr"])), f"{name} leaf {leaf}: {int((bits(hdr) != bits(z['hdr'])).any(axis=2).sum())} pixels differ"
+        assert np.array_equal(rgb, z["rgb"]) and rays == int(z["n_rays_rendered"])
 
 
 def test_scene_hit_against_the_oracle(hd, oracle):
@@ -182,6 +183,10 @@ def test_renders_against_the_oracle(hd, oracle):
             assert np.array_equal(bits(hdr), bits(want)), (k, seed, depth, int((bits(hdr) != bits(want)).any(axis=2).sum()))
             assert rays == st["rays"] and nans == st.get("nan_rays", 0)
             assert np.array_equal(rgb, osc.render(cam.to_c(), spp, _abi.RenderOptsC(seed=seed, max_depth=depth)))
+            if scene.triangle_meshes and depth != 1:                                     # the same frame with every closest hit through the BVH traversals
+                for leaf in (1, 20):
+                    hdr_b, rgb_b, rays_b, _ = hd_render(hd, scene, cam, spp, seed, depth, leaf)
+                    assert np.array_equal(bits(hdr_b), bits(want)) and rays_b == rays, (k, seed, depth, leaf)
 
 
 def test_scatter_against_the_oracle(hd, oracle):
