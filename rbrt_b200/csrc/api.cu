@@ -508,6 +508,7 @@ static int render_host(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t
 
 int rbrt_gpu_render(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
                     uint8_t* rgb_out, rbrt_stats* stats) {
+    LOCK;                                                                 // (recursive: render_host takes it again; comm() is read under it)
     // non-root ranks of a collective render may pass NULL; the root must not
     if (!rgb_out && !(scene && reinterpret_cast<const Scene*>(scene)->collective && comm().rank != 0 && (!opts || opts->shard_count == 0))) {
         set_error("null rgb_out"); return RBRT_E_INVALID;
@@ -517,6 +518,7 @@ int rbrt_gpu_render(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t sp
 
 int rbrt_gpu_render_hdr(const rbrt_scene* scene, const rbrt_camera* cam, uint32_t spp, const rbrt_render_opts* opts,
                         float* hdr_out, rbrt_stats* stats) {
+    LOCK;
     static float dummy;                                                   // non-root ranks: "an HDR render", without a buffer
     const bool nonroot = scene && reinterpret_cast<const Scene*>(scene)->collective && comm().rank != 0 && (!opts || opts->shard_count == 0);
     if (!hdr_out && !nonroot) { set_error("null rgb_f32_out"); return RBRT_E_INVALID; }
