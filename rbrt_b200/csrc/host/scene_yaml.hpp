@@ -15,6 +15,8 @@
 //                `.nan`, or what Rust's f64::from_str takes and is finite); floats are rounded to f64 first and then to f32,
 //                integers straight to f32, as serde's `v as f32` does.  null / booleans / quoted scalars are type errors.
 //   String       any scalar, its text taken as written.
+//   tabs         as libyaml (serde_yaml's parser): never as indentation, not where a block value would start (`key:<tab>v`), fine after a value.
+//                (PyYAML, the Python host's parser, refuses a tab after a value too: the one known difference between the hosts.)
 // Every failure is the reference's panic: message on stderr, exit code 101.
 #pragma once
 #include <cmath>
@@ -144,6 +146,13 @@ class Parser {
         return std::string::npos;
     }
 
+    // libyaml (PyYAML, serde_yaml's unsafe-libyaml) does not skip a tab where a block-context token may start: `key:\tvalue` and `-\tvalue` are
+    // "found character that cannot start any token"
+    void no_tab_before_value(const std::string& t, size_t from) const {
+        size_t i = from;
+        while (i < t.size() && is_blank_ch(t[i])) { if (t[i] == '\t') fail("found character '\\t' that cannot start any token"); ++i; }
+    }
+
     NodeP block_node(int indent) {
         const std::string t = content(li_);
         if (starts_seq_item(t)) return block_seq(indent);
@@ -166,6 +175,7 @@ class Parser {
             std::string t = content(li_);
             if (ind > indent) fail("bad indentation of a sequence entry");
             if (!starts_seq_item(t)) break;                                  // (a sequence written at its key's indentation ends at the next key)
+            no_tab_before_value(strip_comment(lines_[li_]), (size_t)ind + 1);
             // the entry's content starts after "- ": treat it as a block that begins on this line, indented to that column
             std::string& raw = lines_[li_];
             raw[ind] = ' ';
@@ -195,6 +205,7 @@ class Parser {
             size_t used = 0;
             NodeP key = flow_scalar(strip(t.substr(0, c)), used, false);
             key->line = (int)li_ + 1;
+            no_tab_before_value(strip_comment(lines_[li_]), (size_t)ind + c + 1);      // (the raw line: `key:<tab>` at the end of a line is refused too)
             std::string rest = strip(t.substr(c + 1));
             ++li_;
             NodeP val;

@@ -149,8 +149,18 @@ def test_what_serde_refuses(tmp_path):
                  ok.replace("sphere_blueprints: []", "sphere_blueprints: [{radius: 1, center: [0, 0, 0]}]"),          # material_type missing
                  ok.replace("sphere_blueprints: []", "sphere_blueprints: [{radius: 1, center: [0, 0, 0], material_type: [metal]}]"),
                  ok.replace("sphere_blueprints: []", "sphere_blueprints: [[1, [0, 0, 0], metal]]"),                   # sequence form needs all five
+                 ok.replace("camera_focal_length_mm: 28.0", "camera_focal_length_mm:\t28.0"),                             # libyaml: a tab cannot start a token
+                 ok.replace("sphere_blueprints: []", "sphere_blueprints:\n-\tradius: 1"),
                  "", "# nothing\n", "just a scalar\n", "[1, 2\n", "{a: 1\n", "a: 'unterminated\n", "a: b: c\n", "a: *nowhere\n"):
         assert both(tmp_path, text) is None, text
+    for text in (ok.replace("\n", "\r\n"), ok.replace("\n", "   \n"), "\ufeff" + ok):
+        assert both(tmp_path, text) is not None, text                                   # CRLF, trailing blanks, a BOM
+    assert both(tmp_path, ok.replace("camera_blueprint:\n", "camera_blueprint:\t\n")) is None       # a tab where the value would start
+    # One known difference between the hosts: a tab AFTER a value (`28.0<tab>`, `}<tab># comment`).  libyaml — hence serde_yaml — skips it, and so does
+    # the CLI; PyYAML's pure-Python scanner never skips tabs and refuses the file.
+    p = tmp_path / "tab.yaml"
+    p.write_text(ok.replace("28.0\n", "28.0\t\n").replace("z: 4.0}", "z: 4.0}\t# tab before a comment"))
+    assert cli_dump(p)[0] is not None and py_dump(p)[0] is None
     # ... and what it takes that one might not expect: the sequence form of a whole blueprint, a numeric-looking material_type
     text = ok.replace("sphere_blueprints: []", "sphere_blueprints: [[1, [0, 0, 0], 42, ~, 0.5]]")
     assert "material_type 2:42\nalbedo None\nmaterial_param " + bits(0.5) in both(tmp_path, text)
